@@ -1,0 +1,222 @@
+/*
+ * lanefit_b200.h -- C ABI of the B200-native (sm_100a) hot path of
+ * wvangansbeke/LaneDetection_End2End.
+ *
+ * The reference is pure Python/PyTorch and has NO FFI of its own;
+ * the entry points below are what a binding for its hot path would bind.  Each
+ * one names the reference code it replaces (paths relative to the reference
+ * root, BP = Backprojection_Loss).  INTEGRATION.md shows the ctypes stub a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless noted; the caller owns all memory,
+ *     the library never allocates or frees user-visible buffers;
+ *   - every call is asynchronous on `stream` and never synchronises it;
+ *   - return value: 0 = LF_OK, negative = LF_ERR_* (argument / launch errors,
+ *     detected on the host before or at launch);
+ *   - numerical failures (singular normal equations) are reported through a
+ *     device-side `status` word the caller reads when it chooses to;
+ *   - feature maps are NHWC ("channels_last") fp32 unless a dtype argument says
+ *     otherwise; lane weight maps are planar [B, L, H, W].
+ */
+#ifndef LANEFIT_B200_H
+#define LANEFIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* lf_stream_t; /* == cudaStream_t */
+
+#define LF_OK 0
+#define LF_ERR_INVALID_ARGUMENT (-1)
+#define LF_ERR_UNSUPPORTED (-2)
+#define LF_ERR_WORKSPACE_TOO_SMALL (-3)
+#define LF_ERR_CUDA (-4)
+
+/* element types */
+#define LF_F32 0
+#define LF_BF16 1
+
+/* activation applied to the decoder output before the fit (BP/Networks/LSQ_layer.py:27-47) */
+#define LF_ACT_NONE 0
+#define LF_ACT_SQUARE 1
+#define LF_ACT_ABS 2
+#define LF_ACT_RELU 3
+#define LF_ACT_SIGMOID 4
+#define LF_ACT_SOFTPLUS 5
+
+/* normal-equation solver (BP/Networks/LSQ_layer.py:112-118) */
+#define LF_SOLVER_INVERSE 0  /* torch.inverse + bmm  (:114-116): LU, partial pivoting  */
+#define LF_SOLVER_CHOLESKY 1 /* GELS                 (BP/Networks/gels.py:11-15)       */
+
+/* bits of the device status word written by lf_lsq_fwd */
+#define LF_STATUS_SINGULAR 1    /* zero pivot: torch.inverse would raise (BP/main.py:289-292) */
+#define LF_STATUS_NONFINITE 2   /* NaN/Inf in the moments or in beta                         */
+#define LF_STATUS_NOT_POSDEF 4  /* Cholesky pivot <= 0: torch.cholesky would raise           */
+
+#define LF_MAX_ORDER 4
+
+int lf_version(void);
+const char* lf_error_string(int code);
+/* last CUDA error string seen by the library on this thread (host pointer) */
+const char* lf_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * Weighted least-squares layer, forward.
+ * Replaces, fused into one launch: square_tensor / activation_layer
+ * (BP/Networks/LSQ_layer.py:19-20,27-47,295), the row mask index_fill (:237-238,301)
+ * and Weighted_least_squares.forward (:85-154), incl. the GELS variant
+ * (BP/Networks/gels.py:11-15); BEV variant: Birds_Eye_View_Loss/Networks/LSQ_layer.py:90-167.
+ *
+ *   o        [B,L,H,W]  raw decoder output (o_dtype LF_F32 | LF_BF16)
+ *   xtab     [H*W] f32  grid[:,0]                      (BEV x coordinate of every pixel)
+ *   ytab     [H*W] f32  const - grid[:,1]              (:94, const = 255 BP / 1 BEV)
+ *   yrow     [H]   f32  ytab of each row if ytab is constant along rows (true for every
+ *                       homography the reference builds), else NULL -> general kernel
+ *   mask_rows           rows [0,mask_rows) get weight zero and are never read
+ *   beta     [B,L,order+1] f64 out, highest power first (:100-104)
+ *   zinv     [B,L,(order+1)^2] f64 out: (Y^T W^2 Y + reg I)^-1, consumed by lf_lsq_bwd
+ *   masked   [B,L,H,W] f32 out or NULL: activation(o) with masked rows zeroed (output #5
+ *            of Net.forward, :315)
+ *   status   int32 out: OR of LF_STATUS_* over all B*L systems (caller zeroes it)
+ *   workspace: lf_lsq_workspace_bytes() bytes, ZEROED once before first use; the
+ *            library leaves it reusable (tickets reset) after every launch.
+ * ------------------------------------------------------------------------- */
+size_t lf_lsq_workspace_bytes(int B, int L, int H, int W, int order);
+int lf_lsq_fwd(const void* o, int o_dtype, const float* xtab, const float* ytab, const float* yrow,
+               int B, int L, int H, int W, int order, int mask_rows, int act, double reg_ls, int solver,
+               double* beta, double* zinv, float* masked, int* status,
+               void* workspace, size_t workspace_bytes, lf_stream_t stream);
+
+/* Backward of the above: d_o = dL/d o given gbeta = dL/d beta [B,L,order+1] f64.
+ * Replaces autograd through mul/bmm/inverse (BP/Networks/LSQ_layer.py:111-116) ==
+ * GELS.backward (BP/Networks/gels.py:18-25) composed with the activation and mask:
+ *   z = Z^-1 g ;  d_o = mask * act'(o) * 2 act(o) * (x - phi^T beta) * (phi^T z).
+ * d_o has the dtype of o. */
+int lf_lsq_bwd(const void* o, int o_dtype, const float* xtab, const float* ytab, const float* yrow,
+               int B, int L, int H, int W, int order, int mask_rows, int act,
+               const double* beta, const double* zinv, const double* gbeta,
+               void* d_o, lf_stream_t stream);
+
+/* ========================================================================= *
+ * ERFNet encoder/decoder building blocks (BP/Networks/ERFNet.py:11-176).
+ * Feature maps are NHWC fp32: element (n,y,x,c) at ((n*H+y)*W+x)*cstride + coff + c.
+ * The reference modules are assembled from these calls by
+ * lanedetection_end2end_b200/ops_net.py (one autograd Function per reference block).
+ * ========================================================================= */
+#define LF_MAX_TAPS 9
+
+/* Generic implicit-GEMM convolution, one output phase per call:
+ *   out[n, j*osy+oy0, i*osx+ox0, out_coff+co] =
+ *     epi( sum_t sum_ci in[n, j*isy+dy[t], i*isx+dx[t], ci] * wmat[(wtap[t]*Cin+ci)*CoutPad + co] )
+ * for n<N, j<Hs, i<Ws, co<Cout, zero outside the input.  Covers Conv2d forward (any stride,
+ * padding, dilation: ERFNet.py:15,29-37), ConvTranspose2d forward as 4 phases (:101), and both
+ * input gradients.  epi: +bias, ReLU, *(mask_src>0), +add_src*(add_mask>0); mask/add tensors
+ * share the output layout. */
+typedef struct LfConvArgs {
+    const float* in;
+    const float* wmat;      /* [ntap_slots][Cin][CoutPad] packed GEMM weights */
+    const float* bias;      /* [Cout] or NULL */
+    float* out;
+    const float* mask_src;  /* NULL or forward activation whose sign gates the result */
+    const float* add_src;   /* NULL or tensor added to the result ... */
+    const float* add_mask;  /* ... gated by (add_mask > 0) when non-NULL */
+    int N, Hin, Win, Cin, in_cstride;
+    int Hout, Wout, out_cstride, out_coff, Cout, CoutPad;
+    int Hs, Ws, osy, osx, oy0, ox0, isy, isx;
+    int ntaps;
+    int dy[LF_MAX_TAPS], dx[LF_MAX_TAPS], wtap[LF_MAX_TAPS];
+    int relu;
+} LfConvArgs;
+int lf_conv_f32(const LfConvArgs* args, lf_stream_t stream);
+
+/* Weight gradient as a split-K GEMM over pixels:
+ *   partial[s][t][cp][cq] = sum_{(n,j,i) in split s} P[n, j*psy+pdy[t], i*psx+pdx[t], cp]
+ *                                                  * Q[n, j*qsy+qdy[t], i*qsx+qdx[t], cq]
+ * Conv2d: P = layer input (gathered), Q = output gradient (dense); ConvTranspose2d: P = layer
+ * input (dense), Q = output gradient (gathered).  qsum_partial (optional) receives the column
+ * sums of Q over the domain (bias gradient when Q is dense).  lf_wgrad_reduce sums the splits in
+ * fixed order into dst[t*st + cp*sp + cq*sq] (any weight layout). */
+typedef struct LfWgradArgs {
+    const float* P;
+    const float* Q;
+    float* partial;       /* [nsplit][ntaps][CpPad][CqPad] */
+    float* qsum_partial;  /* [nsplit][CqPad] or NULL */
+    int N, Hs, Ws;
+    int Hp, Wp, Cp, p_cstride, p_coff, psy, psx;
+    int Hq, Wq, Cq, q_cstride, q_coff, qsy, qsx;
+    int ntaps;
+    int pdy[LF_MAX_TAPS], pdx[LF_MAX_TAPS], qdy[LF_MAX_TAPS], qdx[LF_MAX_TAPS];
+    int CpPad, CqPad; /* multiples of 64 */
+    int nsplit;
+} LfWgradArgs;
+int lf_wgrad_f32(const LfWgradArgs* args, lf_stream_t stream);
+int lf_wgrad_reduce(const float* partial, int nsplit, int ntaps, int Cp, int Cq, int CpPad, int CqPad,
+                    float* dst, int st, int sp, int sq, lf_stream_t stream);
+/* dst[c] = sum over splits of partial[s][c]  (bias gradients) */
+int lf_vec_reduce(const float* partial, int nsplit, int C, int Cpad, float* dst, lf_stream_t stream);
+/* partial[blk][c] = sum over a pixel range of src[pix*cstride + coff + c]; nblk returned by the query */
+int lf_colsum_blocks(long long npix);
+int lf_colsum(const float* src, long long npix, int C, int cstride, int coff, float* partial, int Cpad,
+              lf_stream_t stream);
+
+/* 2x2/stride-2 max pooling into a channel slice (DownsamplerBlock, ERFNet.py:16,20) and its
+ * gradient (first maximum wins, like ATen); accumulate != 0 adds into d_in. */
+int lf_maxpool2_fwd(const float* in, int N, int Hin, int Win, int C, int in_cstride, float* out,
+                    int out_cstride, int out_coff, lf_stream_t stream);
+int lf_maxpool2_bwd(const float* in, int N, int Hin, int Win, int C, int in_cstride, const float* d_out,
+                    int out_cstride, int out_coff, float* d_in, int din_cstride, int accumulate,
+                    lf_stream_t stream);
+
+/* BatchNorm2d, training mode, eps as given (1e-3 in ERFNet.py:17,33,39,102), dense [npix][C].
+ *  stats   : per-block fp64 partial sums of x and x^2      -> partial[nblk][2][C]
+ *  finalize: mean, invstd, scale = gamma*invstd, shift = beta - mean*scale; running stats
+ *            updated with `momentum` (unbiased variance) when running_mean != NULL
+ *  apply   : y = relu?( (x*scale+shift) * drop[n][c]? + res? )
+ *  bwd     : g = dy * (ymask>0)? * drop? ;  s1 = sum g, s2 = sum g*xhat  (dgamma = s2, dbeta = s1)
+ *            dx = scale * (g - s1/npix - xhat*s2/npix)                                        */
+int lf_bn_blocks(long long npix, int C);
+int lf_bn_stats(const float* x, long long npix, int C, double* partial, lf_stream_t stream);
+int lf_bn_finalize(const double* partial, int nblk, long long npix, int C, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                   float* mean, float* invstd, float* scale, float* shift, lf_stream_t stream);
+int lf_bn_eval_prepare(int C, const float* gamma, const float* beta, float eps, const float* running_mean,
+                       const float* running_var, float* scale, float* shift, lf_stream_t stream);
+int lf_bn_apply(const float* x, long long npix, int C, int pix_per_image, const float* scale,
+                const float* shift, const float* drop, const float* res, int relu, float* y,
+                lf_stream_t stream);
+int lf_bn_bwd_reduce(const float* dy, const float* ymask, const float* drop, const float* x, long long npix,
+                     int C, int pix_per_image, const float* mean, const float* invstd, double* partial,
+                     lf_stream_t stream);
+int lf_bn_bwd_finalize(const double* partial, int nblk, long long npix, int C, float* dgamma, float* dbeta,
+                       float* c1, float* c2, lf_stream_t stream);
+int lf_bn_bwd_apply(const float* dy, const float* ymask, const float* drop, const float* x, long long npix,
+                    int C, int pix_per_image, const float* mean, const float* invstd, const float* gamma,
+                    const float* c1, const float* c2, float* dx, lf_stream_t stream);
+
+/* Decoder.output_conv: ConvTranspose2d(16 -> L, 2, stride 2) (ERFNet.py:124,152).
+ * x NHWC [N,H,W,Cin] -> out planar [N,L,2H,2W] (the layout the LSQ layer reads).
+ * w is the reference layout [Cin][L][2][2]. */
+int lf_outconv_fwd(const float* x, const float* w, const float* bias, int N, int H, int W, int Cin, int L,
+                   float* out, lf_stream_t stream);
+int lf_outconv_bwd_data(const float* d_out, const float* w, int N, int H, int W, int Cin, int L, float* d_x,
+                        lf_stream_t stream);
+int lf_outconv_wgrad_blocks(long long npix);
+/* partial[blk][Cin*L*4 + L]: weight gradient (reference layout) then bias gradient */
+int lf_outconv_bwd_weight(const float* x, const float* d_out, int N, int H, int W, int Cin, int L,
+                          float* partial, lf_stream_t stream);
+
+/* NCHW fp32 image [N,C,H,W] -> NHWC padded to Cpad channels (zeros), the stem's input layout */
+int lf_nchw_to_nhwc_pad(const float* in, int N, int C, int H, int W, int Cpad, float* out, lf_stream_t stream);
+/* NHWC [N,H,W,C] <-> NCHW [N,C,H,W] (module-boundary layout changes) */
+int lf_nhwc_to_nchw(const float* in, int N, int H, int W, int C, float* out, lf_stream_t stream);
+int lf_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out, lf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANEFIT_B200_H */

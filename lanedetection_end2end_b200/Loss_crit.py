@@ -1,0 +1,126 @@
+"""Losses that consume the curve coefficients beta -- host-side mirror of the
+reference's ``Loss_crit.py`` (BP/Loss_crit.py; BEV: Birds_Eye_View_Loss/Loss_crit.py).
+
+  define_loss_crit      BP/Loss_crit.py:47-67
+  backprojection_loss   :161-218   (float64; supplies dL/dbeta to the fused LSQ backward)
+  Area_Loss             :87-143    (closed-form weighted area between curves)
+  MSE_Loss              :146-159
+The arithmetic here is O(B*56) float64 -- launch-latency, not bandwidth; fusing it into
+the LSQ kernels' epilogue/prologue is SURVEY.md 8f rank 1 ("next").
+"""
+import torch
+import torch.nn as nn
+
+if __package__:                        # imported as lanedetection_end2end_b200.Loss_crit
+    from .Networks.utils import get_homography
+else:                                  # imported as top-level `Loss_crit` by the reference's main.py
+    from Networks.utils import get_homography
+
+
+def define_loss_crit(options):
+    if options.loss_policy == "mse":
+        loss_crit = MSE_Loss(options)
+    elif options.loss_policy == "backproject":
+        loss_crit = backprojection_loss(options)
+    elif options.loss_policy == "area":
+        loss_crit = Area_Loss(options.order, options.weight_funct)
+    elif options.loss_policy == "homography_mse":
+        # referenced but never defined by the reference (BP/Loss_crit.py:56-57 -> NameError)
+        raise NameError("name 'Homography_MSE_Loss' is not defined")
+    else:
+        return NotImplementedError("The requested loss criterion is not implemented")
+    weights = torch.Tensor([1] + [options.weight_seg] * options.nclasses)
+    if not getattr(options, "no_cuda", False) or torch.cuda.is_available():
+        weights = weights.cuda()       # the reference moves them unconditionally (:64)
+    return loss_crit, nn.CrossEntropyLoss(weights)
+
+
+def _design(y, order):
+    return torch.stack([y ** k for k in range(order, 0, -1)] + [torch.ones_like(y)], 1)
+
+
+class backprojection_loss(nn.Module):
+    """Sample the fitted curve at the 56 TuSimple rows in BEV space, project the samples
+    back into the image with M^-1 and take the masked mean squared x-error (float64).
+
+    forward(params [B,order+1,1] f64, x_gt [B,56] f64, valid [B,56] f64) -> (loss, x_cal*valid)
+    """
+
+    def __init__(self, options):
+        super().__init__()
+        if options.order > 3:
+            raise NotImplementedError(
+                "Requested order {} for polynomial fit is not implemented".format(options.order))
+        M, M_inv = get_homography(options.resize, options.no_mapping)
+        self.M, self.M_inv = torch.from_numpy(M).double(), torch.from_numpy(M_inv).double()
+        y_d = (torch.arange(160, 720, 10) - 80).double() / 2.5          # image rows of the h_samples (:173)
+        self.y_prime = (self.M[1, 1] * y_d + self.M[1, 2]) / (self.M[2, 1] * y_d + self.M[2, 2])
+        self.Y = _design(255 - self.y_prime, options.order)            # [56, order+1]  (:176-188)
+        self._dev = None
+
+    def _to(self, device):
+        if self._dev != device:
+            self.M, self.M_inv = self.M.to(device), self.M_inv.to(device)
+            self.y_prime, self.Y = self.y_prime.to(device), self.Y.to(device)
+            self._dev = device
+
+    def forward(self, params, x_gt, valid_samples):
+        self._to(params.device)
+        p = params.reshape(params.size(0), -1).double()
+        x_prime = p @ self.Y.t()                                        # [B,56]   (:205)
+        Mi, yp = self.M_inv, self.y_prime
+        num = Mi[0, 0] * x_prime + (Mi[0, 1] * yp + Mi[0, 2])           # M^-1 [x', y', 1]^T  (:208-210)
+        den = Mi[2, 0] * x_prime + (Mi[2, 1] * yp + Mi[2, 2])
+        x_cal = num / den
+        x_err = (x_gt - x_cal) * valid_samples                          # (:214)
+        nvalid = valid_samples.sum()
+        loss = torch.sum(x_err ** 2) / nvalid                           # (:215)
+        if nvalid == 0:
+            loss = 0
+        return loss, x_cal * valid_samples
+
+
+class Area_Loss(nn.Module):
+    """int_0^0.7 W(y) (delta_a y^2 + delta_b y + delta_c)^2 dy with W in {1, 1-y, 1-sqrt(y)},
+    averaged over the lanes whose ground-truth parameters are all non-zero (:98-143)."""
+
+    def __init__(self, order, weight_funct):
+        super().__init__()
+        self.order = order
+        self.weight_funct = weight_funct
+
+    def forward(self, params, gt_params, compute=True):
+        diff = params.squeeze(-1) - gt_params
+        a, b = diff[:, 0], diff[:, 1]
+        t = 0.7
+        if self.order == 2:
+            c = diff[:, 2]
+            if self.weight_funct == "none":
+                loss_fit = a * a * t ** 5 / 5 + a * b * t ** 4 / 2 + (b * b + 2 * a * c) * t ** 3 / 3 \
+                    + b * c * t ** 2 + c * c * t
+            elif self.weight_funct == "linear":
+                loss_fit = c * c * t - t ** 5 * (2 * a * b / 5 - a * a / 5) + t ** 2 * (b * c - c * c / 2) \
+                    - a * a * t ** 6 / 6 - t ** 4 * (b * b / 4 - a * b / 2 + a * c / 2) \
+                    + t ** 3 * (b * b / 3 - 2 * c * b / 3 + 2 * a * c / 3)
+            elif self.weight_funct == "quadratic":
+                loss_fit = t ** 3 * (b * b / 3 + 2 * a * c / 3) - t ** 3.5 * (2 * b * b / 7 + 4 * a * c / 7) \
+                    + c * c * t + 0.2 * a * a * t ** 5 - 2 / 11 * a * a * t ** 5.5 - 2 / 3 * c * c * t ** 1.5 \
+                    + 0.5 * a * b * t ** 4 - 4 / 9 * a * b * t ** 4.5 + b * c * t ** 2 - 0.8 * b * c * t ** 2.5
+            else:
+                return NotImplementedError("The requested weight function is not implemented")
+        elif self.order == 1:
+            loss_fit = b * b * t + a * b * t ** 2 + a * a * t ** 3 / 3
+        else:
+            return NotImplementedError("The requested order is not implemented")
+        present = (gt_params != 0).all(1)        # bool restatement of the .byte() mask (:140-141)
+        sel = loss_fit[present]
+        return sel.mean(0) if sel.numel() != 0 else 0
+
+
+class MSE_Loss(nn.Module):
+    def __init__(self, options):
+        super().__init__()
+        self.loss_crit = nn.MSELoss()
+
+    def forward(self, params, gt_params, compute=True):
+        return self.loss_crit(params.squeeze(-1), gt_params)

@@ -1,0 +1,189 @@
+"""Host-side mirror of the reference's ``Networks/ERFNet.py`` (BP/Networks/ERFNet.py:11-176):
+same class names, constructor arguments, sub-module / parameter names (so ``state_dict``s
+and ``define_init_weights`` work unchanged) and forward signatures.  The ``nn.Conv2d`` /
+``nn.BatchNorm2d`` / ``nn.ConvTranspose2d`` children are PARAMETER CONTAINERS only -- their
+own forward is never called; every block runs as one autograd Function over the sm_100a
+kernels (ops_net.py).  Feature maps travel between blocks as NHWC memory viewed with the
+reference's NCHW shape (channels_last), so chaining blocks costs no layout change.
+"""
+import torch
+import torch.nn as nn
+
+from ._pkg import submodule
+
+_ops = submodule("ops_net")
+
+
+def _track(bn, training):
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+
+
+class DownsamplerBlock(nn.Module):
+    """relu(bn(cat[conv3x3 stride 2 (x), maxpool2x2 (x)]))  (reference :11-22)."""
+
+    def __init__(self, ninput, noutput):
+        super().__init__()
+        self.conv = nn.Conv2d(ninput, noutput - ninput, (3, 3), stride=2, padding=1, bias=True)
+        self.pool = nn.MaxPool2d(2, stride=2)
+        self.bn = nn.BatchNorm2d(noutput, eps=1e-3)
+        self.ninput = ninput
+
+    def forward(self, input):
+        need_dx = input.requires_grad and torch.is_grad_enabled()
+        if self.ninput % 4 != 0:
+            if need_dx:
+                raise NotImplementedError("input gradient of a DownsamplerBlock with %d input channels" % self.ninput)
+            x = _ops.image_to_nhwc_pad(input, (self.ninput + 3) // 4 * 4)
+        else:
+            x = _ops.as_nhwc(input)
+        y = _ops.DownFunction.apply(x, self.ninput, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias,
+                                    self.bn.running_mean, self.bn.running_var, self.training, need_dx)
+        _track(self.bn, self.training)
+        return _ops.as_nchw_view(y)
+
+
+class non_bottleneck_1d(nn.Module):
+    """Factorised residual block: 3x1 -> relu -> 1x3 -> bn -> relu -> 3x1(d) -> relu -> 1x3(d) -> bn ->
+    dropout2d -> (+x) -> relu  (reference :25-60)."""
+
+    def __init__(self, chann, dropprob, dilated):
+        super().__init__()
+        self.conv3x1_1 = nn.Conv2d(chann, chann, (3, 1), stride=1, padding=(1, 0), bias=True)
+        self.conv1x3_1 = nn.Conv2d(chann, chann, (1, 3), stride=1, padding=(0, 1), bias=True)
+        self.bn1 = nn.BatchNorm2d(chann, eps=1e-03)
+        self.conv3x1_2 = nn.Conv2d(chann, chann, (3, 1), stride=1, padding=(1 * dilated, 0), bias=True,
+                                   dilation=(dilated, 1))
+        self.conv1x3_2 = nn.Conv2d(chann, chann, (1, 3), stride=1, padding=(0, 1 * dilated), bias=True,
+                                   dilation=(1, dilated))
+        self.bn2 = nn.BatchNorm2d(chann, eps=1e-03)
+        self.dropout = nn.Dropout2d(dropprob)
+        self.dilated = dilated
+        self.drop_mask_override = None      # tests inject a fixed [N,C] mask here
+
+    def _drop_mask(self, x):
+        if self.drop_mask_override is not None:
+            return self.drop_mask_override.to(device=x.device, dtype=torch.float32).contiguous()
+        p = self.dropout.p
+        if not self.training or p == 0:
+            return None
+        N, _, _, C = x.shape
+        keep = (torch.rand(N, C, device=x.device) >= p).float()      # Dropout2d: whole channels (:41,57-58)
+        return (keep / (1.0 - p)).contiguous()
+
+    def forward(self, input):
+        x = _ops.as_nhwc(input)
+        y = _ops.Nb1dFunction.apply(
+            x, self.conv3x1_1.weight, self.conv3x1_1.bias, self.conv1x3_1.weight, self.conv1x3_1.bias,
+            self.bn1.weight, self.bn1.bias, self.conv3x1_2.weight, self.conv3x1_2.bias,
+            self.conv1x3_2.weight, self.conv1x3_2.bias, self.bn2.weight, self.bn2.bias,
+            self.bn1.running_mean, self.bn1.running_var, self.bn2.running_mean, self.bn2.running_var,
+            self.dilated, self._drop_mask(x), self.training)
+        _track(self.bn1, self.training)
+        _track(self.bn2, self.training)
+        return _ops.as_nchw_view(y)
+
+
+class Encoder(nn.Module):
+    def __init__(self, in_channels, num_classes):
+        super().__init__()
+        self.initial_block = DownsamplerBlock(in_channels, 16)
+        self.layers = nn.ModuleList()
+        self.layers.append(DownsamplerBlock(16, 64))
+        for _ in range(5):
+            self.layers.append(non_bottleneck_1d(64, 0.03, 1))
+        self.layers.append(DownsamplerBlock(64, 128))
+        for _ in range(2):
+            for d in (2, 4, 8, 16):
+                self.layers.append(non_bottleneck_1d(128, 0.3, d))
+        # only used in encoder-only mode (reference :84,92-93); a 1x1 conv on 128 channels
+        self.output_conv = nn.Conv2d(128, num_classes, 1, stride=1, padding=0, bias=True)
+
+    def forward(self, input, predict=False):
+        output = self.initial_block(input)
+        for layer in self.layers:
+            output = layer(output)
+        if predict:
+            # encoder-only pretraining head: not on the end-to-end hot path
+            output = torch.nn.functional.conv2d(output, self.output_conv.weight, self.output_conv.bias)
+        return output
+
+
+class UpsamplerBlock(nn.Module):
+    """relu(bn(convT3x3 stride 2 (x)))  (reference :98-107)."""
+
+    def __init__(self, ninput, noutput):
+        super().__init__()
+        self.conv = nn.ConvTranspose2d(ninput, noutput, 3, stride=2, padding=1, output_padding=1, bias=True)
+        self.bn = nn.BatchNorm2d(noutput, eps=1e-3)
+
+    def forward(self, input):
+        x = _ops.as_nhwc(input)
+        y = _ops.UpFunction.apply(x, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias,
+                                  self.bn.running_mean, self.bn.running_var, self.training)
+        _track(self.bn, self.training)
+        return _ops.as_nchw_view(y)
+
+
+class _OutputConvT(nn.ConvTranspose2d):
+    """ConvTranspose2d(16 -> L, 2, stride 2) emitting planar NCHW maps (reference :124,152)."""
+
+    def forward(self, input):
+        return _ops.OutConvFunction.apply(_ops.as_nhwc(input), self.weight, self.bias)
+
+
+class Decoder(nn.Module):
+    def __init__(self, num_classes, pretrain, do_segmentation=False):
+        super().__init__()
+        self.pretrain = pretrain
+        self.layers = nn.ModuleList()
+        self.layers.append(UpsamplerBlock(128, 64))
+        self.layers.append(non_bottleneck_1d(64, 0, 1))
+        self.layers.append(non_bottleneck_1d(64, 0, 1))
+        self.layers.append(UpsamplerBlock(64, 16))
+        self.layers.append(non_bottleneck_1d(16, 0, 1))
+        self.layers.append(non_bottleneck_1d(16, 0, 1))
+        self.output_conv = _OutputConvT(16, num_classes, 2, stride=2, padding=0, output_padding=0, bias=True)
+        if pretrain:
+            self.output_conv2 = _OutputConvT(16, num_classes + 1, 2, stride=2, padding=0, output_padding=0, bias=True)
+        self.do_segmentation = do_segmentation
+        if do_segmentation:
+            self.layers1 = nn.ModuleList()
+            self.layers1.append(UpsamplerBlock(128, 64))
+            self.layers1.append(non_bottleneck_1d(64, 0, 1))
+            self.layers1.append(non_bottleneck_1d(64, 0, 1))
+            self.layers1.append(UpsamplerBlock(64, 16))
+            self.layers1.append(non_bottleneck_1d(16, 0, 1))
+            self.layers1.append(non_bottleneck_1d(16, 0, 1))
+            self.layers1.append(_OutputConvT(16, num_classes + 1, 2, stride=2, padding=0, output_padding=0, bias=True))
+
+    def forward(self, input, flag):
+        output = input
+        output_seg = input
+        for layer in self.layers:
+            output = layer(output)
+        if self.pretrain and not flag:
+            output = self.output_conv2(output)
+        else:
+            output = self.output_conv(output)
+        if self.do_segmentation:
+            for layer1 in self.layers1:
+                output_seg = layer1(output_seg)
+        return output, output_seg
+
+
+class Net(nn.Module):
+    """ERFNet.  forward(input, flag, only_encode=False) -> (encoder_output, decoder_output, output_seg)
+    (reference :164-176; the BEV variant returns the first two only, see ERFNet_bev)."""
+
+    def __init__(self, layers=18, in_channels=1, out_channels=1, pretrained=False, pool=False):
+        super().__init__()
+        self.encoder = Encoder(in_channels, out_channels)
+        self.decoder = Decoder(out_channels, pretrained)
+
+    def forward(self, input, flag, only_encode=False):
+        if only_encode:
+            return self.encoder.forward(input, predict=True)
+        encoder_output = self.encoder(input)
+        decoder_output, output_seg = self.decoder.forward(encoder_output, flag)
+        return encoder_output, decoder_output, output_seg

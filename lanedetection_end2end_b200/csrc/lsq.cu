@@ -1,0 +1,615 @@
+// Fused weighted least-squares layer for sm_100a:  activation -> row mask ->
+// moments of (m*a(o))^2 over the BEV meshgrid -> (order+1)x(order+1) solve, and its
+// closed-form backward.  Replaces BP/Networks/LSQ_layer.py:19-20,27-47,85-154,237-238,
+// 295,301 and BP/Networks/gels.py:9-25 of the reference (see include/lanefit_b200.h).
+//
+// Design (DESIGN.md section "K5/K6"):
+//  * HBM-bound: each map element is read exactly once (fwd) / read once + written once
+//    (bwd); masked rows are never read.
+//  * Row-separable fast path: for every homography the reference builds, y depends on
+//    the row only, so  S_k = sum_r y_r^k A_r,  T_k = sum_r y_r^k B_r  with
+//    A_r = sum_c w^2, B_r = sum_c w^2 x.  Per pixel only 2 fp32 accumulations; the
+//    3d+2 moments are accumulated in fp64 once per row by one lane each ("lane k owns
+//    moment k"), which keeps the kernel far from the fp64 pipe limit.
+//  * x table reads (L2-resident, batch-invariant) are amortised over the lanes of an
+//    image: one CTA handles (row chunk, image, up to 4 lanes).
+//  * Cross-CTA reduction is deterministic: per-chunk partials in a workspace, the last
+//    CTA to arrive (ticket atomic) sums them in fixed order and one thread per system
+//    solves it in fp64 registers (LU with partial pivoting == torch.inverse, or
+//    Cholesky == GELS).  No cuBLAS/cuSOLVER batched call, no host sync.
+#include "lf_common.cuh"
+
+namespace lf {
+
+constexpr int LSQ_THREADS = 256;
+constexpr int LSQ_WARPS = LSQ_THREADS / 32;
+constexpr int LSQ_MAXL = 4;    // lanes handled by one CTA
+constexpr int LSQ_MAXNM = 16;  // >= 3*LF_MAX_ORDER+2 = 14
+constexpr int LSQ_ACT_RUNTIME = -1;
+
+struct LsqArgs {
+    const void* o;
+    const float* xtab;
+    const float* ytab;
+    const float* yrow;
+    int B, L, H, W, order, mask_rows, act, solver, rows_per_cta, nchunks;
+    double reg_ls;
+    double* beta;
+    double* zinv;
+    float* masked;
+    int* status;
+    double* partials;
+    int* tickets;
+    // backward only
+    const double* gbeta;
+    void* d_o;
+};
+
+// ---------------------------------------------------------------------------------
+// activation and its derivative (BP/Networks/LSQ_layer.py:27-47)
+// ---------------------------------------------------------------------------------
+template <int ACT_T>
+__device__ __forceinline__ float act_fn(float o, int act_rt) {
+    const int act = (ACT_T == LSQ_ACT_RUNTIME) ? act_rt : ACT_T;
+    switch (act) {
+        case LF_ACT_SQUARE: return o * o;
+        case LF_ACT_ABS: return fabsf(o);
+        case LF_ACT_RELU: return fmaxf(o, 0.f);
+        case LF_ACT_SIGMOID: return 1.f / (1.f + expf(-o));
+        case LF_ACT_SOFTPLUS: return (o > 20.f) ? o : log1pf(expf(o));  // nn.Softplus threshold 20
+        default: return o;
+    }
+}
+// returns act'(o) * act(o)  (the product the backward needs), given a = act(o)
+template <int ACT_T>
+__device__ __forceinline__ float dact_times_act(float o, int act_rt) {
+    const int act = (ACT_T == LSQ_ACT_RUNTIME) ? act_rt : ACT_T;
+    switch (act) {
+        case LF_ACT_SQUARE: return 2.f * o * o * o;
+        case LF_ACT_ABS: return o;  // sign(o)*|o|
+        case LF_ACT_RELU: return fmaxf(o, 0.f);
+        case LF_ACT_SIGMOID: {
+            float s = 1.f / (1.f + expf(-o));
+            return s * (1.f - s) * s;
+        }
+        case LF_ACT_SOFTPLUS: {
+            if (o > 20.f) return o;
+            float e = expf(o);
+            return (e / (1.f + e)) * log1pf(e);
+        }
+        default: return o;
+    }
+}
+
+template <bool BF16>
+__device__ __forceinline__ float4 load_map4(const void* base, size_t elem_off) {
+    if (BF16) {
+        const uint2* p = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off);
+        return bf16x4_to_f4(ld_stream_u2(p));
+    } else {
+        return ld_stream_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off));
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ float load_map1(const void* base, size_t elem_off) {
+    if (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[elem_off]);
+    return reinterpret_cast<const float*>(base)[elem_off];
+}
+template <bool BF16>
+__device__ __forceinline__ void store_map4(void* base, size_t elem_off, float4 v) {
+    if (BF16) {
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = f4_to_bf16x4(v);
+    } else {
+        st_stream_f4(reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off), v);
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ void store_map1(void* base, size_t elem_off, float v) {
+    if (BF16)
+        reinterpret_cast<__nv_bfloat16*>(base)[elem_off] = __float2bfloat16(v);
+    else
+        reinterpret_cast<float*>(base)[elem_off] = v;
+}
+
+// ---------------------------------------------------------------------------------
+// (order+1)x(order+1) solve in fp64, one thread per system.
+//   Z_ij = S_{2d-i-j} + lambda*delta_ij,  X_i = T_{d-i}   
+// ---------------------------------------------------------------------------------
+template <int N>
+__device__ int lsq_solve(const double* S, const double* T, double lambda, int solver, double* beta, double* zinv) {
+    constexpr int d = N - 1;
+    double Z[N][N], Inv[N][N], X[N];
+    int st = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            Z[i][j] = S[2 * d - i - j] + (i == j ? lambda : 0.0);
+            Inv[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+        X[i] = T[d - i];
+    }
+    for (int k = 0; k <= 2 * d; ++k)
+        if (!isfinite(S[k])) st |= LF_STATUS_NONFINITE;
+    for (int k = 0; k <= d; ++k)
+        if (!isfinite(T[k])) st |= LF_STATUS_NONFINITE;
+
+    if (solver == LF_SOLVER_CHOLESKY) {
+        // Z = U^T U (upper), as torch.cholesky(., upper=True) in gels.py:12
+        double U[N][N];
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) U[i][j] = 0.0;
+        for (int j = 0; j < N; ++j) {
+            double s = Z[j][j];
+            for (int k = 0; k < j; ++k) s -= U[k][j] * U[k][j];
+            if (!(s > 0.0)) {
+                st |= LF_STATUS_NOT_POSDEF;
+                s = 1.0;
+            }
+            const double ujj = sqrt(s);
+            U[j][j] = ujj;
+            for (int i = j + 1; i < N; ++i) {
+                double v = Z[j][i];
+                for (int k = 0; k < j; ++k) v -= U[k][j] * U[k][i];
+                U[j][i] = v / ujj;
+            }
+        }
+        // Inv = (U^T U)^-1 : solve U^T y = e_c, U x = y for every column c
+        for (int c = 0; c < N; ++c) {
+            double yv[N];
+            for (int i = 0; i < N; ++i) {
+                double v = (i == c) ? 1.0 : 0.0;
+                for (int k = 0; k < i; ++k) v -= U[k][i] * yv[k];
+                yv[i] = v / U[i][i];
+            }
+            for (int i = N - 1; i >= 0; --i) {
+                double v = yv[i];
+                for (int k = i + 1; k < N; ++k) v -= U[i][k] * Inv[k][c];
+                Inv[i][c] = v / U[i][i];
+            }
+        }
+    } else {
+        // Gauss-Jordan with partial pivoting on [Z | I]  (torch.inverse, LSQ_layer.py:114)
+        for (int col = 0; col < N; ++col) {
+            int piv = col;
+            double best = fabs(Z[col][col]);
+            for (int r = col + 1; r < N; ++r) {
+                double v = fabs(Z[r][col]);
+                if (v > best) {
+                    best = v;
+                    piv = r;
+                }
+            }
+            if (!(best > 0.0)) {
+                st |= LF_STATUS_SINGULAR;
+                break;
+            }
+            if (piv != col) {
+                for (int j = 0; j < N; ++j) {
+                    double t0 = Z[col][j];
+                    Z[col][j] = Z[piv][j];
+                    Z[piv][j] = t0;
+                    double t1 = Inv[col][j];
+                    Inv[col][j] = Inv[piv][j];
+                    Inv[piv][j] = t1;
+                }
+            }
+            const double ip = 1.0 / Z[col][col];
+            for (int j = 0; j < N; ++j) {
+                Z[col][j] *= ip;
+                Inv[col][j] *= ip;
+            }
+            for (int r = 0; r < N; ++r) {
+                if (r == col) continue;
+                const double f = Z[r][col];
+                for (int j = 0; j < N; ++j) {
+                    Z[r][j] -= f * Z[col][j];
+                    Inv[r][j] -= f * Inv[col][j];
+                }
+            }
+        }
+    }
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = 0; i < N; ++i) {
+        double b = 0.0;
+        for (int j = 0; j < N; ++j) b += Inv[i][j] * X[j];  // beta = Z^-1 X  (:116)
+        if (st & (LF_STATUS_SINGULAR | LF_STATUS_NOT_POSDEF)) b = qnan;
+        if (!isfinite(b)) st |= LF_STATUS_NONFINITE;
+        beta[i] = b;
+        for (int j = 0; j < N; ++j) zinv[i * N + j] = Inv[i][j];
+    }
+    return st;
+}
+
+// Last-arriving CTA of a (image, lane-group): fixed-order sum of the per-chunk partials
+// and the solves.  `mom` is shared memory [LSQ_MAXL][LSQ_MAXNM].
+__device__ __noinline__ void lsq_finalize(const LsqArgs& a, int b, int l0, int nl, double (*mom)[LSQ_MAXNM], int ticket_idx) {
+    const int t = threadIdx.x;
+    const int d = a.order, NM = 3 * d + 2, n = d + 1;
+    if (t < LSQ_MAXL * LSQ_MAXNM) {
+        const int l = t / LSQ_MAXNM, k = t % LSQ_MAXNM;
+        if (l < nl && k < NM) {
+            const double* p = a.partials + ((size_t)(b * a.L + l0 + l) * a.nchunks) * NM + k;
+            double s = 0.0;
+            for (int c = 0; c < a.nchunks; ++c) s += __ldcg(p + (size_t)c * NM);
+            mom[l][k] = s;
+        }
+    }
+    __syncthreads();
+    if (t < nl) {
+        const int bl = b * a.L + l0 + t;
+        const double* S = mom[t];
+        const double* T = mom[t] + (2 * d + 1);
+        double* beta = a.beta + (size_t)bl * n;
+        double* zinv = a.zinv + (size_t)bl * n * n;
+        int st = 0;
+        switch (d) {
+            case 0: st = lsq_solve<1>(S, T, a.reg_ls, a.solver, beta, zinv); break;
+            case 1: st = lsq_solve<2>(S, T, a.reg_ls, a.solver, beta, zinv); break;
+            case 2: st = lsq_solve<3>(S, T, a.reg_ls, a.solver, beta, zinv); break;
+            case 3: st = lsq_solve<4>(S, T, a.reg_ls, a.solver, beta, zinv); break;
+            default: st = lsq_solve<5>(S, T, a.reg_ls, a.solver, beta, zinv); break;
+        }
+        if (st) atomicOr(a.status, st);
+    }
+    if (t == 0) a.tickets[ticket_idx] = 0;  // leave the workspace reusable
+}
+
+// Block-level tail shared by both forward kernels: red[warp][l][k] holds per-warp
+// moment sums; write this chunk's partial, take a ticket, finalize if last.
+__device__ void lsq_chunk_tail(const LsqArgs& a, double (*red)[LSQ_MAXL][LSQ_MAXNM], double (*mom)[LSQ_MAXNM], int chunk,
+                               int b, int lg, int l0, int nl) {
+    const int t = threadIdx.x;
+    const int NM = 3 * a.order + 2;
+    __syncthreads();
+    if (t < LSQ_MAXL * LSQ_MAXNM) {
+        const int l = t / LSQ_MAXNM, k = t % LSQ_MAXNM;
+        if (l < nl && k < NM) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < LSQ_WARPS; ++w) s += red[w][l][k];
+            a.partials[((size_t)(b * a.L + l0 + l) * a.nchunks + chunk) * NM + k] = s;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    __shared__ int is_last;
+    const int ticket_idx = b * gridDim.z + lg;
+    if (t == 0) {
+        const int tk = atomicAdd(&a.tickets[ticket_idx], 1);
+        is_last = (tk == a.nchunks - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    lsq_finalize(a, b, l0, nl, mom, ticket_idx);
+}
+
+// ---------------------------------------------------------------------------------
+// Forward, row-separable fast path.  grid = (nchunks, B, ceil(L/4)), 256 threads.
+// ---------------------------------------------------------------------------------
+template <int ACT_T, bool BF16>
+__global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const LsqArgs a) {
+    __shared__ double red[LSQ_WARPS][LSQ_MAXL][LSQ_MAXNM];
+    __shared__ double mom[LSQ_MAXL][LSQ_MAXNM];
+    const int chunk = blockIdx.x, b = blockIdx.y, lg = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l0 = lg * LSQ_MAXL;
+    const int nl = min(LSQ_MAXL, a.L - l0);
+    const int d = a.order, NM = 3 * d + 2;
+    const int W4 = a.W >> 2;
+    // lane k owns moment k:  k <= 2d -> S_k (power k of y, times A);  else T_{k-2d-1} (times B)
+    const bool useB = lane > 2 * d;
+    const int ek = useB ? lane - (2 * d + 1) : lane;
+
+    double acc[LSQ_MAXL];
+#pragma unroll
+    for (int l = 0; l < LSQ_MAXL; ++l) acc[l] = 0.0;
+
+    const int r_end = min(a.H, (chunk + 1) * a.rows_per_cta);
+    for (int r = chunk * a.rows_per_cta + warp; r < r_end; r += LSQ_WARPS) {
+        const size_t rowoff = (size_t)r * a.W;
+        if (r < a.mask_rows) {
+            if (a.masked) {
+                for (int l = 0; l < nl; ++l) {
+                    float* m = a.masked + ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff;
+                    for (int c4 = lane; c4 < W4; c4 += 32)
+                        st_stream_f4(reinterpret_cast<float4*>(m) + c4, make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+            }
+            continue;
+        }
+        float A[LSQ_MAXL], Bx[LSQ_MAXL];
+#pragma unroll
+        for (int l = 0; l < LSQ_MAXL; ++l) A[l] = Bx[l] = 0.f;
+#pragma unroll 2
+        for (int c4 = lane; c4 < W4; c4 += 32) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(a.xtab + rowoff) + c4);
+#pragma unroll
+            for (int l = 0; l < LSQ_MAXL; ++l) {
+                if (l < nl) {
+                    const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff + 4 * (size_t)c4;
+                    const float4 o = load_map4<BF16>(a.o, off);
+                    float4 v;
+                    v.x = act_fn<ACT_T>(o.x, a.act);
+                    v.y = act_fn<ACT_T>(o.y, a.act);
+                    v.z = act_fn<ACT_T>(o.z, a.act);
+                    v.w = act_fn<ACT_T>(o.w, a.act);
+                    if (a.masked) st_stream_f4(reinterpret_cast<float4*>(a.masked + off), v);
+                    const float wx = v.x * v.x, wy = v.y * v.y, wz = v.z * v.z, ww = v.w * v.w;
+                    A[l] += (wx + wy) + (wz + ww);
+                    Bx[l] += fmaf(wx, x.x, wy * x.y) + fmaf(wz, x.z, ww * x.w);
+                }
+            }
+        }
+        const double y = (double)__ldg(a.yrow + r);
+        double pw = 1.0;
+        for (int i = 0; i < ek && i < 2 * LF_MAX_ORDER; ++i) pw *= y;
+#pragma unroll
+        for (int l = 0; l < LSQ_MAXL; ++l) {
+            if (l < nl) {
+                const double As = warp_sum((double)A[l]);
+                const double Bs = warp_sum((double)Bx[l]);
+                acc[l] = fma(pw, useB ? Bs : As, acc[l]);
+            }
+        }
+    }
+    if (lane < LSQ_MAXNM) {
+#pragma unroll
+        for (int l = 0; l < LSQ_MAXL; ++l) red[warp][l][lane] = (lane < NM && l < nl) ? acc[l] : 0.0;
+    }
+    lsq_chunk_tail(a, red, mom, chunk, b, lg, l0, nl);
+}
+
+// ---------------------------------------------------------------------------------
+// Forward, general grid (y varies inside a row): per-pixel fp64 accumulation of all
+// 3d+2 moments.  grid = (nchunks, B, L), one lane per CTA.  Slow path, any W.
+// ---------------------------------------------------------------------------------
+template <int ACT_T, bool BF16>
+__global__ void __launch_bounds__(LSQ_THREADS) lsq_fwd_general_kernel(const LsqArgs a) {
+    __shared__ double red[LSQ_WARPS][LSQ_MAXL][LSQ_MAXNM];
+    __shared__ double mom[LSQ_MAXL][LSQ_MAXNM];
+    const int chunk = blockIdx.x, b = blockIdx.y, l = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = a.order;
+    double S[2 * LF_MAX_ORDER + 1], T[LF_MAX_ORDER + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * LF_MAX_ORDER; ++k) S[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k <= LF_MAX_ORDER; ++k) T[k] = 0.0;
+    const size_t map_off = ((size_t)(b * a.L + l) * a.H) * a.W;
+    const size_t p_begin = (size_t)chunk * a.rows_per_cta * a.W;
+    const size_t p_end = min((size_t)a.H, (size_t)(chunk + 1) * a.rows_per_cta) * a.W;
+    const size_t p_mask = (size_t)a.mask_rows * a.W;
+    for (size_t p = p_begin + threadIdx.x; p < p_end; p += LSQ_THREADS) {
+        if (p < p_mask) {
+            if (a.masked) a.masked[map_off + p] = 0.f;
+            continue;
+        }
+        const float v = act_fn<ACT_T>(load_map1<BF16>(a.o, map_off + p), a.act);
+        if (a.masked) a.masked[map_off + p] = v;
+        const double w = (double)(v * v);
+        const double y = (double)__ldg(a.ytab + p);
+        const double wx = w * (double)__ldg(a.xtab + p);
+        double py = 1.0;
+#pragma unroll
+        for (int k = 0; k <= 2 * LF_MAX_ORDER; ++k) {
+            if (k <= 2 * d) S[k] = fma(w, py, S[k]);
+            if (k <= d) T[k] = fma(wx, py, T[k]);
+            py *= y;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k <= 2 * LF_MAX_ORDER; ++k) {
+        const double s = warp_sum(S[k]);
+        if (lane == 0 && k <= 2 * d) red[warp][0][k] = s;
+    }
+#pragma unroll
+    for (int k = 0; k <= LF_MAX_ORDER; ++k) {
+        const double s = warp_sum(T[k]);
+        if (lane == 0 && k <= d) red[warp][0][2 * d + 1 + k] = s;
+    }
+    lsq_chunk_tail(a, red, mom, chunk, b, l, l, 1);
+}
+
+// ---------------------------------------------------------------------------------
+// Backward.  d_o = m * a'(o) * 2 a(o) * (x - phi^T beta) * (phi^T z),  z = Z^-1 g.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void lsq_bwd_load_coeffs(const LsqArgs& a, int b, int l0, int nl, double (*bs)[LF_MAX_ORDER + 1],
+                                                    double (*zs)[LF_MAX_ORDER + 1]) {
+    const int n = a.order + 1;
+    const int t = threadIdx.x;
+    if (t < LSQ_MAXL * (LF_MAX_ORDER + 1)) {
+        const int l = t / (LF_MAX_ORDER + 1), i = t % (LF_MAX_ORDER + 1);
+        if (l < nl && i < n) {
+            const size_t bl = (size_t)(b * a.L + l0 + l);
+            bs[l][i] = a.beta[bl * n + i];
+            double s = 0.0;
+            for (int j = 0; j < n; ++j) s += a.zinv[bl * n * n + i * n + j] * a.gbeta[bl * n + j];
+            zs[l][i] = 2.0 * s;  // fold the factor 2
+        }
+    }
+    __syncthreads();
+}
+
+template <int ACT_T, bool BF16>
+__global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const LsqArgs a) {
+    __shared__ double bs[LSQ_MAXL][LF_MAX_ORDER + 1], zs[LSQ_MAXL][LF_MAX_ORDER + 1];
+    const int chunk = blockIdx.x, b = blockIdx.y, lg = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l0 = lg * LSQ_MAXL;
+    const int nl = min(LSQ_MAXL, a.L - l0);
+    const int d = a.order;
+    const int W4 = a.W >> 2;
+    lsq_bwd_load_coeffs(a, b, l0, nl, bs, zs);
+    const int r_end = min(a.H, (chunk + 1) * a.rows_per_cta);
+    for (int r = chunk * a.rows_per_cta + warp; r < r_end; r += LSQ_WARPS) {
+        const size_t rowoff = (size_t)r * a.W;
+        if (r < a.mask_rows) {
+            for (int l = 0; l < nl; ++l) {
+                const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff;
+                for (int c4 = lane; c4 < W4; c4 += 32) store_map4<BF16>(a.d_o, off + 4 * (size_t)c4, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+            continue;
+        }
+        const double y = (double)__ldg(a.yrow + r);
+        float qh[LSQ_MAXL], ql[LSQ_MAXL], sf[LSQ_MAXL];
+#pragma unroll
+        for (int l = 0; l < LSQ_MAXL; ++l) {
+            if (l < nl) {
+                double q = bs[l][0], s = zs[l][0];
+                for (int i = 1; i <= d; ++i) {
+                    q = fma(q, y, bs[l][i]);
+                    s = fma(s, y, zs[l][i]);
+                }
+                qh[l] = (float)q;
+                ql[l] = (float)(q - (double)qh[l]);
+                sf[l] = (float)s;
+            }
+        }
+#pragma unroll 2
+        for (int c4 = lane; c4 < W4; c4 += 32) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(a.xtab + rowoff) + c4);
+#pragma unroll
+            for (int l = 0; l < LSQ_MAXL; ++l) {
+                if (l < nl) {
+                    const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff + 4 * (size_t)c4;
+                    const float4 o = load_map4<BF16>(a.o, off);
+                    float4 g;
+                    g.x = dact_times_act<ACT_T>(o.x, a.act) * (((x.x - qh[l]) - ql[l]) * sf[l]);
+                    g.y = dact_times_act<ACT_T>(o.y, a.act) * (((x.y - qh[l]) - ql[l]) * sf[l]);
+                    g.z = dact_times_act<ACT_T>(o.z, a.act) * (((x.z - qh[l]) - ql[l]) * sf[l]);
+                    g.w = dact_times_act<ACT_T>(o.w, a.act) * (((x.w - qh[l]) - ql[l]) * sf[l]);
+                    store_map4<BF16>(a.d_o, off, g);
+                }
+            }
+        }
+    }
+}
+
+template <int ACT_T, bool BF16>
+__global__ void __launch_bounds__(LSQ_THREADS) lsq_bwd_general_kernel(const LsqArgs a) {
+    __shared__ double bs[LSQ_MAXL][LF_MAX_ORDER + 1], zs[LSQ_MAXL][LF_MAX_ORDER + 1];
+    const int chunk = blockIdx.x, b = blockIdx.y, l = blockIdx.z;
+    const int d = a.order;
+    lsq_bwd_load_coeffs(a, b, l, 1, bs, zs);
+    const size_t map_off = ((size_t)(b * a.L + l) * a.H) * a.W;
+    const size_t p_begin = (size_t)chunk * a.rows_per_cta * a.W;
+    const size_t p_end = min((size_t)a.H, (size_t)(chunk + 1) * a.rows_per_cta) * a.W;
+    const size_t p_mask = (size_t)a.mask_rows * a.W;
+    for (size_t p = p_begin + threadIdx.x; p < p_end; p += LSQ_THREADS) {
+        float g = 0.f;
+        if (p >= p_mask) {
+            const float o = load_map1<BF16>(a.o, map_off + p);
+            const double y = (double)__ldg(a.ytab + p);
+            double q = bs[0][0], s = zs[0][0];
+            for (int i = 1; i <= d; ++i) {
+                q = fma(q, y, bs[0][i]);
+                s = fma(s, y, zs[0][i]);
+            }
+            g = (float)((double)dact_times_act<ACT_T>(o, a.act) * ((double)__ldg(a.xtab + p) - q) * s);
+        }
+        store_map1<BF16>(a.d_o, map_off + p, g);
+    }
+}
+
+static int pick_rows_per_cta(int B, int groups, int H) {
+    int R = LSQ_WARPS;
+    while ((long long)B * groups * ((H + R - 1) / R) > 16384 && R < H) R *= 2;
+    return R;
+}
+
+static int validate(const LsqArgs& a, int o_dtype) {
+    LF_REQUIRE(a.o && a.xtab && (a.ytab || a.yrow));
+    LF_REQUIRE(a.B > 0 && a.L > 0 && a.H > 0 && a.W > 0);
+    LF_REQUIRE(a.order >= 0 && a.order <= LF_MAX_ORDER);
+    LF_REQUIRE(a.mask_rows >= 0 && a.mask_rows <= a.H);
+    LF_REQUIRE(a.act >= LF_ACT_NONE && a.act <= LF_ACT_SOFTPLUS);
+    LF_REQUIRE(o_dtype == LF_F32 || o_dtype == LF_BF16);
+    LF_REQUIRE(a.B <= 65535 && a.L <= 65535);
+    return LF_OK;
+}
+
+}  // namespace lf
+
+using namespace lf;
+
+extern "C" size_t lf_lsq_workspace_bytes(int B, int L, int H, int W, int order) {
+    (void)W;
+    if (B <= 0 || L <= 0 || H <= 0 || order < 0 || order > LF_MAX_ORDER) return 0;
+    // worst case: rows_per_cta = 8 -> nchunks = ceil(H/8); tickets after the partials
+    const size_t nchunks = (size_t)(H + LSQ_WARPS - 1) / LSQ_WARPS;
+    const size_t partials = (size_t)B * L * nchunks * (3 * order + 2) * sizeof(double);
+    const size_t tickets = (size_t)B * L * sizeof(int);
+    return partials + ((tickets + 15) / 16) * 16 + 16;
+}
+
+#define LSQ_DISPATCH(KERNEL, grid, args)                                                   \
+    do {                                                                                   \
+        if (args.act == LF_ACT_SQUARE) {                                                   \
+            if (o_dtype == LF_BF16)                                                        \
+                KERNEL<LF_ACT_SQUARE, true><<<grid, LSQ_THREADS, 0, stream>>>(args);       \
+            else                                                                           \
+                KERNEL<LF_ACT_SQUARE, false><<<grid, LSQ_THREADS, 0, stream>>>(args);      \
+        } else {                                                                           \
+            if (o_dtype == LF_BF16)                                                        \
+                KERNEL<LSQ_ACT_RUNTIME, true><<<grid, LSQ_THREADS, 0, stream>>>(args);     \
+            else                                                                           \
+                KERNEL<LSQ_ACT_RUNTIME, false><<<grid, LSQ_THREADS, 0, stream>>>(args);    \
+        }                                                                                  \
+    } while (0)
+
+extern "C" int lf_lsq_fwd(const void* o, int o_dtype, const float* xtab, const float* ytab, const float* yrow, int B,
+                          int L, int H, int W, int order, int mask_rows, int act, double reg_ls, int solver,
+                          double* beta, double* zinv, float* masked, int* status, void* workspace,
+                          size_t workspace_bytes, lf_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    LsqArgs a{};
+    a.o = o; a.xtab = xtab; a.ytab = ytab; a.yrow = yrow;
+    a.B = B; a.L = L; a.H = H; a.W = W; a.order = order; a.mask_rows = mask_rows; a.act = act; a.solver = solver;
+    a.reg_ls = reg_ls; a.beta = beta; a.zinv = zinv; a.masked = masked; a.status = status;
+    int rc = validate(a, o_dtype);
+    if (rc != LF_OK) return rc;
+    LF_REQUIRE(beta && zinv && status && workspace);
+    LF_REQUIRE(solver == LF_SOLVER_INVERSE || solver == LF_SOLVER_CHOLESKY);
+    if (workspace_bytes < lf_lsq_workspace_bytes(B, L, H, W, order)) return LF_ERR_WORKSPACE_TOO_SMALL;
+    const bool rowsep = (yrow != nullptr) && (W % 4 == 0);
+    if (!rowsep && !ytab) return LF_ERR_INVALID_ARGUMENT;
+    const int groups = rowsep ? (L + LSQ_MAXL - 1) / LSQ_MAXL : L;
+    a.rows_per_cta = pick_rows_per_cta(B, groups, H);
+    a.nchunks = (H + a.rows_per_cta - 1) / a.rows_per_cta;
+    const size_t nchunks_max = (size_t)(H + LSQ_WARPS - 1) / LSQ_WARPS;
+    a.partials = reinterpret_cast<double*>(workspace);
+    const size_t partial_bytes = (size_t)B * L * nchunks_max * (3 * order + 2) * sizeof(double);
+    a.tickets = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + ((partial_bytes + 15) / 16) * 16);
+    dim3 grid(a.nchunks, B, groups);
+    if (rowsep)
+        LSQ_DISPATCH(lsq_fwd_rowsep_kernel, grid, a);
+    else
+        LSQ_DISPATCH(lsq_fwd_general_kernel, grid, a);
+    return check_launch();
+}
+
+extern "C" int lf_lsq_bwd(const void* o, int o_dtype, const float* xtab, const float* ytab, const float* yrow, int B,
+                          int L, int H, int W, int order, int mask_rows, int act, const double* beta,
+                          const double* zinv, const double* gbeta, void* d_o, lf_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    LsqArgs a{};
+    a.o = o; a.xtab = xtab; a.ytab = ytab; a.yrow = yrow;
+    a.B = B; a.L = L; a.H = H; a.W = W; a.order = order; a.mask_rows = mask_rows; a.act = act;
+    a.beta = const_cast<double*>(beta); a.zinv = const_cast<double*>(zinv); a.gbeta = gbeta; a.d_o = d_o;
+    int rc = validate(a, o_dtype);
+    if (rc != LF_OK) return rc;
+    LF_REQUIRE(beta && zinv && gbeta && d_o);
+    const bool rowsep = (yrow != nullptr) && (W % 4 == 0);
+    if (!rowsep && !ytab) return LF_ERR_INVALID_ARGUMENT;
+    const int groups = rowsep ? (L + LSQ_MAXL - 1) / LSQ_MAXL : L;
+    a.rows_per_cta = pick_rows_per_cta(B, groups, H);
+    a.nchunks = (H + a.rows_per_cta - 1) / a.rows_per_cta;
+    dim3 grid(a.nchunks, B, groups);
+    if (rowsep)
+        LSQ_DISPATCH(lsq_bwd_rowsep_kernel, grid, a);
+    else
+        LSQ_DISPATCH(lsq_bwd_general_kernel, grid, a);
+    return check_launch();
+}

@@ -1,0 +1,520 @@
+"""Host side of the ERFNet blocks: one ``torch.autograd.Function`` per reference block
+(DownsamplerBlock, non_bottleneck_1d, UpsamplerBlock, output ConvTranspose2d -- see
+BP/Networks/ERFNet.py), each a fixed sequence of C-ABI launches (include/lanefit_b200.h)
+on NHWC fp32 tensors.  Torch provides device memory, the stream and the autograd graph;
+no torch operator touches a feature map on this path.
+
+Training-mode memory plan per non_bottleneck_1d (what backward needs):
+  x (block input), t1 = relu(conv3x1_1), t2 = conv1x3_1 (pre-BN), t3 = relu(bn1),
+  t4 = relu(conv3x1_2), t5 = conv1x3_2 (pre-BN), y = block output, the two (mean, invstd)
+  pairs and the dropout mask.
+"""
+import ctypes
+
+import torch
+
+from . import _capi
+from . import net_plans as plans
+
+MAX_TAPS = 9
+BN_EPS = 1e-3
+BN_MOMENTUM = 0.1
+
+_i = ctypes.c_int
+_p = ctypes.c_void_p
+
+
+class LfConvArgs(ctypes.Structure):
+    _fields_ = [("inp", _p), ("wmat", _p), ("bias", _p), ("out", _p), ("mask_src", _p), ("add_src", _p),
+                ("add_mask", _p),
+                ("N", _i), ("Hin", _i), ("Win", _i), ("Cin", _i), ("in_cstride", _i),
+                ("Hout", _i), ("Wout", _i), ("out_cstride", _i), ("out_coff", _i), ("Cout", _i), ("CoutPad", _i),
+                ("Hs", _i), ("Ws", _i), ("osy", _i), ("osx", _i), ("oy0", _i), ("ox0", _i), ("isy", _i), ("isx", _i),
+                ("ntaps", _i), ("dy", _i * MAX_TAPS), ("dx", _i * MAX_TAPS), ("wtap", _i * MAX_TAPS),
+                ("relu", _i)]
+
+
+class LfWgradArgs(ctypes.Structure):
+    _fields_ = [("P", _p), ("Q", _p), ("partial", _p), ("qsum_partial", _p),
+                ("N", _i), ("Hs", _i), ("Ws", _i),
+                ("Hp", _i), ("Wp", _i), ("Cp", _i), ("p_cstride", _i), ("p_coff", _i), ("psy", _i), ("psx", _i),
+                ("Hq", _i), ("Wq", _i), ("Cq", _i), ("q_cstride", _i), ("q_coff", _i), ("qsy", _i), ("qsx", _i),
+                ("ntaps", _i), ("pdy", _i * MAX_TAPS), ("pdx", _i * MAX_TAPS), ("qdy", _i * MAX_TAPS),
+                ("qdx", _i * MAX_TAPS),
+                ("CpPad", _i), ("CqPad", _i), ("nsplit", _i)]
+
+
+_NET_PROTOS = {
+    "lf_conv_f32": (_i, [ctypes.POINTER(LfConvArgs), _p]),
+    "lf_wgrad_f32": (_i, [ctypes.POINTER(LfWgradArgs), _p]),
+    "lf_wgrad_reduce": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p]),
+    "lf_vec_reduce": (_i, [_p, _i, _i, _i, _p, _p]),
+    "lf_colsum_blocks": (_i, [ctypes.c_longlong]),
+    "lf_colsum": (_i, [_p, ctypes.c_longlong, _i, _i, _i, _p, _i, _p]),
+    "lf_maxpool2_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "lf_maxpool2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p]),
+    "lf_bn_blocks": (_i, [ctypes.c_longlong, _i]),
+    "lf_bn_stats": (_i, [_p, ctypes.c_longlong, _i, _p, _p]),
+    "lf_bn_finalize": (_i, [_p, _i, ctypes.c_longlong, _i, _p, _p, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p, _p,
+                            _p, _p]),
+    "lf_bn_eval_prepare": (_i, [_i, _p, _p, ctypes.c_float, _p, _p, _p, _p, _p]),
+    "lf_bn_apply": (_i, [_p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
+    "lf_bn_bwd_reduce": (_i, [_p, _p, _p, _p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p]),
+    "lf_bn_bwd_finalize": (_i, [_p, _i, ctypes.c_longlong, _i, _p, _p, _p, _p, _p]),
+    "lf_bn_bwd_apply": (_i, [_p, _p, _p, _p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "lf_outconv_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "lf_outconv_bwd_data": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "lf_outconv_wgrad_blocks": (_i, [ctypes.c_longlong]),
+    "lf_outconv_bwd_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "lf_nchw_to_nhwc_pad": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "lf_nhwc_to_nchw": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "lf_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+}
+_capi.PROTOTYPES.update(_NET_PROTOS)
+
+ptr = _capi.ptr
+
+
+def _lib():
+    return _capi.lib()
+
+
+def _stream():
+    return _capi.stream_ptr()
+
+
+def _empty(shape, like, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+# --------------------------------------------------------------------------------------
+# weight packing (parameter-sized tensors; reference layouts -> GEMM layouts)
+# --------------------------------------------------------------------------------------
+
+def pack_conv_fwd(w, ci_pad=None):
+    """Conv2d weight [Co,Ci,kh,kw] -> [kh*kw, CiPad, CoPad] (zero padded)."""
+    Co, Ci, kh, kw = w.shape
+    ci_pad = ci_pad or Ci
+    out = w.new_zeros(kh * kw, ci_pad, plans.cout_pad(Co))
+    out[:, :Ci, :Co] = w.permute(2, 3, 1, 0).reshape(kh * kw, Ci, Co)
+    return out
+
+
+def pack_conv_dgrad(w):
+    """Conv2d weight [Co,Ci,kh,kw] -> [kh*kw, Co, CiPad]: the transposed GEMM operand."""
+    Co, Ci, kh, kw = w.shape
+    out = w.new_zeros(kh * kw, Co, plans.cout_pad(Ci))
+    out[:, :, :Ci] = w.permute(2, 3, 0, 1).reshape(kh * kw, Co, Ci)
+    return out
+
+
+def pack_convT_fwd(w):
+    """ConvTranspose2d weight [Ci,Co,kh,kw] -> [kh*kw, Ci, CoPad]."""
+    Ci, Co, kh, kw = w.shape
+    out = w.new_zeros(kh * kw, Ci, plans.cout_pad(Co))
+    out[:, :, :Co] = w.permute(2, 3, 0, 1).reshape(kh * kw, Ci, Co)
+    return out
+
+
+def pack_convT_dgrad(w):
+    """ConvTranspose2d weight [Ci,Co,kh,kw] -> [kh*kw, Co, CiPad]."""
+    Ci, Co, kh, kw = w.shape
+    out = w.new_zeros(kh * kw, Co, plans.cout_pad(Ci))
+    out[:, :, :Ci] = w.permute(2, 3, 1, 0).reshape(kh * kw, Co, Ci)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# launch helpers
+# --------------------------------------------------------------------------------------
+
+def run_conv(phases, x, wmat, cin, out, cout, out_coff=0, bias=None, relu=False, mask_src=None, add_src=None,
+             add_mask=None):
+    """x: [N,Hin,Win,Cx] NHWC (Cx = channel stride), out: [N,Hout,Wout,Co_total]."""
+    h = _lib()
+    N, Hin, Win, cx = x.shape
+    _, Hout, Wout, cot = out.shape
+    a = LfConvArgs()
+    a.inp, a.wmat, a.bias, a.out = x.data_ptr(), wmat.data_ptr(), (bias.data_ptr() if bias is not None else None), \
+        out.data_ptr()
+    a.mask_src = mask_src.data_ptr() if mask_src is not None else None
+    a.add_src = add_src.data_ptr() if add_src is not None else None
+    a.add_mask = add_mask.data_ptr() if add_mask is not None else None
+    a.N, a.Hin, a.Win, a.Cin, a.in_cstride = N, Hin, Win, cin, cx
+    a.Hout, a.Wout, a.out_cstride, a.out_coff, a.Cout, a.CoutPad = Hout, Wout, cot, out_coff, cout, wmat.shape[2]
+    a.relu = int(relu)
+    assert wmat.shape[1] == cin, (wmat.shape, cin)
+    st = _stream()
+    for ph in phases:
+        a.Hs, a.Ws, a.osy, a.osx, a.oy0, a.ox0, a.isy, a.isx = (ph["Hs"], ph["Ws"], ph["osy"], ph["osx"], ph["oy0"],
+                                                               ph["ox0"], ph["isy"], ph["isx"])
+        taps = ph["taps"]
+        a.ntaps = len(taps)
+        for t, (dy, dx, slot) in enumerate(taps):
+            a.dy[t], a.dx[t], a.wtap[t] = dy, dx, slot
+        _capi.check(h.lf_conv_f32(ctypes.byref(a), st), "lf_conv_f32")
+    return out
+
+
+def _nsplit_for(tiles, M):
+    target = 148 * 6
+    ns = max(1, min((target + tiles - 1) // tiles, max(1, M // 256)))
+    return int(ns)
+
+
+def run_wgrad(plan, P, cp, Q, cq, q_coff, N, dst_w, layout, dst_b=None, cp_true=None, cq_true=None):
+    """Weight (and optionally bias) gradient.  layout: (st, sp, sq) strides of dst_w for
+    (tap, cp, cq).  cp/cq: channel counts handed to the GEMM (multiples of 4); *_true: the
+    counts actually written (<= cp/cq)."""
+    h = _lib()
+    _, Hp, Wp, cps = P.shape
+    _, Hq, Wq, cqs = Q.shape
+    ntaps = len(plan["ptaps"])
+    a = LfWgradArgs()
+    a.P, a.Q = P.data_ptr(), Q.data_ptr()
+    a.N, a.Hs, a.Ws = N, plan["Hs"], plan["Ws"]
+    a.Hp, a.Wp, a.Cp, a.p_cstride, a.p_coff, a.psy, a.psx = Hp, Wp, cp, cps, 0, plan["psy"], plan["psx"]
+    a.Hq, a.Wq, a.Cq, a.q_cstride, a.q_coff, a.qsy, a.qsx = Hq, Wq, cq, cqs, q_coff, plan["qsy"], plan["qsx"]
+    a.ntaps = ntaps
+    for t in range(ntaps):
+        a.pdy[t], a.pdx[t] = plan["ptaps"][t]
+        a.qdy[t], a.qdx[t] = plan["qtaps"][t]
+    a.CpPad, a.CqPad = plans.pad_to(cp, 64), plans.pad_to(cq, 64)
+    tiles = (a.CpPad // 64) * (a.CqPad // 64) * ntaps
+    M = N * plan["Hs"] * plan["Ws"]
+    a.nsplit = _nsplit_for(tiles, M)
+    partial = torch.empty(a.nsplit * ntaps * a.CpPad * a.CqPad, dtype=torch.float32, device=P.device)
+    a.partial = partial.data_ptr()
+    qpart = None
+    if dst_b is not None:
+        qpart = torch.empty(a.nsplit * a.CqPad, dtype=torch.float32, device=P.device)
+        a.qsum_partial = qpart.data_ptr()
+    st = _stream()
+    _capi.check(h.lf_wgrad_f32(ctypes.byref(a), st), "lf_wgrad_f32")
+    s_t, s_p, s_q = layout
+    _capi.check(h.lf_wgrad_reduce(ptr(partial), a.nsplit, ntaps, cp_true or cp, cq_true or cq, a.CpPad, a.CqPad,
+                                  ptr(dst_w), s_t, s_p, s_q, st), "lf_wgrad_reduce")
+    if dst_b is not None:
+        _capi.check(h.lf_vec_reduce(ptr(qpart), a.nsplit, cq_true or cq, a.CqPad, ptr(dst_b), st), "lf_vec_reduce")
+
+
+def run_colsum(src, C, coff, dst):
+    """dst[c] = sum over all pixels of src[..., coff + c]   (src NHWC)."""
+    h = _lib()
+    npix = src.numel() // src.shape[-1]
+    nblk = h.lf_colsum_blocks(npix)
+    cpad = plans.pad_to(C, 4)
+    part = torch.empty(nblk * cpad, dtype=torch.float32, device=src.device)
+    st = _stream()
+    _capi.check(h.lf_colsum(ptr(src), npix, C, src.shape[-1], coff, ptr(part), cpad, st), "lf_colsum")
+    _capi.check(h.lf_vec_reduce(ptr(part), nblk, C, cpad, ptr(dst), st), "lf_vec_reduce")
+
+
+class BNState:
+    """Per-call BatchNorm2d state: batch (mean, invstd) for backward, (scale, shift) for apply."""
+    __slots__ = ("mean", "invstd", "scale", "shift")
+
+
+def bn_forward_stats(x, gamma, beta, running_mean, running_var, training):
+    """x: dense NHWC.  Returns BNState; updates running stats in training mode
+    (nn.BatchNorm2d(eps=1e-3, momentum=0.1), ERFNet.py:17,33,39,102)."""
+    h = _lib()
+    C = x.shape[-1]
+    npix = x.numel() // C
+    s = BNState()
+    buf = torch.empty(4, C, dtype=torch.float32, device=x.device)
+    s.mean, s.invstd, s.scale, s.shift = buf[0], buf[1], buf[2], buf[3]
+    st = _stream()
+    if training:
+        nblk = h.lf_bn_blocks(npix, C)
+        part = torch.empty(nblk * 2 * C, dtype=torch.float64, device=x.device)
+        _capi.check(h.lf_bn_stats(ptr(x), npix, C, ptr(part), st), "lf_bn_stats")
+        _capi.check(h.lf_bn_finalize(ptr(part), nblk, npix, C, ptr(gamma), ptr(beta), BN_EPS, BN_MOMENTUM,
+                                     ptr(running_mean), ptr(running_var), ptr(s.mean), ptr(s.invstd), ptr(s.scale),
+                                     ptr(s.shift), st), "lf_bn_finalize")
+    else:
+        _capi.check(h.lf_bn_eval_prepare(C, ptr(gamma), ptr(beta), BN_EPS, ptr(running_mean), ptr(running_var),
+                                         ptr(s.scale), ptr(s.shift), st), "lf_bn_eval_prepare")
+    return s
+
+
+def bn_apply(x, s, relu, drop=None, res=None):
+    h = _lib()
+    C = x.shape[-1]
+    npix = x.numel() // C
+    y = torch.empty_like(x)
+    ppi = x.shape[1] * x.shape[2]
+    _capi.check(h.lf_bn_apply(ptr(x), npix, C, ppi, ptr(s.scale), ptr(s.shift), ptr(drop), ptr(res), int(relu), ptr(y),
+                              _stream()), "lf_bn_apply")
+    return y
+
+
+def bn_backward(dy, ymask, drop, x, s, gamma):
+    """-> (dx, dgamma, dbeta).  g = dy*(ymask>0)*drop is recomputed on the fly."""
+    h = _lib()
+    C = x.shape[-1]
+    npix = x.numel() // C
+    ppi = x.shape[1] * x.shape[2]
+    st = _stream()
+    nblk = h.lf_bn_blocks(npix, C)
+    part = torch.empty(nblk * 2 * C, dtype=torch.float64, device=x.device)
+    _capi.check(h.lf_bn_bwd_reduce(ptr(dy), ptr(ymask), ptr(drop), ptr(x), npix, C, ppi, ptr(s.mean), ptr(s.invstd),
+                                   ptr(part), st), "lf_bn_bwd_reduce")
+    buf = torch.empty(4, C, dtype=torch.float32, device=x.device)
+    dgamma, dbeta, c1, c2 = buf[0], buf[1], buf[2], buf[3]
+    _capi.check(h.lf_bn_bwd_finalize(ptr(part), nblk, npix, C, ptr(dgamma), ptr(dbeta), ptr(c1), ptr(c2), st),
+                "lf_bn_bwd_finalize")
+    dx = torch.empty_like(x)
+    _capi.check(h.lf_bn_bwd_apply(ptr(dy), ptr(ymask), ptr(drop), ptr(x), npix, C, ppi, ptr(s.mean), ptr(s.invstd),
+                                  ptr(gamma), ptr(c1), ptr(c2), ptr(dx), st), "lf_bn_bwd_apply")
+    return dx, dgamma, dbeta
+
+
+def _require_training_for_backward(training):
+    if not training:
+        raise RuntimeError("backward through eval-mode BatchNorm is not implemented on the B200 path "
+                           "(the reference only back-propagates in train mode, BP/main.py:232,338)")
+
+
+# --------------------------------------------------------------------------------------
+# DownsamplerBlock  (ERFNet.py:11-22):  relu(bn(cat[conv3x3 s2 p1 (x), maxpool2(x)]))
+# --------------------------------------------------------------------------------------
+class DownFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cin, w, b, gamma, beta, rm, rv, training, need_dx):
+        """x: [N,H,W,Cx] NHWC with Cx >= cin (stem: 3 channels padded to 4)."""
+        _capi.require_cuda(x)
+        h = _lib()
+        N, H, W, cx = x.shape
+        cc = w.shape[0]                      # conv output channels = noutput - ninput
+        cout = cc + cin
+        cin_gemm = plans.pad_to(cin, 4)
+        wmat = pack_conv_fwd(w, cin_gemm)
+        phases, (Ho, Wo) = plans.conv_fwd_plan(H, W, 3, 3, 2, 1, 1, 1, 1)
+        cat = _empty((N, Ho, Wo, cout), x)
+        run_conv(phases, x, wmat, cin_gemm, cat, cc, 0, bias=b)
+        _capi.check(h.lf_maxpool2_fwd(ptr(x), N, H, W, cin, cx, ptr(cat), cout, cc, _stream()), "lf_maxpool2_fwd")
+        s = bn_forward_stats(cat, gamma, beta, rm, rv, training)
+        y = bn_apply(cat, s, relu=True)
+        ctx.save_for_backward(x, w, cat, y, gamma, s.mean, s.invstd)
+        ctx.cfg = (cin, training, need_dx)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, cat, y, gamma, mean, invstd = ctx.saved_tensors
+        cin, training, need_dx = ctx.cfg
+        _require_training_for_backward(training)
+        h = _lib()
+        dy = dy.contiguous()
+        N, H, W, cx = x.shape
+        cc = w.shape[0]
+        cout = cc + cin
+        s = BNState()
+        s.mean, s.invstd = mean, invstd
+        dcat, dgamma, dbeta = bn_backward(dy, y, None, cat, s, gamma)
+        # weight / bias gradient of the conv part (channels [0,cc) of dcat)
+        dw = torch.empty_like(w)
+        db = _empty((cc,), x)
+        wplan = plans.conv_wgrad_plan(H, W, 3, 3, 2, 1, 1, 1, 1)
+        cin_gemm = plans.pad_to(cin, 4)
+        cq_gemm = plans.pad_to(cc, 4)
+        run_wgrad(wplan, x, cin_gemm, dcat, cq_gemm, 0, N, dw, (1, 9, cin * 9), db, cp_true=cin, cq_true=cc)
+        dx = None
+        if need_dx:
+            dx = _empty((N, H, W, cx), x)
+            wd = pack_conv_dgrad(w)                      # [9, cc, cinPad]
+            phases, _ = plans.transposed_gather_plan(dcat.shape[1], dcat.shape[2], H, W, 3, 1)
+            run_conv(phases, dcat, wd, cc, dx, cin, 0)
+            _capi.check(h.lf_maxpool2_bwd(ptr(x), N, H, W, cin, cx, ptr(dcat), cout, cc, ptr(dx), cx, 1, _stream()),
+                        "lf_maxpool2_bwd")
+        return dx, None, dw, db, dgamma, dbeta, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------
+# non_bottleneck_1d  (ERFNet.py:25-60)
+# --------------------------------------------------------------------------------------
+class Nb1dFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, g1, be1, w3, b3, w4, b4, g2, be2, rm1, rv1, rm2, rv2, dil, drop, training):
+        _capi.require_cuda(x)
+        N, H, W, C = x.shape
+        p31, _ = plans.conv_fwd_plan(H, W, 3, 1, 1, 1, 0, 1, 1)
+        p13, _ = plans.conv_fwd_plan(H, W, 1, 3, 1, 0, 1, 1, 1)
+        p31d, _ = plans.conv_fwd_plan(H, W, 3, 1, 1, dil, 0, dil, 1)
+        p13d, _ = plans.conv_fwd_plan(H, W, 1, 3, 1, 0, dil, 1, dil)
+        t1 = run_conv(p31, x, pack_conv_fwd(w1), C, torch.empty_like(x), C, bias=b1, relu=True)
+        t2 = run_conv(p13, t1, pack_conv_fwd(w2), C, torch.empty_like(x), C, bias=b2)
+        s1 = bn_forward_stats(t2, g1, be1, rm1, rv1, training)
+        t3 = bn_apply(t2, s1, relu=True)
+        t4 = run_conv(p31d, t3, pack_conv_fwd(w3), C, torch.empty_like(x), C, bias=b3, relu=True)
+        t5 = run_conv(p13d, t4, pack_conv_fwd(w4), C, torch.empty_like(x), C, bias=b4)
+        s2 = bn_forward_stats(t5, g2, be2, rm2, rv2, training)
+        y = bn_apply(t5, s2, relu=True, drop=drop, res=x)
+        ctx.save_for_backward(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1.mean, s1.invstd, s2.mean, s2.invstd,
+                              drop if drop is not None else x.new_empty(0))
+        ctx.cfg = (dil, training, drop is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, m1, is1, m2, is2, drop) = ctx.saved_tensors
+        dil, training, has_drop = ctx.cfg
+        _require_training_for_backward(training)
+        drop = drop if has_drop else None
+        dy = dy.contiguous()
+        N, H, W, C = x.shape
+        s1, s2 = BNState(), BNState()
+        s1.mean, s1.invstd, s2.mean, s2.invstd = m1, is1, m2, is2
+        lay = lambda w: (1, w.shape[2] * w.shape[3], w.shape[1] * w.shape[2] * w.shape[3])  # (tap, ci, co) strides
+
+        # y = relu(bn2(t5)*drop + x)
+        d5, dg2, dbe2 = bn_backward(dy, y, drop, t5, s2, g2)
+        # conv1x3_2 (dilated)
+        dw4, db4 = torch.empty_like(w4), _empty((C,), x)
+        run_wgrad(plans.conv_wgrad_plan(H, W, 1, 3, 1, 0, dil, 1, dil), t4, C, d5, C, 0, N, dw4, lay(w4), db4)
+        pd, _ = plans.conv_dgrad_plan_s1(H, W, 1, 3, 0, dil, 1, dil)
+        d4 = run_conv(pd, d5, pack_conv_dgrad(w4), C, torch.empty_like(x), C, mask_src=t4)
+        # conv3x1_2 (dilated)
+        dw3, db3 = torch.empty_like(w3), _empty((C,), x)
+        run_wgrad(plans.conv_wgrad_plan(H, W, 3, 1, 1, dil, 0, dil, 1), t3, C, d4, C, 0, N, dw3, lay(w3), db3)
+        pd, _ = plans.conv_dgrad_plan_s1(H, W, 3, 1, dil, 0, dil, 1)
+        d3 = run_conv(pd, d4, pack_conv_dgrad(w3), C, torch.empty_like(x), C, mask_src=t3)
+        # bn1 (+relu already applied through mask_src=t3)
+        d2, dg1, dbe1 = bn_backward(d3, None, None, t2, s1, g1)
+        # conv1x3_1
+        dw2, db2 = torch.empty_like(w2), _empty((C,), x)
+        run_wgrad(plans.conv_wgrad_plan(H, W, 1, 3, 1, 0, 1, 1, 1), t1, C, d2, C, 0, N, dw2, lay(w2), db2)
+        pd, _ = plans.conv_dgrad_plan_s1(H, W, 1, 3, 0, 1, 1, 1)
+        d1 = run_conv(pd, d2, pack_conv_dgrad(w2), C, torch.empty_like(x), C, mask_src=t1)
+        # conv3x1_1, plus the residual branch: dx = dgrad + dy*(y>0)
+        dw1, db1 = torch.empty_like(w1), _empty((C,), x)
+        run_wgrad(plans.conv_wgrad_plan(H, W, 3, 1, 1, 1, 0, 1, 1), x, C, d1, C, 0, N, dw1, lay(w1), db1)
+        pd, _ = plans.conv_dgrad_plan_s1(H, W, 3, 1, 1, 0, 1, 1)
+        dx = run_conv(pd, d1, pack_conv_dgrad(w1), C, torch.empty_like(x), C, add_src=dy, add_mask=y)
+        return (dx, dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2, None, None, None, None, None, None,
+                None)
+
+
+# --------------------------------------------------------------------------------------
+# UpsamplerBlock  (ERFNet.py:98-107):  relu(bn(convT3x3 s2 p1 op1 (x)))
+# --------------------------------------------------------------------------------------
+class UpFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, rm, rv, training):
+        _capi.require_cuda(x)
+        N, H, W, ci = x.shape
+        co = w.shape[1]
+        phases, (Ho, Wo) = plans.transposed_gather_plan(H, W, 2 * H, 2 * W, 3, 1)
+        u = run_conv(phases, x, pack_convT_fwd(w), ci, _empty((N, Ho, Wo, co), x), co, bias=b)
+        s = bn_forward_stats(u, gamma, beta, rm, rv, training)
+        y = bn_apply(u, s, relu=True)
+        ctx.save_for_backward(x, w, u, y, gamma, s.mean, s.invstd)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, u, y, gamma, mean, invstd = ctx.saved_tensors
+        _require_training_for_backward(ctx.training)
+        dy = dy.contiguous()
+        N, H, W, ci = x.shape
+        co = w.shape[1]
+        s = BNState()
+        s.mean, s.invstd = mean, invstd
+        du, dgamma, dbeta = bn_backward(dy, y, None, u, s, gamma)
+        dw, db = torch.empty_like(w), _empty((co,), x)
+        run_wgrad(plans.convT_wgrad_plan(H, W, 3, 1), x, ci, du, co, 0, N, dw, (1, co * 9, 9))
+        run_colsum(du, co, 0, db)
+        pd, _ = plans.convT_dgrad_plan(2 * H, 2 * W, H, W, 3, 1)
+        dx = run_conv(pd, du, pack_convT_dgrad(w), co, torch.empty_like(x), ci)
+        return dx, dw, db, dgamma, dbeta, None, None, None
+
+
+# --------------------------------------------------------------------------------------
+# Decoder.output_conv (ERFNet.py:124,152): ConvTranspose2d(16 -> L, 2, stride 2)
+# NHWC in -> planar NCHW out (what the LSQ layer consumes and Net.forward returns)
+# --------------------------------------------------------------------------------------
+class OutConvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _capi.require_cuda(x)
+        h = _lib()
+        N, H, W, ci = x.shape
+        L = w.shape[1]
+        out = _empty((N, L, 2 * H, 2 * W), x)
+        _capi.check(h.lf_outconv_fwd(ptr(x), ptr(w.contiguous()), ptr(b), N, H, W, ci, L, ptr(out), _stream()),
+                    "lf_outconv_fwd")
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        h = _lib()
+        dout = dout.contiguous()
+        N, H, W, ci = x.shape
+        L = w.shape[1]
+        st = _stream()
+        dx = torch.empty_like(x)
+        _capi.check(h.lf_outconv_bwd_data(ptr(dout), ptr(w.contiguous()), N, H, W, ci, L, ptr(dx), st),
+                    "lf_outconv_bwd_data")
+        nblk = h.lf_outconv_wgrad_blocks(N * H * W)
+        width = ci * L * 4 + L
+        part = torch.empty(nblk * width, dtype=torch.float32, device=x.device)
+        _capi.check(h.lf_outconv_bwd_weight(ptr(x), ptr(dout), N, H, W, ci, L, ptr(part), st), "lf_outconv_bwd_weight")
+        red = _empty((width,), x)
+        _capi.check(h.lf_vec_reduce(ptr(part), nblk, width, width, ptr(red), st), "lf_vec_reduce")
+        dw = red[:ci * L * 4].view(ci, L, 2, 2)
+        db = red[ci * L * 4:]
+        return dx, dw, db
+
+
+# --------------------------------------------------------------------------------------
+# layout changes at the module boundary
+# --------------------------------------------------------------------------------------
+def image_to_nhwc_pad(x, cpad):
+    """[N,C,H,W] fp32 -> [N,H,W,cpad] (zero padded); no gradient (input images)."""
+    _capi.require_cuda(x)
+    x = x.contiguous().float()
+    N, C, H, W = x.shape
+    out = _empty((N, H, W, cpad), x)
+    _capi.check(_lib().lf_nchw_to_nhwc_pad(ptr(x), N, C, H, W, cpad, ptr(out), _stream()), "lf_nchw_to_nhwc_pad")
+    return out
+
+
+class ToNHWC(torch.autograd.Function):
+    """NCHW-contiguous -> NHWC-contiguous [N,H,W,C]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _capi.require_cuda(x)
+        x = x.contiguous()
+        N, C, H, W = x.shape
+        out = _empty((N, H, W, C), x)
+        _capi.check(_lib().lf_nchw_to_nhwc(ptr(x), N, C, H, W, ptr(out), _stream()), "lf_nchw_to_nhwc")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        N, H, W, C = g.shape
+        out = _empty((N, C, H, W), g)
+        _capi.check(_lib().lf_nhwc_to_nchw(ptr(g), N, H, W, C, ptr(out), _stream()), "lf_nhwc_to_nchw")
+        return out
+
+
+def as_nhwc(x):
+    """Accept what a reference caller passes (NCHW-shaped) and return a dense [N,H,W,C] tensor.
+    channels_last inputs (what our own blocks emit, viewed as NCHW) are re-viewed for free."""
+    if x.dim() != 4:
+        raise ValueError("expected a 4-D feature map")
+    xp = x.permute(0, 2, 3, 1)
+    if xp.is_contiguous():
+        return xp
+    return ToNHWC.apply(x)
+
+
+def as_nchw_view(y):
+    """[N,H,W,C] dense -> NCHW-shaped view (channels_last strides), zero copy."""
+    return y.permute(0, 3, 1, 2)

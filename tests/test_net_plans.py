@@ -1,0 +1,134 @@
+"""CPU check of the host-side geometry (net_plans.py + the weight packers in ops_net.py):
+a torch emulation of the generic conv / wgrad kernels' contract (LfConvArgs / LfWgradArgs in
+include/lanefit_b200.h) fed with the SAME plans and packed weights the CUDA launches get, compared
+against torch's own convolutions and autograd."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lanedetection_end2end_b200 import net_plans as plans
+from lanedetection_end2end_b200 import ops_net as ops
+
+torch.manual_seed(0)
+DT = torch.float64
+
+
+def emulate_conv(phases, x, wmat, cin, Hout, Wout, cout):
+    """x [N,Hin,Win,Cx] NHWC, wmat [T,cin,CoPad] -> out [N,Hout,Wout,cout]."""
+    N, Hin, Win, _ = x.shape
+    out = torch.zeros(N, Hout, Wout, cout, dtype=x.dtype)
+    for ph in phases:
+        for j in range(ph["Hs"]):
+            for i in range(ph["Ws"]):
+                acc = torch.zeros(N, cout, dtype=x.dtype)
+                for dy, dx, slot in ph["taps"]:
+                    iy, ix = j * ph["isy"] + dy, i * ph["isx"] + dx
+                    if 0 <= iy < Hin and 0 <= ix < Win:
+                        acc += x[:, iy, ix, :cin] @ wmat[slot, :, :cout]
+                out[:, j * ph["osy"] + ph["oy0"], i * ph["osx"] + ph["ox0"]] = acc
+    return out
+
+
+def emulate_wgrad(plan, P, cp, Q, cq, q_coff):
+    """-> dW [T, cp, cq]."""
+    N, Hp, Wp, _ = P.shape
+    _, Hq, Wq, _ = Q.shape
+    T = len(plan["ptaps"])
+    dW = torch.zeros(T, cp, cq, dtype=P.dtype)
+    for t in range(T):
+        for j in range(plan["Hs"]):
+            for i in range(plan["Ws"]):
+                py, px = j * plan["psy"] + plan["ptaps"][t][0], i * plan["psx"] + plan["ptaps"][t][1]
+                qy, qx = j * plan["qsy"] + plan["qtaps"][t][0], i * plan["qsx"] + plan["qtaps"][t][1]
+                if 0 <= py < Hp and 0 <= px < Wp and 0 <= qy < Hq and 0 <= qx < Wq:
+                    dW[t] += P[:, py, px, :cp].t() @ Q[:, qy, qx, q_coff:q_coff + cq]
+    return dW
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("kh,kw,dil", [(3, 1, 1), (1, 3, 1), (3, 1, 2), (1, 3, 4), (3, 1, 8)])
+def test_factorised_conv_fwd_dgrad_wgrad(kh, kw, dil):
+    N, C, H, W = 2, 8, 9, 11
+    ph, pw = (dil, 0) if kh == 3 else (0, dil)
+    dh, dw_ = (dil, 1) if kh == 3 else (1, dil)
+    x = torch.randn(N, C, H, W, dtype=DT, requires_grad=True)
+    w = torch.randn(C, C, kh, kw, dtype=DT, requires_grad=True)
+    y = F.conv2d(x, w, None, 1, (ph, pw), (dh, dw_))
+    gy = torch.randn_like(y)
+    gx, gw = torch.autograd.grad(y, (x, w), gy)
+    phases, (Ho, Wo) = plans.conv_fwd_plan(H, W, kh, kw, 1, ph, pw, dh, dw_)
+    got = emulate_conv(phases, nhwc(x.detach()), ops.pack_conv_fwd(w.detach()), C, Ho, Wo, C)
+    torch.testing.assert_close(nchw(got), y.detach())
+    pd, _ = plans.conv_dgrad_plan_s1(H, W, kh, kw, ph, pw, dh, dw_)
+    got = emulate_conv(pd, nhwc(gy), ops.pack_conv_dgrad(w.detach()), C, H, W, C)
+    torch.testing.assert_close(nchw(got), gx)
+    wp = plans.conv_wgrad_plan(H, W, kh, kw, 1, ph, pw, dh, dw_)
+    dW = emulate_wgrad(wp, nhwc(x.detach()), C, nhwc(gy), C, 0)          # [T, ci, co]
+    torch.testing.assert_close(dW.permute(2, 1, 0).reshape(C, C, kh, kw), gw)
+
+
+@pytest.mark.parametrize("cin,cout", [(3, 16), (8, 24)])
+def test_downsampler_conv(cin, cout):
+    N, H, W = 2, 10, 12
+    cc = cout - cin
+    x = torch.randn(N, cin, H, W, dtype=DT, requires_grad=True)
+    w = torch.randn(cc, cin, 3, 3, dtype=DT, requires_grad=True)
+    y = F.conv2d(x, w, None, 2, 1)
+    gy = torch.randn_like(y)
+    gx, gw = torch.autograd.grad(y, (x, w), gy)
+    cin_g = plans.pad_to(cin, 4)
+    xp = F.pad(nhwc(x.detach()), (0, cin_g - cin))
+    phases, (Ho, Wo) = plans.conv_fwd_plan(H, W, 3, 3, 2, 1, 1, 1, 1)
+    got = emulate_conv(phases, xp, ops.pack_conv_fwd(w.detach(), cin_g), cin_g, Ho, Wo, cc)
+    torch.testing.assert_close(nchw(got), y.detach())
+    # input gradient = transposed-conv gather over the output gradient (4 phases)
+    pd, _ = plans.transposed_gather_plan(Ho, Wo, H, W, 3, 1)
+    wd = ops.pack_conv_dgrad(w.detach())
+    got = emulate_conv(pd, nhwc(gy), wd, cc, H, W, cin)
+    torch.testing.assert_close(nchw(got), gx)
+    wp = plans.conv_wgrad_plan(H, W, 3, 3, 2, 1, 1, 1, 1)
+    dW = emulate_wgrad(wp, xp, cin_g, nhwc(gy), cc, 0)[:, :cin]
+    torch.testing.assert_close(dW.permute(2, 1, 0).reshape(cc, cin, 3, 3), gw)
+
+
+def test_upsampler_convT():
+    N, ci, co, H, W = 2, 8, 4, 5, 6
+    x = torch.randn(N, ci, H, W, dtype=DT, requires_grad=True)
+    w = torch.randn(ci, co, 3, 3, dtype=DT, requires_grad=True)
+    y = F.conv_transpose2d(x, w, None, 2, 1, 1)
+    assert y.shape[2:] == (2 * H, 2 * W)
+    gy = torch.randn_like(y)
+    gx, gw = torch.autograd.grad(y, (x, w), gy)
+    phases, (Ho, Wo) = plans.transposed_gather_plan(H, W, 2 * H, 2 * W, 3, 1)
+    got = emulate_conv(phases, nhwc(x.detach()), ops.pack_convT_fwd(w.detach()), ci, Ho, Wo, co)
+    torch.testing.assert_close(nchw(got), y.detach())
+    pd, _ = plans.convT_dgrad_plan(2 * H, 2 * W, H, W, 3, 1)
+    got = emulate_conv(pd, nhwc(gy), ops.pack_convT_dgrad(w.detach()), co, H, W, ci)
+    torch.testing.assert_close(nchw(got), gx)
+    wp = plans.convT_wgrad_plan(H, W, 3, 1)
+    dW = emulate_wgrad(wp, nhwc(x.detach()), ci, nhwc(gy), co, 0)          # [T, ci, co]
+    torch.testing.assert_close(dW.permute(1, 2, 0).reshape(ci, co, 3, 3), gw)
+
+
+def test_wgrad_destination_strides_match_weight_layouts():
+    # (st, sp, sq) used by ops_net for Conv2d [Co,Ci,kh,kw] and ConvTranspose2d [Ci,Co,kh,kw]
+    Co, Ci, kh, kw = 5, 3, 3, 1
+    w = torch.arange(Co * Ci * kh * kw).reshape(Co, Ci, kh, kw)
+    st, sp, sq = 1, kh * kw, Ci * kh * kw
+    for t in range(kh * kw):
+        for ci in range(Ci):
+            for co in range(Co):
+                assert w.reshape(-1)[t * st + ci * sp + co * sq] == w[co, ci, t // kw, t % kw]
+    wT = torch.arange(Ci * Co * 9).reshape(Ci, Co, 3, 3)
+    st, sp, sq = 1, Co * 9, 9
+    for t in range(9):
+        for ci in range(Ci):
+            for co in range(Co):
+                assert wT.reshape(-1)[t * st + ci * sp + co * sq] == wT[ci, co, t // 3, t % 3]
