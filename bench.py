@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec (forward + backward) of the hot path
+ERFNet -> activation/mask -> weighted least squares -> backprojection loss.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels via the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+Workload (BASELINE.json configs[1]): egolane 2-lane, order 2, batch 32 per GPU, 256x512, fp32 I/O,
+model.train() with dropout, `zero_grad -> forward -> loss -> backward` (optimizer excluded).
+Multi-GPU = weak scaling: 32 images per GPU, per-replica BN statistics, one flat-gradient all-reduce
+(NCCL) per step inside the timed region.
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM.  `e2e`: through the public modules
+with HOST (pinned) inputs copied in every step and the loss read back every step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    1: dict(name="egolane_2lane_b1_256x512_fp32", nclasses=2, order=2, mask=0.3, resize=256, batch=1),
+    2: dict(name="egolane_2lane_b32_256x512_fp32", nclasses=2, order=2, mask=0.3, resize=256, batch=32),
+    3: dict(name="tusimple_4lane_b64_256x512", nclasses=4, order=3, mask=0.2, resize=256, batch=64),
+    4: dict(name="tusimple_4lane_b32pergpu_320x640", nclasses=4, order=3, mask=0.2, resize=320, batch=32),
+}
+FWD_GFLOP_PER_IMG = {(2, 256): 13.231, (4, 256): 13.239, (4, 320): 20.686, (2, 320): 20.673}
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            d["_source"] = "measured"
+            return d
+        except Exception:
+            pass
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_args(cfg, no_cuda=False):
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    argv = ["--image_dir", "x", "--gt_dir", "y", "--nclasses", str(cfg["nclasses"]), "--order", str(cfg["order"]),
+            "--batch_size", str(cfg["batch"]), "--mask_percentage", str(cfg["mask"]), "--resize", str(cfg["resize"]),
+            "--loss_policy", "backproject", "--end_to_end", "True"]
+    if no_cuda:
+        argv.append("--no_cuda")
+    return define_args().parse_args(argv)
+
+
+def host_batch(cfg, seed, pinned):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    B, R = cfg["batch"], cfg["resize"]
+    x = torch.rand(B, 3, R, 2 * R, generator=g)
+    xgt = torch.rand(B, 4, 56, generator=g, dtype=torch.float64) * 500.0
+    valid = torch.ones(B, 4, 56, dtype=torch.float64)
+    valid[:, :, :8] = 0
+    if pinned:
+        x, xgt, valid = x.pin_memory(), xgt.pin_memory(), valid.pin_memory()
+    return x, xgt, valid
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's CPU restatement of the reference path (kind "port";
+# the reference is Python and cannot travel to the GPU box)
+# ----------------------------------------------------------------------------------------------
+def cpu_port_run(cfg, steps, warmup, sample_images):
+    import torch
+    from oracle import erfnet_oracle as eo, lsq_oracle as lo, inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    L, order, R = cfg["nclasses"], cfg["order"], cfg["resize"]
+    Bs = max(1, min(cfg["batch"], sample_images))
+    P = {k[4:]: torch.from_numpy(v).requires_grad_(True) for k, v in inputs.make_erfnet_params(3, L, seed=0).items()}
+    M, Minv = lo.get_homography(R)
+    grid = lo.projective_grid(R, 2 * R, M.astype("float32"))
+    crit = lo.BackprojectionLoss(order, R, M=M, M_inv=Minv)
+    zero_rows = lo.mask_rows(R, cfg["mask"])
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(Bs, 3, R, 2 * R, generator=g)
+    xgt = torch.rand(Bs, 4, 56, generator=g, dtype=torch.float64) * 500.0
+    valid = torch.ones(Bs, 4, 56, dtype=torch.float64)
+    valid[:, :, :8] = 0
+    drop_p = {p: (0.03 if p.startswith("encoder.layers.") and int(p.split(".")[-1]) < 6 else 0.3) for p, _ in eo.ENC_NB}
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for p in P.values():
+            p.grad = None
+        masks = {k: (torch.rand(Bs, P[k + ".bn2.weight"].numel()) >= pr).float() / (1 - pr) for k, pr in drop_p.items()}
+        # masked rows are skipped (identical to multiplying by zero for finite grids; at resize 320 the
+        # reference itself yields NaN)
+        loss, _, _, _ = eo.full_step(x, P, grid, order, L, zero_rows, xgt, valid, drop_masks=masks, loss_obj=crit,
+                                     resize=R, skip_rows=zero_rows if R != 256 else 0)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return {"value": Bs / med, "unit": "images/sec", "cores": cores, "kind": "port",
+            "sample": "%d steps x %d images (of the %d-image batch), fwd+bwd fp32, torch-CPU oracle port of the "
+                      "reference modules, %d threads, median step %.3f s" % (steps, Bs, cfg["batch"], cores, med),
+            "ms_per_step": med * 1e3, "images_per_step": Bs}
+
+
+def run_reference_arm(a, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_port_run(cfg, a.steps, a.warmup, a.cpu_sample)
+    line = {"impl": "reference", "metric": "images/sec (fwd+bwd)", "value": r["value"], "unit": "images/sec",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "per_gpu_batch": cfg["batch"], "images_per_step": r["images_per_step"],
+                       "resolution": "%dx%d" % (cfg["resize"], 2 * cfg["resize"])},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(a, cfg):
+    import torch
+    import torch.distributed as dist
+    from lanedetection_end2end_b200 import _capi
+    from lanedetection_end2end_b200.Networks.LSQ_layer import Net
+    from lanedetection_end2end_b200.Networks.utils import define_init_weights
+    from lanedetection_end2end_b200.Loss_crit import backprojection_loss
+    from lanedetection_end2end_b200.ddp import FlatGradAllReduce, broadcast_parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _capi.lib()     # fail loudly if the extension is missing
+
+    args = build_args(cfg)
+    L, B = cfg["nclasses"], cfg["batch"]
+    torch.manual_seed(0)
+    model = Net(args)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        define_init_weights(model, "kaiming")
+    model = model.cuda().train()
+    model.defer_status_check = True
+    crit = backprojection_loss(args)
+    broadcast_parameters(model)
+    reducer = FlatGradAllReduce(model) if world > 1 else None
+
+    hx, hxgt, hvalid = host_batch(cfg, 1234 + rank, pinned=True)
+    dx, dxgt, dvalid = hx.to(dev), hxgt.to(dev), hvalid.to(dev)
+    gt_line = torch.zeros(B, 4)
+
+    def step(x, xgt, valid):
+        model.zero_grad(set_to_none=True)
+        out = model(x, gt_line, True)
+        loss = 0
+        for l in range(L):
+            ll, _ = crit(out[l], xgt[:, l], valid[:, l])
+            loss = loss + ll
+        loss = loss / L
+        loss.backward()
+        if reducer is not None:
+            reducer()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    for _ in range(max(a.warmup, 3)):
+        step(dx, dxgt, dvalid)
+    barrier()
+    st = int(model.lsq_status.item())
+    if st:
+        raise RuntimeError("LSQ status %d during warm-up" % st)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _capi.LAUNCHES
+    ms_dev = timed(lambda: step(dx, dxgt, dvalid), a.steps)
+    launches = (_capi.LAUNCHES - l0) // a.steps
+
+    def e2e_step():
+        x = hx.to(dev, non_blocking=True)
+        xgt = hxgt.to(dev, non_blocking=True)
+        valid = hvalid.to(dev, non_blocking=True)
+        loss = step(x, xgt, valid)
+        v = float(loss.item())           # D2H read of the step's result
+        if int(model.lsq_status.item()):
+            raise RuntimeError("singular normal matrix")
+        return v
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+    clocks = sampler.stop() if sampler is not None else None
+
+    # one traced step: CUDA events around every C-ABI launch on the launching stream
+    table, roofline, roofline_lsq = None, None, None
+    peaks = load_peaks()
+    if rank == 0:
+        _capi.TRACE = []
+        step(dx, dxgt, dvalid)
+        torch.cuda.synchronize()
+        trace, _capi.TRACE = _capi.TRACE, None
+        agg = {}
+        for name, e0, e1, flops, nbytes in trace:
+            d = agg.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0, "bytes": 0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        tot = sum(d["ms"] for d in agg.values())
+        table = {k: dict(v, share=v["ms"] / tot if tot else 0.0) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+        dom = next(iter(table))
+        d = table[dom]
+        if d["flops"] > 0:
+            ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            peak = peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None, "launches_per_step": d["launches"],
+                        "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["share"],
+                        "peak_source": peaks["_source"] + " (sustained dense bf16)"}
+        else:
+            ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            peak = peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"])
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": None, "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
+                        "share_of_step": d["share"], "peak_source": peaks["_source"]}
+        for k in ("lf_lsq_fwd", "lf_lsq_bwd"):
+            if k in table:
+                dd = table[k]
+                ach = dd["bytes"] / (dd["ms"] * 1e-3) / 1e9
+                roofline_lsq = roofline_lsq or {}
+                roofline_lsq[k] = {"bound": "hbm", "achieved": ach, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                   "frac": ach / peaks.get("hbm_gbs"), "avg_launch_ms": dd["ms"] / dd["launches"],
+                                   "note": "launch-latency regime at this size; see bench_lsq.py for the stress config"}
+        outdir = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(outdir):
+            json.dump(table, open(os.path.join(outdir, "kernel_table_n%d.json" % world), "w"), indent=1)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_port_run(cfg, 4, 1, a.cpu_sample)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        imgs = world * B * a.steps
+        h2d = hx.numel() * 4 + hxgt.numel() * 8 + hvalid.numel() * 8
+        gflop = FWD_GFLOP_PER_IMG.get((L, cfg["resize"]))
+        line = {"metric": "images/sec (fwd+bwd)", "value": imgs / (ms_dev * 1e-3), "unit": "images/sec",
+                "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": cfg["name"], "per_gpu_batch": B, "global_batch": world * B,
+                           "resolution": "%dx%d" % (cfg["resize"], 2 * cfg["resize"]), "nclasses": L,
+                           "order": cfg["order"], "parallelism": "dp%d" % world,
+                           "l2": "no flush needed: ~6 GB of activations per step >> 126 MB L2",
+                           "conv_mode": "fp32 FFMA (parity mode)", "init": "kaiming, torch.manual_seed(0)"},
+                "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / a.steps},
+                "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches,
+                "clocks": clocks,
+                "algorithmic_tflops": (3 * gflop * imgs / 1e3) / (ms_dev * 1e-3) if gflop else None,
+                "roofline": roofline, "roofline_lsq": roofline_lsq, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
+    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=8, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    cfg = dict(CONFIGS[a.config])
+    if a.batch:
+        cfg["batch"] = a.batch
+    if a.impl == "reference":
+        run_reference_arm(a, cfg)
+    else:
+        run_ours(a, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,61 @@ PROTOTYPES = {
                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
 }
 
+MAX_TAPS = 9
+
+_i = ctypes.c_int
+_p = ctypes.c_void_p
+
+
+class LfConvArgs(ctypes.Structure):
+    _fields_ = [("inp", _p), ("wmat", _p), ("bias", _p), ("out", _p), ("mask_src", _p), ("add_src", _p),
+                ("add_mask", _p),
+                ("N", _i), ("Hin", _i), ("Win", _i), ("Cin", _i), ("in_cstride", _i),
+                ("Hout", _i), ("Wout", _i), ("out_cstride", _i), ("out_coff", _i), ("Cout", _i), ("CoutPad", _i),
+                ("Hs", _i), ("Ws", _i), ("osy", _i), ("osx", _i), ("oy0", _i), ("ox0", _i), ("isy", _i), ("isx", _i),
+                ("ntaps", _i), ("dy", _i * MAX_TAPS), ("dx", _i * MAX_TAPS), ("wtap", _i * MAX_TAPS),
+                ("relu", _i)]
+
+
+class LfWgradArgs(ctypes.Structure):
+    _fields_ = [("P", _p), ("Q", _p), ("partial", _p), ("qsum_partial", _p),
+                ("N", _i), ("Hs", _i), ("Ws", _i),
+                ("Hp", _i), ("Wp", _i), ("Cp", _i), ("p_cstride", _i), ("p_coff", _i), ("psy", _i), ("psx", _i),
+                ("Hq", _i), ("Wq", _i), ("Cq", _i), ("q_cstride", _i), ("q_coff", _i), ("qsy", _i), ("qsx", _i),
+                ("ntaps", _i), ("pdy", _i * MAX_TAPS), ("pdx", _i * MAX_TAPS), ("qdy", _i * MAX_TAPS),
+                ("qdx", _i * MAX_TAPS),
+                ("CpPad", _i), ("CqPad", _i), ("nsplit", _i)]
+
+
+_NET_PROTOS = {
+    "lf_conv_f32": (_i, [ctypes.POINTER(LfConvArgs), _p]),
+    "lf_wgrad_f32": (_i, [ctypes.POINTER(LfWgradArgs), _p]),
+    "lf_wgrad_reduce": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p]),
+    "lf_vec_reduce": (_i, [_p, _i, _i, _i, _p, _p]),
+    "lf_colsum_blocks": (_i, [ctypes.c_longlong]),
+    "lf_colsum": (_i, [_p, ctypes.c_longlong, _i, _i, _i, _p, _i, _p]),
+    "lf_maxpool2_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "lf_maxpool2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p]),
+    "lf_bn_blocks": (_i, [ctypes.c_longlong, _i]),
+    "lf_bn_stats": (_i, [_p, ctypes.c_longlong, _i, _p, _p]),
+    "lf_bn_finalize": (_i, [_p, _i, ctypes.c_longlong, _i, _p, _p, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p, _p,
+                            _p, _p]),
+    "lf_bn_eval_prepare": (_i, [_i, _p, _p, ctypes.c_float, _p, _p, _p, _p, _p]),
+    "lf_bn_apply": (_i, [_p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
+    "lf_bn_bwd_reduce": (_i, [_p, _p, _p, _p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p]),
+    "lf_bn_bwd_finalize": (_i, [_p, _i, ctypes.c_longlong, _i, _p, _p, _p, _p, _p]),
+    "lf_bn_bwd_apply": (_i, [_p, _p, _p, _p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "lf_outconv_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "lf_outconv_bwd_data": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "lf_outconv_wgrad_blocks": (_i, [ctypes.c_longlong]),
+    "lf_outconv_bwd_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "lf_nchw_to_nhwc_pad": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "lf_nhwc_to_nchw": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "lf_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+}
+PROTOTYPES.update(_NET_PROTOS)
+
+
 _lib = None
 
 
@@ -68,6 +123,28 @@ def check(rc, what):
         if rc == -4:
             msg += ": " + h.lf_last_cuda_error().decode()
         raise LanefitError("%s failed: %s (code %d)" % (what, msg, rc))
+
+
+LAUNCHES = 0          # kernels launched through the C ABI since import (every call below = 1 launch)
+TRACE = None          # set to a list to record (name, start_event, end_event, flops, bytes) per launch
+
+
+def call(name, *args, flops=0, nbytes=0):
+    """Invoke one launching entry point: counts it, optionally brackets it with CUDA events on
+    the current stream (bench.py's per-kernel roofline), and raises on a non-zero return."""
+    global LAUNCHES
+    fn = getattr(lib(), name)
+    if TRACE is None:
+        rc = fn(*args)
+    else:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        TRACE.append((name, e0, e1, flops, nbytes))
+    LAUNCHES += 1
+    check(rc, name)
 
 
 def ptr(t):

@@ -86,12 +86,13 @@ class LsqFunction(torch.autograd.Function):
         status = status_out if status_out is not None else torch.zeros(1, dtype=torch.int32, device=dev)
         nbytes = h.lf_lsq_workspace_bytes(B, L, H, W, order)
         ws = _workspace(dev, nbytes)
+        esz = o.element_size()
         with torch.cuda.device(dev):
-            rc = h.lf_lsq_fwd(_capi.ptr(o), _capi.dtype_id(o), _capi.ptr(tables.xtab), _capi.ptr(tables.ytab),
-                              _capi.ptr(tables.yrow), B, L, H, W, order, mask_rows, act, float(reg_ls), solver,
-                              _capi.ptr(beta), _capi.ptr(zinv), _capi.ptr(masked), _capi.ptr(status),
-                              _capi.ptr(ws), ws.numel(), _capi.stream_ptr())
-        _capi.check(rc, "lf_lsq_fwd")
+            _capi.call("lf_lsq_fwd", _capi.ptr(o), _capi.dtype_id(o), _capi.ptr(tables.xtab), _capi.ptr(tables.ytab),
+                       _capi.ptr(tables.yrow), B, L, H, W, order, mask_rows, act, float(reg_ls), solver,
+                       _capi.ptr(beta), _capi.ptr(zinv), _capi.ptr(masked), _capi.ptr(status),
+                       _capi.ptr(ws), ws.numel(), _capi.stream_ptr(),
+                       nbytes=B * L * H * W * (esz + (4 if want_masked else 0)))
         if status_out is None:
             # same implicit sync + RuntimeError as torch.inverse in the reference
             # (BP/Networks/LSQ_layer.py:114, caught at BP/main.py:289-292)
@@ -114,12 +115,11 @@ class LsqFunction(torch.autograd.Function):
         B, L, H, W = o.shape
         gbeta = gbeta.to(torch.float64).contiguous()
         d_o = torch.empty_like(o)
-        h = _capi.lib()
         with torch.cuda.device(o.device):
-            rc = h.lf_lsq_bwd(_capi.ptr(o), _capi.dtype_id(o), _capi.ptr(t.xtab), _capi.ptr(t.ytab), _capi.ptr(t.yrow),
-                              B, L, H, W, order, mask_rows, act, _capi.ptr(beta), _capi.ptr(zinv), _capi.ptr(gbeta),
-                              _capi.ptr(d_o), _capi.stream_ptr())
-        _capi.check(rc, "lf_lsq_bwd")
+            _capi.call("lf_lsq_bwd", _capi.ptr(o), _capi.dtype_id(o), _capi.ptr(t.xtab), _capi.ptr(t.ytab),
+                       _capi.ptr(t.yrow), B, L, H, W, order, mask_rows, act, _capi.ptr(beta), _capi.ptr(zinv),
+                       _capi.ptr(gbeta), _capi.ptr(d_o), _capi.stream_ptr(),
+                       nbytes=2 * B * L * H * W * o.element_size())
         return d_o, None, None, None, None, None, None, None, None
 
 

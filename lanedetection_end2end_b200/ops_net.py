@@ -16,61 +16,9 @@ import torch
 from . import _capi
 from . import net_plans as plans
 
-MAX_TAPS = 9
 BN_EPS = 1e-3
 BN_MOMENTUM = 0.1
-
-_i = ctypes.c_int
-_p = ctypes.c_void_p
-
-
-class LfConvArgs(ctypes.Structure):
-    _fields_ = [("inp", _p), ("wmat", _p), ("bias", _p), ("out", _p), ("mask_src", _p), ("add_src", _p),
-                ("add_mask", _p),
-                ("N", _i), ("Hin", _i), ("Win", _i), ("Cin", _i), ("in_cstride", _i),
-                ("Hout", _i), ("Wout", _i), ("out_cstride", _i), ("out_coff", _i), ("Cout", _i), ("CoutPad", _i),
-                ("Hs", _i), ("Ws", _i), ("osy", _i), ("osx", _i), ("oy0", _i), ("ox0", _i), ("isy", _i), ("isx", _i),
-                ("ntaps", _i), ("dy", _i * MAX_TAPS), ("dx", _i * MAX_TAPS), ("wtap", _i * MAX_TAPS),
-                ("relu", _i)]
-
-
-class LfWgradArgs(ctypes.Structure):
-    _fields_ = [("P", _p), ("Q", _p), ("partial", _p), ("qsum_partial", _p),
-                ("N", _i), ("Hs", _i), ("Ws", _i),
-                ("Hp", _i), ("Wp", _i), ("Cp", _i), ("p_cstride", _i), ("p_coff", _i), ("psy", _i), ("psx", _i),
-                ("Hq", _i), ("Wq", _i), ("Cq", _i), ("q_cstride", _i), ("q_coff", _i), ("qsy", _i), ("qsx", _i),
-                ("ntaps", _i), ("pdy", _i * MAX_TAPS), ("pdx", _i * MAX_TAPS), ("qdy", _i * MAX_TAPS),
-                ("qdx", _i * MAX_TAPS),
-                ("CpPad", _i), ("CqPad", _i), ("nsplit", _i)]
-
-
-_NET_PROTOS = {
-    "lf_conv_f32": (_i, [ctypes.POINTER(LfConvArgs), _p]),
-    "lf_wgrad_f32": (_i, [ctypes.POINTER(LfWgradArgs), _p]),
-    "lf_wgrad_reduce": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p]),
-    "lf_vec_reduce": (_i, [_p, _i, _i, _i, _p, _p]),
-    "lf_colsum_blocks": (_i, [ctypes.c_longlong]),
-    "lf_colsum": (_i, [_p, ctypes.c_longlong, _i, _i, _i, _p, _i, _p]),
-    "lf_maxpool2_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
-    "lf_maxpool2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p]),
-    "lf_bn_blocks": (_i, [ctypes.c_longlong, _i]),
-    "lf_bn_stats": (_i, [_p, ctypes.c_longlong, _i, _p, _p]),
-    "lf_bn_finalize": (_i, [_p, _i, ctypes.c_longlong, _i, _p, _p, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p, _p,
-                            _p, _p]),
-    "lf_bn_eval_prepare": (_i, [_i, _p, _p, ctypes.c_float, _p, _p, _p, _p, _p]),
-    "lf_bn_apply": (_i, [_p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
-    "lf_bn_bwd_reduce": (_i, [_p, _p, _p, _p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p]),
-    "lf_bn_bwd_finalize": (_i, [_p, _i, ctypes.c_longlong, _i, _p, _p, _p, _p, _p]),
-    "lf_bn_bwd_apply": (_i, [_p, _p, _p, _p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
-    "lf_outconv_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
-    "lf_outconv_bwd_data": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
-    "lf_outconv_wgrad_blocks": (_i, [ctypes.c_longlong]),
-    "lf_outconv_bwd_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
-    "lf_nchw_to_nhwc_pad": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
-    "lf_nhwc_to_nchw": (_i, [_p, _i, _i, _i, _i, _p, _p]),
-    "lf_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
-}
-_capi.PROTOTYPES.update(_NET_PROTOS)
+LfConvArgs, LfWgradArgs = _capi.LfConvArgs, _capi.LfWgradArgs
 
 ptr = _capi.ptr
 
@@ -152,7 +100,9 @@ def run_conv(phases, x, wmat, cin, out, cout, out_coff=0, bias=None, relu=False,
         a.ntaps = len(taps)
         for t, (dy, dx, slot) in enumerate(taps):
             a.dy[t], a.dx[t], a.wtap[t] = dy, dx, slot
-        _capi.check(h.lf_conv_f32(ctypes.byref(a), st), "lf_conv_f32")
+        _capi.call("lf_conv_f32", ctypes.byref(a), st,
+                   flops=2 * N * ph["Hs"] * ph["Ws"] * len(taps) * cin * cout,
+                   nbytes=4 * N * ph["Hs"] * ph["Ws"] * (cin + cout))
     return out
 
 
@@ -190,12 +140,12 @@ def run_wgrad(plan, P, cp, Q, cq, q_coff, N, dst_w, layout, dst_b=None, cp_true=
         qpart = torch.empty(a.nsplit * a.CqPad, dtype=torch.float32, device=P.device)
         a.qsum_partial = qpart.data_ptr()
     st = _stream()
-    _capi.check(h.lf_wgrad_f32(ctypes.byref(a), st), "lf_wgrad_f32")
+    _capi.call("lf_wgrad_f32", ctypes.byref(a), st, flops=2 * M * ntaps * cp * cq, nbytes=4 * M * (cp + cq))
     s_t, s_p, s_q = layout
-    _capi.check(h.lf_wgrad_reduce(ptr(partial), a.nsplit, ntaps, cp_true or cp, cq_true or cq, a.CpPad, a.CqPad,
-                                  ptr(dst_w), s_t, s_p, s_q, st), "lf_wgrad_reduce")
+    _capi.call("lf_wgrad_reduce", ptr(partial), a.nsplit, ntaps, cp_true or cp, cq_true or cq, a.CpPad, a.CqPad,
+                                  ptr(dst_w), s_t, s_p, s_q, st)
     if dst_b is not None:
-        _capi.check(h.lf_vec_reduce(ptr(qpart), a.nsplit, cq_true or cq, a.CqPad, ptr(dst_b), st), "lf_vec_reduce")
+        _capi.call("lf_vec_reduce", ptr(qpart), a.nsplit, cq_true or cq, a.CqPad, ptr(dst_b), st)
 
 
 def run_colsum(src, C, coff, dst):
@@ -206,8 +156,8 @@ def run_colsum(src, C, coff, dst):
     cpad = plans.pad_to(C, 4)
     part = torch.empty(nblk * cpad, dtype=torch.float32, device=src.device)
     st = _stream()
-    _capi.check(h.lf_colsum(ptr(src), npix, C, src.shape[-1], coff, ptr(part), cpad, st), "lf_colsum")
-    _capi.check(h.lf_vec_reduce(ptr(part), nblk, C, cpad, ptr(dst), st), "lf_vec_reduce")
+    _capi.call("lf_colsum", ptr(src), npix, C, src.shape[-1], coff, ptr(part), cpad, st)
+    _capi.call("lf_vec_reduce", ptr(part), nblk, C, cpad, ptr(dst), st)
 
 
 class BNState:
@@ -228,13 +178,13 @@ def bn_forward_stats(x, gamma, beta, running_mean, running_var, training):
     if training:
         nblk = h.lf_bn_blocks(npix, C)
         part = torch.empty(nblk * 2 * C, dtype=torch.float64, device=x.device)
-        _capi.check(h.lf_bn_stats(ptr(x), npix, C, ptr(part), st), "lf_bn_stats")
-        _capi.check(h.lf_bn_finalize(ptr(part), nblk, npix, C, ptr(gamma), ptr(beta), BN_EPS, BN_MOMENTUM,
+        _capi.call("lf_bn_stats", ptr(x), npix, C, ptr(part), st)
+        _capi.call("lf_bn_finalize", ptr(part), nblk, npix, C, ptr(gamma), ptr(beta), BN_EPS, BN_MOMENTUM,
                                      ptr(running_mean), ptr(running_var), ptr(s.mean), ptr(s.invstd), ptr(s.scale),
-                                     ptr(s.shift), st), "lf_bn_finalize")
+                                     ptr(s.shift), st)
     else:
-        _capi.check(h.lf_bn_eval_prepare(C, ptr(gamma), ptr(beta), BN_EPS, ptr(running_mean), ptr(running_var),
-                                         ptr(s.scale), ptr(s.shift), st), "lf_bn_eval_prepare")
+        _capi.call("lf_bn_eval_prepare", C, ptr(gamma), ptr(beta), BN_EPS, ptr(running_mean), ptr(running_var),
+                                         ptr(s.scale), ptr(s.shift), st)
     return s
 
 
@@ -244,8 +194,8 @@ def bn_apply(x, s, relu, drop=None, res=None):
     npix = x.numel() // C
     y = torch.empty_like(x)
     ppi = x.shape[1] * x.shape[2]
-    _capi.check(h.lf_bn_apply(ptr(x), npix, C, ppi, ptr(s.scale), ptr(s.shift), ptr(drop), ptr(res), int(relu), ptr(y),
-                              _stream()), "lf_bn_apply")
+    _capi.call("lf_bn_apply", ptr(x), npix, C, ppi, ptr(s.scale), ptr(s.shift), ptr(drop), ptr(res), int(relu), ptr(y),
+                              _stream())
     return y
 
 
@@ -258,15 +208,14 @@ def bn_backward(dy, ymask, drop, x, s, gamma):
     st = _stream()
     nblk = h.lf_bn_blocks(npix, C)
     part = torch.empty(nblk * 2 * C, dtype=torch.float64, device=x.device)
-    _capi.check(h.lf_bn_bwd_reduce(ptr(dy), ptr(ymask), ptr(drop), ptr(x), npix, C, ppi, ptr(s.mean), ptr(s.invstd),
-                                   ptr(part), st), "lf_bn_bwd_reduce")
+    _capi.call("lf_bn_bwd_reduce", ptr(dy), ptr(ymask), ptr(drop), ptr(x), npix, C, ppi, ptr(s.mean), ptr(s.invstd),
+                                   ptr(part), st)
     buf = torch.empty(4, C, dtype=torch.float32, device=x.device)
     dgamma, dbeta, c1, c2 = buf[0], buf[1], buf[2], buf[3]
-    _capi.check(h.lf_bn_bwd_finalize(ptr(part), nblk, npix, C, ptr(dgamma), ptr(dbeta), ptr(c1), ptr(c2), st),
-                "lf_bn_bwd_finalize")
+    _capi.call("lf_bn_bwd_finalize", ptr(part), nblk, npix, C, ptr(dgamma), ptr(dbeta), ptr(c1), ptr(c2), st)
     dx = torch.empty_like(x)
-    _capi.check(h.lf_bn_bwd_apply(ptr(dy), ptr(ymask), ptr(drop), ptr(x), npix, C, ppi, ptr(s.mean), ptr(s.invstd),
-                                  ptr(gamma), ptr(c1), ptr(c2), ptr(dx), st), "lf_bn_bwd_apply")
+    _capi.call("lf_bn_bwd_apply", ptr(dy), ptr(ymask), ptr(drop), ptr(x), npix, C, ppi, ptr(s.mean), ptr(s.invstd),
+                                  ptr(gamma), ptr(c1), ptr(c2), ptr(dx), st)
     return dx, dgamma, dbeta
 
 
@@ -293,7 +242,7 @@ class DownFunction(torch.autograd.Function):
         phases, (Ho, Wo) = plans.conv_fwd_plan(H, W, 3, 3, 2, 1, 1, 1, 1)
         cat = _empty((N, Ho, Wo, cout), x)
         run_conv(phases, x, wmat, cin_gemm, cat, cc, 0, bias=b)
-        _capi.check(h.lf_maxpool2_fwd(ptr(x), N, H, W, cin, cx, ptr(cat), cout, cc, _stream()), "lf_maxpool2_fwd")
+        _capi.call("lf_maxpool2_fwd", ptr(x), N, H, W, cin, cx, ptr(cat), cout, cc, _stream())
         s = bn_forward_stats(cat, gamma, beta, rm, rv, training)
         y = bn_apply(cat, s, relu=True)
         ctx.save_for_backward(x, w, cat, y, gamma, s.mean, s.invstd)
@@ -326,8 +275,7 @@ class DownFunction(torch.autograd.Function):
             wd = pack_conv_dgrad(w)                      # [9, cc, cinPad]
             phases, _ = plans.transposed_gather_plan(dcat.shape[1], dcat.shape[2], H, W, 3, 1)
             run_conv(phases, dcat, wd, cc, dx, cin, 0)
-            _capi.check(h.lf_maxpool2_bwd(ptr(x), N, H, W, cin, cx, ptr(dcat), cout, cc, ptr(dx), cx, 1, _stream()),
-                        "lf_maxpool2_bwd")
+            _capi.call("lf_maxpool2_bwd", ptr(x), N, H, W, cin, cx, ptr(dcat), cout, cc, ptr(dx), cx, 1, _stream())
         return dx, None, dw, db, dgamma, dbeta, None, None, None, None
 
 
@@ -443,8 +391,7 @@ class OutConvFunction(torch.autograd.Function):
         N, H, W, ci = x.shape
         L = w.shape[1]
         out = _empty((N, L, 2 * H, 2 * W), x)
-        _capi.check(h.lf_outconv_fwd(ptr(x), ptr(w.contiguous()), ptr(b), N, H, W, ci, L, ptr(out), _stream()),
-                    "lf_outconv_fwd")
+        _capi.call("lf_outconv_fwd", ptr(x), ptr(w.contiguous()), ptr(b), N, H, W, ci, L, ptr(out), _stream())
         ctx.save_for_backward(x, w)
         return out
 
@@ -457,14 +404,13 @@ class OutConvFunction(torch.autograd.Function):
         L = w.shape[1]
         st = _stream()
         dx = torch.empty_like(x)
-        _capi.check(h.lf_outconv_bwd_data(ptr(dout), ptr(w.contiguous()), N, H, W, ci, L, ptr(dx), st),
-                    "lf_outconv_bwd_data")
+        _capi.call("lf_outconv_bwd_data", ptr(dout), ptr(w.contiguous()), N, H, W, ci, L, ptr(dx), st)
         nblk = h.lf_outconv_wgrad_blocks(N * H * W)
         width = ci * L * 4 + L
         part = torch.empty(nblk * width, dtype=torch.float32, device=x.device)
-        _capi.check(h.lf_outconv_bwd_weight(ptr(x), ptr(dout), N, H, W, ci, L, ptr(part), st), "lf_outconv_bwd_weight")
+        _capi.call("lf_outconv_bwd_weight", ptr(x), ptr(dout), N, H, W, ci, L, ptr(part), st)
         red = _empty((width,), x)
-        _capi.check(h.lf_vec_reduce(ptr(part), nblk, width, width, ptr(red), st), "lf_vec_reduce")
+        _capi.call("lf_vec_reduce", ptr(part), nblk, width, width, ptr(red), st)
         dw = red[:ci * L * 4].view(ci, L, 2, 2)
         db = red[ci * L * 4:]
         return dx, dw, db
@@ -479,7 +425,7 @@ def image_to_nhwc_pad(x, cpad):
     x = x.contiguous().float()
     N, C, H, W = x.shape
     out = _empty((N, H, W, cpad), x)
-    _capi.check(_lib().lf_nchw_to_nhwc_pad(ptr(x), N, C, H, W, cpad, ptr(out), _stream()), "lf_nchw_to_nhwc_pad")
+    _capi.call("lf_nchw_to_nhwc_pad", ptr(x), N, C, H, W, cpad, ptr(out), _stream())
     return out
 
 
@@ -492,7 +438,7 @@ class ToNHWC(torch.autograd.Function):
         x = x.contiguous()
         N, C, H, W = x.shape
         out = _empty((N, H, W, C), x)
-        _capi.check(_lib().lf_nchw_to_nhwc(ptr(x), N, C, H, W, ptr(out), _stream()), "lf_nchw_to_nhwc")
+        _capi.call("lf_nchw_to_nhwc", ptr(x), N, C, H, W, ptr(out), _stream())
         return out
 
     @staticmethod
@@ -500,7 +446,7 @@ class ToNHWC(torch.autograd.Function):
         g = g.contiguous()
         N, H, W, C = g.shape
         out = _empty((N, C, H, W), g)
-        _capi.check(_lib().lf_nhwc_to_nchw(ptr(g), N, H, W, C, ptr(out), _stream()), "lf_nhwc_to_nchw")
+        _capi.call("lf_nhwc_to_nchw", ptr(g), N, H, W, C, ptr(out), _stream())
         return out
 
 

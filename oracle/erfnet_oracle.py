@@ -22,16 +22,14 @@ ENC_NB += [("encoder.layers.%d" % (7 + i), d) for i, d in enumerate([2, 4, 8, 16
 
 
 def _bn(x, P, prefix, training, taps, stats_out=None):
+    """nn.BatchNorm2d(eps=1e-3) forward: batch statistics in training mode (the functional form of
+    what the reference's modules call), running statistics otherwise."""
     w, b = P[prefix + ".weight"], P[prefix + ".bias"]
     if training:
-        mean = x.mean(dim=(0, 2, 3))
-        var = x.var(dim=(0, 2, 3), unbiased=False)
         if stats_out is not None:
-            stats_out[prefix] = (mean.detach(), x.var(dim=(0, 2, 3), unbiased=True).detach())
-    else:
-        mean, var = P[prefix + ".running_mean"], P[prefix + ".running_var"]
-    inv = torch.rsqrt(var + BN_EPS)
-    return (x - mean[None, :, None, None]) * (inv * w)[None, :, None, None] + b[None, :, None, None]
+            stats_out[prefix] = (x.detach().mean(dim=(0, 2, 3)), x.detach().var(dim=(0, 2, 3), unbiased=True))
+        return F.batch_norm(x, None, None, w, b, True, 0.1, BN_EPS)
+    return F.batch_norm(x, P[prefix + ".running_mean"], P[prefix + ".running_var"], w, b, False, 0.1, BN_EPS)
 
 
 def downsampler(x, P, prefix, training=True, taps=None, stats_out=None):

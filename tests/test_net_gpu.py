@@ -1,0 +1,301 @@
+"""GPU parity of the ERFNet blocks and of the whole hot path (ERFNet -> LSQ -> loss, forward
+and backward) through the reference-mirroring modules, against the torch-CPU oracle and the
+committed golden outputs of the reference itself.
+
+fp32 "parity mode" kernels (CUDA-core FFMA): block-level gate 1e-4 norm-wise (typically 1e-6).
+Whole-path gate vs the reference: |ours - fp64| <= |ref32 - fp64| * 4 + 1e-4.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inputs, lsq_oracle as lo, erfnet_oracle as eo
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def rel(a, b):
+    a = a.detach().double().cpu() if torch.is_tensor(a) else torch.as_tensor(a, dtype=torch.float64)
+    b = b.detach().double().cpu() if torch.is_tensor(b) else torch.as_tensor(b, dtype=torch.float64)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def E():
+    from lanedetection_end2end_b200.Networks import ERFNet
+    return ERFNet
+
+
+def load_params(module, P, prefix):
+    sd = module.state_dict()
+    for k in sd:
+        key = prefix + "." + k if prefix else k
+        if key in P:
+            sd[k] = P[key].detach().clone()
+    module.load_state_dict(sd)
+
+
+def oracle_params(names_prefix, P_np, dtype=torch.float64):
+    return {k: torch.from_numpy(v).to(dtype).requires_grad_(True) for k, v in P_np.items() if k.startswith(names_prefix)}
+
+
+def run_block(block, x_nchw, gy_seed=0):
+    x = x_nchw.cuda().requires_grad_(True)
+    y = block(x)
+    g = torch.Generator().manual_seed(gy_seed)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy.cuda())
+    return y, x.grad, gy
+
+
+def check_grads(block, oracle_P, prefix, tol=TOL):
+    for n, p in block.named_parameters():
+        ref = oracle_P[prefix + "." + n].grad
+        scale = max(float(ref.abs().max()), 1e-3 * max(float(q.grad.abs().max()) for q in oracle_P.values()
+                                                        if q.grad is not None))
+        err = float((p.grad.double().cpu() - ref).abs().max())
+        assert err <= tol * scale, (n, err, scale)
+
+
+@pytest.mark.parametrize("cin,cout,H,W", [(3, 16, 32, 48), (16, 64, 16, 24), (64, 128, 8, 12)])
+def test_downsampler_block(cin, cout, H, W):
+    torch.manual_seed(1)
+    P_np = {k[4:]: v for k, v in inputs.make_erfnet_params(3, 2, seed=5).items()}
+    prefix = {3: "encoder.initial_block", 16: "encoder.layers.0", 64: "encoder.layers.6"}[cin]
+    blk = E().DownsamplerBlock(cin, cout).cuda().train()
+    P = oracle_params(prefix, P_np)
+    load_params(blk, {k: v.float() for k, v in P.items()}, prefix)
+    x = torch.randn(3, cin, H, W)
+    if cin == 3:
+        xg = x.cuda()
+        y = blk(xg)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(0))
+        y.backward(gy.cuda())
+        gx = None
+    else:
+        y, gx, gy = run_block(blk, x)
+    x64 = x.double().requires_grad_(True)
+    stats = {}
+    yo = eo.downsampler(x64, P, prefix, True, stats_out=stats)
+    yo.backward(gy.double())
+    assert rel(y, yo) <= TOL
+    if gx is not None:
+        assert rel(gx, x64.grad) <= TOL
+    check_grads(blk, P, prefix)
+    mean, var = stats[prefix + ".bn"]
+    assert rel(blk.bn.running_mean, 0.1 * mean) <= TOL
+    assert rel(blk.bn.running_var, 0.9 + 0.1 * var) <= TOL
+    assert int(blk.bn.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("C,dil,H,W,drop", [(64, 1, 16, 24, True), (128, 2, 8, 16, False), (128, 16, 32, 64, True),
+                                            (128, 8, 8, 16, False), (16, 1, 24, 40, False)])
+def test_non_bottleneck_1d_block(C, dil, H, W, drop):
+    P_np = {k[4:]: v for k, v in inputs.make_erfnet_params(3, 2, seed=6).items()}
+    prefix = {64: "encoder.layers.1", 128: "encoder.layers.7", 16: "decoder.layers.4"}[C]
+    blk = E().non_bottleneck_1d(C, 0.3 if drop else 0.0, dil).cuda().train()
+    P = oracle_params(prefix, P_np)
+    load_params(blk, {k: v.float() for k, v in P.items()}, prefix)
+    N = 3
+    mask = None
+    if drop:
+        keep = (torch.rand(N, C, generator=torch.Generator().manual_seed(2)) >= 0.3).float() / 0.7
+        blk.drop_mask_override = keep
+        mask = keep.double()
+    x = torch.randn(N, C, H, W, generator=torch.Generator().manual_seed(3))
+    y, gx, gy = run_block(blk, x)
+    x64 = x.double().requires_grad_(True)
+    yo = eo.non_bottleneck_1d(x64, P, prefix, dil, True, mask)
+    yo.backward(gy.double())
+    assert rel(y, yo) <= TOL
+    assert rel(gx, x64.grad) <= TOL
+    check_grads(blk, P, prefix)
+
+
+@pytest.mark.parametrize("ci,co,H,W", [(128, 64, 8, 12), (64, 16, 12, 20)])
+def test_upsampler_block(ci, co, H, W):
+    P_np = {k[4:]: v for k, v in inputs.make_erfnet_params(3, 2, seed=7).items()}
+    prefix = {128: "decoder.layers.0", 64: "decoder.layers.3"}[ci]
+    blk = E().UpsamplerBlock(ci, co).cuda().train()
+    P = oracle_params(prefix, P_np)
+    load_params(blk, {k: v.float() for k, v in P.items()}, prefix)
+    x = torch.randn(2, ci, H, W, generator=torch.Generator().manual_seed(4))
+    y, gx, gy = run_block(blk, x)
+    x64 = x.double().requires_grad_(True)
+    yo = eo.upsampler(x64, P, prefix, True)
+    yo.backward(gy.double())
+    assert y.shape == yo.shape
+    assert rel(y, yo) <= TOL
+    assert rel(gx, x64.grad) <= TOL
+    check_grads(blk, P, prefix)
+
+
+@pytest.mark.parametrize("L", [2, 4, 5])
+def test_output_conv(L):
+    import torch.nn.functional as F
+    blk = E()._OutputConvT(16, L, 2, stride=2, padding=0, output_padding=0, bias=True).cuda()
+    x = torch.randn(2, 16, 12, 20)
+    y, gx, gy = run_block(blk, x)
+    assert y.is_contiguous() and y.shape == (2, L, 24, 40)
+    x64 = x.double().requires_grad_(True)
+    w, b = blk.weight.detach().double().cpu().requires_grad_(True), blk.bias.detach().double().cpu().requires_grad_(True)
+    yo = F.conv_transpose2d(x64, w, b, stride=2)
+    yo.backward(gy.double())
+    assert rel(y, yo) <= TOL and rel(gx, x64.grad) <= TOL
+    assert rel(blk.weight.grad, w.grad) <= TOL and rel(blk.bias.grad, b.grad) <= TOL
+
+
+def _build_net(L, order, mask_pct, B):
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    from lanedetection_end2end_b200.Networks.LSQ_layer import Net
+    args = define_args().parse_args(["--image_dir", "x", "--gt_dir", "y", "--nclasses", str(L), "--order", str(order),
+                                     "--batch_size", str(B), "--mask_percentage", str(mask_pct),
+                                     "--loss_policy", "backproject"])
+    return Net(args), args
+
+
+@pytest.mark.parametrize("name", ["net_l2_d2", "net_l4_d3"])
+def test_full_path_matches_reference_golden(name):
+    """ERFNet -> activation -> mask -> LSQ -> backprojection loss, forward + backward, through the
+    same calls the reference's main.py makes (BP/main.py:286-305,338-339), vs the golden outputs
+    of the reference itself."""
+    from lanedetection_end2end_b200.Loss_crit import backprojection_loss
+    g = load(name)
+    meta = json.loads(str(g["meta"]))
+    L, order, B = meta["L"], meta["order"], meta["B"]
+    model, args = _build_net(L, order, meta["mask_pct"], B)
+    P_np = inputs.make_erfnet_params(3, L, seed=meta["param_seed"])
+    sd = model.state_dict()
+    for k, v in P_np.items():
+        sd[k] = torch.from_numpy(v)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    for m in model.modules():
+        if hasattr(m, "dropout"):
+            m.dropout.p = 0
+    # the grid must be bit-identical to the reference's (same torch ops on the same cv2 homography)
+    np.testing.assert_array_equal(model.grid[0].cpu().numpy(), load("lsq_bp_l2_d2")["grid0"])
+    x = torch.from_numpy(inputs.make_images(B, 256, 512, seed=meta["image_seed"])).cuda()
+    xgt_np, valid_np = inputs.make_loss_targets(B, 4, seed=meta["target_seed"])
+    xgt, valid = torch.from_numpy(xgt_np).cuda(), torch.from_numpy(valid_np).cuda()
+    taps = {}
+    hooks = []
+    mods = {"encoder.initial_block": model.net.encoder.initial_block, "decoder.output_conv": model.net.decoder.output_conv}
+    mods.update({"encoder.layers.%d" % i: l for i, l in enumerate(model.net.encoder.layers)})
+    mods.update({"decoder.layers.%d" % i: l for i, l in enumerate(model.net.decoder.layers)})
+    for n, mod in mods.items():
+        hooks.append(mod.register_forward_hook(lambda _m, _i, o, n=n: taps.__setitem__(n, o)))
+    out = model(x, torch.zeros(B, 4), True)
+    for h in hooks:
+        h.remove()
+    betas = [b for b in out[:4] if b is not None]
+    assert len(betas) == L and betas[0].dtype == torch.float64 and betas[0].shape == (B, order + 1, 1)
+    crit = backprojection_loss(args)
+    total = 0
+    for l in range(L):
+        ll, _ = crit(betas[l], xgt[:, l], valid[:, l])
+        total = total + ll
+    loss = total / L
+    loss.backward()
+
+    def gate(ours, key_stem, what):
+        v64, v32 = g[key_stem.replace("{}", "f64")], g[key_stem.replace("{}", "f32")]
+        return ours, v64, v32
+
+    # layer-wise activations
+    worst = 0.0
+    for n, t in taps.items():
+        k64, k32 = "act_f64/%s" % n, "act_f32/%s" % n
+        got = t.detach().double().cpu().contiguous().numpy().reshape(-1)[g[k64 + "/idx"]]
+        scale = g[k64 + "/stat"][2]
+        e_ours = np.abs(got - g[k64 + "/val"]).max() / scale
+        e_ref = np.abs(g[k32 + "/val"] - g[k64 + "/val"]).max() / scale
+        worst = max(worst, e_ours)
+        assert e_ours <= 4 * e_ref + TOL, (n, e_ours, e_ref)
+    # curve coefficients, loss
+    b64, b32 = g["beta_f64"], g["beta_f32"]
+    ours = torch.stack([b.squeeze(-1) for b in betas], 1).detach().cpu().numpy()
+    nw = lambda a, b: float((np.abs(a - b).max(-1) / np.abs(b).max(-1)).max())
+    assert nw(ours, b64) <= 4 * nw(b32, b64) + TOL, (nw(ours, b64), nw(b32, b64))
+    l64, l32 = float(g["loss_f64"]), float(g["loss_f32"])
+    assert abs(float(loss) - l64) <= 4 * abs(l32 - l64) + TOL * abs(l64)
+    # parameter gradients
+    gscale = max(g[k][2] for k in g.files if k.startswith("grad_f64/") and k.endswith("/stat"))
+    no_grad = set(json.loads(str(g["params_without_grad"])))
+    for n, p in model.named_parameters():
+        if n in no_grad:
+            assert p.grad is None, n
+            continue
+        k64, k32 = "grad_f64/" + n, "grad_f32/" + n
+        got = p.grad.double().cpu().numpy().reshape(-1)[g[k64 + "/idx"]]
+        scale = max(g[k64 + "/stat"][2], 1e-6 * gscale)
+        e_ours = np.abs(got - g[k64 + "/val"]).max() / scale
+        e_ref = np.abs(g[k32 + "/val"] - g[k64 + "/val"]).max() / scale
+        assert e_ours <= 4 * e_ref + 10 * TOL, (n, e_ours, e_ref)
+    # BN running statistics after one step
+    for n, b in model.named_buffers():
+        if n.endswith("running_mean") or n.endswith("running_var"):
+            ref = g["buf_f64/" + n]
+            assert np.abs(b.cpu().numpy() - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-3), n
+
+
+def test_eval_mode_forward_and_early_return():
+    model, args = _build_net(2, 2, 0.3, 2)
+    P_np = inputs.make_erfnet_params(3, 2, seed=11)
+    sd = model.state_dict()
+    for k, v in P_np.items():
+        sd[k] = torch.from_numpy(v)
+    rng = np.random.default_rng(0)
+    for k in sd:
+        if k.endswith("running_mean"):
+            sd[k] = torch.from_numpy(rng.standard_normal(sd[k].shape).astype(np.float32) * 0.1)
+        if k.endswith("running_var"):
+            sd[k] = torch.from_numpy((1 + rng.random(sd[k].shape)).astype(np.float32))
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    x = torch.from_numpy(inputs.make_images(2, 256, 512, seed=9))
+    with torch.no_grad():
+        out = model(x.cuda(), torch.zeros(2, 4), True)
+        early = model(x.cuda(), torch.zeros(2, 4), True, early_return=True)
+    P = {k[4:]: v.double().cpu() for k, v in sd.items() if k.startswith("net.")}
+    enc, dec = eo.erfnet_forward(x.double(), P, training=False)
+    assert rel(out[5], dec) <= TOL and rel(early, dec) <= TOL
+    assert out[8].shape == (2, 128, 32, 64) and rel(out[8], enc) <= TOL
+    masked = lo.activate_and_mask(dec, "square", 77)
+    assert rel(out[4], masked) <= 4 * TOL
+    assert out[2] is None and out[3] is None and out[6] is None
+    # running stats untouched in eval
+    assert int(model.net.encoder.initial_block.bn.num_batches_tracked) == 0
+
+
+def test_error_conventions():
+    """order > 3 -> NotImplementedError, unknown activation -> NotImplementedError, unknown model -> KeyError
+    (BP/Networks/LSQ_layer.py:44,105-107; BP/Networks/__init__.py:16-17); CPU tensors are refused."""
+    from lanedetection_end2end_b200 import Networks
+    from lanedetection_end2end_b200.Networks import LSQ_layer
+    from lanedetection_end2end_b200._capi import LanefitError
+    with pytest.raises(KeyError):
+        Networks.define_model("resnet")
+    with pytest.raises(NotImplementedError):
+        LSQ_layer.activation_layer("tanh")
+    size = torch.Size([1, 2, 256, 512])
+    ls = LSQ_layer.Weighted_least_squares(size, 2, 4, True)
+    grid = torch.from_numpy(load("lsq_bp_l2_d2")["grid0"]).cuda().unsqueeze(0)
+    W = torch.rand(1, 2, 256, 512, device="cuda")
+    with pytest.raises(NotImplementedError):
+        ls(W, grid)
+    b, _ = ls.forward_all(W, grid)         # the extension API allows order 4
+    assert b.shape == (1, 2, 5)
+    ls2 = LSQ_layer.Weighted_least_squares(size, 2, 2, True)
+    b0, b1, b2, b3 = ls2(W, grid)
+    assert b0.shape == (1, 3, 1) and b0.dtype == torch.float64 and b2 is None and b3 is None
+    with pytest.raises(LanefitError):
+        ls2(W.cpu(), grid.cpu())
