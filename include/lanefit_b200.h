@@ -134,6 +134,27 @@ typedef struct LfConvArgs {
 } LfConvArgs;
 int lf_conv_f32(const LfConvArgs* args, lf_stream_t stream);
 
+/* tcgen05 (TF32 in, fp32 accumulate) implementation of the factorised 3-tap convolutions of
+ * non_bottleneck_1d (BP/Networks/ERFNet.py:29-37) and their input gradients, for dense NHWC fp32
+ * tensors with C in {64,128} channels in and out:
+ *   out[n,y,x,co] = epi( sum_{t<3} sum_ci in[n, y+dy[t], x+dx[t], ci] * wpack[co*3*C + t*C + ci] )
+ * epi as in LfConvArgs.  Requires a bx*by = 128 pixel patch with bx | W, by | H
+ * (lf_conv1d_tc_supported tells).  Same results as lf_conv_f32 up to TF32 rounding of the operands. */
+typedef struct LfConvTcArgs {
+    const float* in;
+    const float* wpack;    /* [C][3*C], K contiguous */
+    const float* bias;     /* [C] or NULL */
+    float* out;
+    const float* mask_src;
+    const float* add_src;
+    const float* add_mask;
+    int N, H, W, C;
+    int dy[3], dx[3];
+    int relu;
+} LfConvTcArgs;
+int lf_conv1d_tc_supported(int N, int H, int W, int C);
+int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream);
+
 /* Weight gradient as a split-K GEMM over pixels:
  *   partial[s][t][cp][cq] = sum_{(n,j,i) in split s} P[n, j*psy+pdy[t], i*psx+pdx[t], cp]
  *                                                  * Q[n, j*qsy+qdy[t], i*qsx+qdx[t], cq]

@@ -53,6 +53,12 @@ class LfConvArgs(ctypes.Structure):
                 ("relu", _i)]
 
 
+class LfConvTcArgs(ctypes.Structure):
+    _fields_ = [("inp", _p), ("wpack", _p), ("bias", _p), ("out", _p), ("mask_src", _p), ("add_src", _p),
+                ("add_mask", _p), ("N", _i), ("H", _i), ("W", _i), ("C", _i), ("dy", _i * 3), ("dx", _i * 3),
+                ("relu", _i)]
+
+
 class LfWgradArgs(ctypes.Structure):
     _fields_ = [("P", _p), ("Q", _p), ("partial", _p), ("qsum_partial", _p),
                 ("N", _i), ("Hs", _i), ("Ws", _i),
@@ -66,6 +72,8 @@ class LfWgradArgs(ctypes.Structure):
 _NET_PROTOS = {
     "lf_conv_f32": (_i, [ctypes.POINTER(LfConvArgs), _p]),
     "lf_wgrad_f32": (_i, [ctypes.POINTER(LfWgradArgs), _p]),
+    "lf_conv1d_tc": (_i, [ctypes.POINTER(LfConvTcArgs), _p]),
+    "lf_conv1d_tc_supported": (_i, [_i, _i, _i, _i]),
     "lf_wgrad_reduce": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p]),
     "lf_vec_reduce": (_i, [_p, _i, _i, _i, _p, _p]),
     "lf_colsum_blocks": (_i, [ctypes.c_longlong]),

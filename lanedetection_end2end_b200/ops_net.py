@@ -10,6 +10,7 @@ Training-mode memory plan per non_bottleneck_1d (what backward needs):
   pairs and the dropout mask.
 """
 import ctypes
+import os
 
 import torch
 
@@ -18,7 +19,20 @@ from . import net_plans as plans
 
 BN_EPS = 1e-3
 BN_MOMENTUM = 0.1
-LfConvArgs, LfWgradArgs = _capi.LfConvArgs, _capi.LfWgradArgs
+LfConvArgs, LfWgradArgs, LfConvTcArgs = _capi.LfConvArgs, _capi.LfWgradArgs, _capi.LfConvTcArgs
+
+# Convolution arithmetic for the dense 3-tap convolutions of non_bottleneck_1d (C in {64,128}):
+#   "fp32": CUDA-core FFMA implicit GEMM (parity mode, fp32-exact)
+#   "tf32": tcgen05 tensor cores, TF32 multiply / fp32 accumulate (what cuDNN does for the reference's
+#           fp32 convs on Ampere+ GPUs); every other layer shape stays on the fp32 kernel.
+CONV_MODE = os.environ.get("LANEFIT_CONV_MODE", "fp32")
+
+
+def set_conv_mode(mode):
+    global CONV_MODE
+    if mode not in ("fp32", "tf32"):
+        raise ValueError(mode)
+    CONV_MODE = mode
 
 ptr = _capi.ptr
 
@@ -104,6 +118,60 @@ def run_conv(phases, x, wmat, cin, out, cout, out_coff=0, bias=None, relu=False,
                    flops=2 * N * ph["Hs"] * ph["Ws"] * len(taps) * cin * cout,
                    nbytes=4 * N * ph["Hs"] * ph["Ws"] * (cin + cout))
     return out
+
+
+def pack_tc_fwd(w):
+    """Conv2d weight [Co,Ci,kh,kw] (3 taps) -> [Co][3*Ci], K = (tap, ci) contiguous."""
+    Co, Ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(Co, kh * kw * Ci).contiguous()
+
+
+def pack_tc_dgrad(w):
+    """-> [Ci][3*Co]: the GEMM operand of the input gradient (taps negated by the caller)."""
+    Co, Ci, kh, kw = w.shape
+    return w.permute(1, 2, 3, 0).reshape(Ci, kh * kw * Co).contiguous()
+
+
+def tc_supported(x):
+    N, H, W, C = x.shape
+    return bool(_lib().lf_conv1d_tc_supported(N, H, W, C))
+
+
+def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_src=None, add_mask=None):
+    """3-tap convolution on tcgen05.  taps: [(dy, dx)] * 3 in weight-slot order."""
+    N, H, W, C = x.shape
+    a = LfConvTcArgs()
+    a.inp, a.wpack, a.out = x.data_ptr(), wpack.data_ptr(), out.data_ptr()
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.mask_src = mask_src.data_ptr() if mask_src is not None else None
+    a.add_src = add_src.data_ptr() if add_src is not None else None
+    a.add_mask = add_mask.data_ptr() if add_mask is not None else None
+    a.N, a.H, a.W, a.C = N, H, W, C
+    for t, (dy, dx) in enumerate(taps):
+        a.dy[t], a.dx[t] = dy, dx
+    a.relu = int(relu)
+    _capi.call("lf_conv1d_tc", ctypes.byref(a), _stream(), flops=2 * N * H * W * 3 * C * C, nbytes=8 * N * H * W * C)
+    return out
+
+
+def conv3(x, w, vertical, dil, transposed, **epi):
+    """One factorised 3-tap convolution of non_bottleneck_1d (or its input gradient when
+    ``transposed``): dispatches to the tcgen05 kernel in tf32 mode, else to the fp32 kernel."""
+    N, H, W, C = x.shape
+    out = torch.empty_like(x)
+    if CONV_MODE == "tf32" and C in (64, 128) and tc_supported(x):
+        sgn = -1 if transposed else 1
+        taps = [((sgn * (k - 1) * dil, 0) if vertical else (0, sgn * (k - 1) * dil)) for k in range(3)]
+        wp = pack_tc_dgrad(w) if transposed else pack_tc_fwd(w)
+        return run_conv_tc(taps, x, wp, out, **epi)
+    kh, kw = (3, 1) if vertical else (1, 3)
+    ph, pw = (dil, 0) if vertical else (0, dil)
+    dh, dw = (dil, 1) if vertical else (1, dil)
+    if transposed:
+        phases, _ = plans.conv_dgrad_plan_s1(H, W, kh, kw, ph, pw, dh, dw)
+        return run_conv(phases, x, pack_conv_dgrad(w), C, out, C, **epi)
+    phases, _ = plans.conv_fwd_plan(H, W, kh, kw, 1, ph, pw, dh, dw)
+    return run_conv(phases, x, pack_conv_fwd(w), C, out, C, **epi)
 
 
 def _nsplit_for(tiles, M):
@@ -287,16 +355,12 @@ class Nb1dFunction(torch.autograd.Function):
     def forward(ctx, x, w1, b1, w2, b2, g1, be1, w3, b3, w4, b4, g2, be2, rm1, rv1, rm2, rv2, dil, drop, training):
         _capi.require_cuda(x)
         N, H, W, C = x.shape
-        p31, _ = plans.conv_fwd_plan(H, W, 3, 1, 1, 1, 0, 1, 1)
-        p13, _ = plans.conv_fwd_plan(H, W, 1, 3, 1, 0, 1, 1, 1)
-        p31d, _ = plans.conv_fwd_plan(H, W, 3, 1, 1, dil, 0, dil, 1)
-        p13d, _ = plans.conv_fwd_plan(H, W, 1, 3, 1, 0, dil, 1, dil)
-        t1 = run_conv(p31, x, pack_conv_fwd(w1), C, torch.empty_like(x), C, bias=b1, relu=True)
-        t2 = run_conv(p13, t1, pack_conv_fwd(w2), C, torch.empty_like(x), C, bias=b2)
+        t1 = conv3(x, w1, True, 1, False, bias=b1, relu=True)
+        t2 = conv3(t1, w2, False, 1, False, bias=b2)
         s1 = bn_forward_stats(t2, g1, be1, rm1, rv1, training)
         t3 = bn_apply(t2, s1, relu=True)
-        t4 = run_conv(p31d, t3, pack_conv_fwd(w3), C, torch.empty_like(x), C, bias=b3, relu=True)
-        t5 = run_conv(p13d, t4, pack_conv_fwd(w4), C, torch.empty_like(x), C, bias=b4)
+        t4 = conv3(t3, w3, True, dil, False, bias=b3, relu=True)
+        t5 = conv3(t4, w4, False, dil, False, bias=b4)
         s2 = bn_forward_stats(t5, g2, be2, rm2, rv2, training)
         y = bn_apply(t5, s2, relu=True, drop=drop, res=x)
         ctx.save_for_backward(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1.mean, s1.invstd, s2.mean, s2.invstd,
@@ -321,25 +385,21 @@ class Nb1dFunction(torch.autograd.Function):
         # conv1x3_2 (dilated)
         dw4, db4 = torch.empty_like(w4), _empty((C,), x)
         run_wgrad(plans.conv_wgrad_plan(H, W, 1, 3, 1, 0, dil, 1, dil), t4, C, d5, C, 0, N, dw4, lay(w4), db4)
-        pd, _ = plans.conv_dgrad_plan_s1(H, W, 1, 3, 0, dil, 1, dil)
-        d4 = run_conv(pd, d5, pack_conv_dgrad(w4), C, torch.empty_like(x), C, mask_src=t4)
+        d4 = conv3(d5, w4, False, dil, True, mask_src=t4)
         # conv3x1_2 (dilated)
         dw3, db3 = torch.empty_like(w3), _empty((C,), x)
         run_wgrad(plans.conv_wgrad_plan(H, W, 3, 1, 1, dil, 0, dil, 1), t3, C, d4, C, 0, N, dw3, lay(w3), db3)
-        pd, _ = plans.conv_dgrad_plan_s1(H, W, 3, 1, dil, 0, dil, 1)
-        d3 = run_conv(pd, d4, pack_conv_dgrad(w3), C, torch.empty_like(x), C, mask_src=t3)
+        d3 = conv3(d4, w3, True, dil, True, mask_src=t3)
         # bn1 (+relu already applied through mask_src=t3)
         d2, dg1, dbe1 = bn_backward(d3, None, None, t2, s1, g1)
         # conv1x3_1
         dw2, db2 = torch.empty_like(w2), _empty((C,), x)
         run_wgrad(plans.conv_wgrad_plan(H, W, 1, 3, 1, 0, 1, 1, 1), t1, C, d2, C, 0, N, dw2, lay(w2), db2)
-        pd, _ = plans.conv_dgrad_plan_s1(H, W, 1, 3, 0, 1, 1, 1)
-        d1 = run_conv(pd, d2, pack_conv_dgrad(w2), C, torch.empty_like(x), C, mask_src=t1)
+        d1 = conv3(d2, w2, False, 1, True, mask_src=t1)
         # conv3x1_1, plus the residual branch: dx = dgrad + dy*(y>0)
         dw1, db1 = torch.empty_like(w1), _empty((C,), x)
         run_wgrad(plans.conv_wgrad_plan(H, W, 3, 1, 1, 1, 0, 1, 1), x, C, d1, C, 0, N, dw1, lay(w1), db1)
-        pd, _ = plans.conv_dgrad_plan_s1(H, W, 3, 1, 1, 0, 1, 1)
-        dx = run_conv(pd, d1, pack_conv_dgrad(w1), C, torch.empty_like(x), C, add_src=dy, add_mask=y)
+        dx = conv3(d1, w1, True, 1, True, add_src=dy, add_mask=y)
         return (dx, dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2, None, None, None, None, None, None,
                 None)
 

@@ -1,0 +1,118 @@
+"""GPU tests of the tcgen05 (TF32) 3-tap convolution kernel (csrc/conv_tc.cu) against the fp32 CUDA-core
+kernel (csrc/conv_f32.cu) and against torch-CPU fp64.
+
+Two kinds of checks:
+  * operands that are exactly representable in TF32 (10 mantissa bits) -> products are exact, both kernels
+    accumulate in fp32 -> agreement to ~1e-6 (catches every descriptor / swizzle / tap / phase bug);
+  * generic fp32 operands -> agreement within TF32 rounding (rel 2e-3 of the output scale).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def ops():
+    from lanedetection_end2end_b200 import ops_net
+    return ops_net
+
+
+def tf32_exact(t):
+    """Zero the 13 low mantissa bits so the value is a TF32 number."""
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+CASES = [
+    # N, C, H, W, vertical, dil
+    (2, 64, 16, 128, True, 1),
+    (2, 64, 16, 128, False, 1),
+    (3, 128, 32, 64, True, 2),
+    (3, 128, 32, 64, False, 4),
+    (2, 128, 32, 64, True, 16),
+    (2, 128, 32, 64, False, 16),
+    (1, 128, 40, 80, True, 8),      # 320x640 geometry: 16x8 patch
+    (1, 64, 80, 160, False, 1),
+    (5, 64, 64, 128, True, 1),      # more tiles than one wave of a small grid
+]
+
+
+@pytest.mark.parametrize("N,C,H,W,vertical,dil", CASES)
+@pytest.mark.parametrize("exact", [True, False])
+def test_tc_forward_matches_fp32_kernel(N, C, H, W, vertical, dil, exact):
+    o = ops()
+    g = torch.Generator().manual_seed(N * 1000 + C + dil)
+    x = torch.randn(N, H, W, C, generator=g).cuda()
+    kh, kw = (3, 1) if vertical else (1, 3)
+    w = (torch.randn(C, C, kh, kw, generator=g) / (3 * C) ** 0.5).cuda()
+    b = torch.randn(C, generator=g).cuda()
+    if exact:
+        x, w = tf32_exact(x), tf32_exact(w)
+    assert o.tc_supported(x)
+    o.set_conv_mode("fp32")
+    ref = o.conv3(x, w, vertical, dil, False, bias=b, relu=False)
+    o.set_conv_mode("tf32")
+    try:
+        got = o.conv3(x, w, vertical, dil, False, bias=b, relu=False)
+        torch.cuda.synchronize()
+    finally:
+        o.set_conv_mode("fp32")
+    scale = float(ref.abs().max())
+    err = float((got - ref).abs().max()) / scale
+    assert err <= (2e-6 if exact else 2e-3), err
+    # independent check against torch-CPU fp64 on a slice
+    xs, ws = x[:1].double().cpu().permute(0, 3, 1, 2), w.double().cpu()
+    pad = (dil, 0) if vertical else (0, dil)
+    dl = (dil, 1) if vertical else (1, dil)
+    cpu = F.conv2d(xs, ws, b.double().cpu(), 1, pad, dl).permute(0, 2, 3, 1)
+    assert float((got[:1].double().cpu() - cpu).abs().max()) / scale <= (2e-6 if exact else 2e-3)
+
+
+@pytest.mark.parametrize("C,H,W,dil", [(64, 16, 128, 1), (128, 32, 64, 8)])
+def test_tc_epilogues_and_dgrad(C, H, W, dil):
+    o = ops()
+    g = torch.Generator().manual_seed(7)
+    N = 2
+    x = tf32_exact(torch.randn(N, H, W, C, generator=g).cuda())
+    w = tf32_exact((torch.randn(C, C, 1, 3, generator=g) / (3 * C) ** 0.5).cuda())
+    b = torch.randn(C, generator=g).cuda()
+    mask = torch.randn(N, H, W, C, generator=g).cuda()
+    add = torch.randn(N, H, W, C, generator=g).cuda()
+    addm = torch.randn(N, H, W, C, generator=g).cuda()
+    outs = {}
+    for mode in ("fp32", "tf32"):
+        o.set_conv_mode(mode)
+        try:
+            outs[mode] = (o.conv3(x, w, False, dil, False, bias=b, relu=True),
+                          o.conv3(x, w, False, dil, True, mask_src=mask),
+                          o.conv3(x, w, False, dil, True, add_src=add, add_mask=addm))
+            torch.cuda.synchronize()
+        finally:
+            o.set_conv_mode("fp32")
+    for a, r in zip(outs["tf32"], outs["fp32"]):
+        assert float((a - r).abs().max()) <= 2e-6 * float(r.abs().max())
+
+
+def test_tc_block_level_tf32_tolerance():
+    """non_bottleneck_1d fwd+bwd in tf32 mode vs fp32 mode: agreement within TF32 rounding."""
+    from lanedetection_end2end_b200.Networks import ERFNet
+    o = ops()
+    torch.manual_seed(0)
+    blk = ERFNet.non_bottleneck_1d(128, 0.0, 4).cuda().train()
+    x = torch.randn(4, 128, 32, 64, device="cuda")
+    gy = torch.randn(4, 128, 32, 64, device="cuda")
+    res = {}
+    for mode in ("fp32", "tf32"):
+        o.set_conv_mode(mode)
+        try:
+            xi = x.clone().requires_grad_(True)
+            blk.zero_grad()
+            y = blk(xi)
+            y.backward(gy)
+            torch.cuda.synchronize()
+            res[mode] = (y.detach().clone(), xi.grad.clone(), blk.conv3x1_2.weight.grad.clone())
+        finally:
+            o.set_conv_mode("fp32")
+    for a, r in zip(res["tf32"], res["fp32"]):
+        assert float((a - r).abs().max()) <= 5e-3 * float(r.abs().max())

@@ -132,3 +132,32 @@ def test_wgrad_destination_strides_match_weight_layouts():
         for ci in range(Ci):
             for co in range(Co):
                 assert wT.reshape(-1)[t * st + ci * sp + co * sq] == wT[ci, co, t // 3, t % 3]
+
+
+@pytest.mark.parametrize("vertical,dil", [(True, 1), (False, 1), (True, 4), (False, 16)])
+def test_tc_kernel_contract_fwd_and_dgrad(vertical, dil):
+    """Contract of lf_conv1d_tc (LfConvTcArgs): out = sum_t in[y+dy_t, x+dx_t] @ wpack[:, t*C:(t+1)*C]^T with the
+    taps / packings ops_net.conv3 builds, vs torch conv2d and its input gradient."""
+    N, C, H, W = 2, 8, 9, 20
+    kh, kw = (3, 1) if vertical else (1, 3)
+    pad = (dil, 0) if vertical else (0, dil)
+    dl = (dil, 1) if vertical else (1, dil)
+    x = torch.randn(N, C, H, W, dtype=DT, requires_grad=True)
+    w = torch.randn(C, C, kh, kw, dtype=DT)
+    y = F.conv2d(x, w, None, 1, pad, dl)
+    gy = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, gy)
+
+    def emulate(inp, wpack, sgn):
+        out = torch.zeros(N, H, W, C, dtype=DT)
+        for t in range(3):
+            dy, dx = ((sgn * (t - 1) * dil, 0) if vertical else (0, sgn * (t - 1) * dil))
+            for yy in range(H):
+                for xx in range(W):
+                    iy, ix = yy + dy, xx + dx
+                    if 0 <= iy < H and 0 <= ix < W:
+                        out[:, yy, xx] += inp[:, iy, ix] @ wpack[:, t * C:(t + 1) * C].t()
+        return out
+
+    torch.testing.assert_close(nchw(emulate(nhwc(x.detach()), ops.pack_tc_fwd(w), 1)), y.detach())
+    torch.testing.assert_close(nchw(emulate(nhwc(gy), ops.pack_tc_dgrad(w), -1)), gx)
