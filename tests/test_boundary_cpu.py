@@ -1,0 +1,154 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header
+declares (no compute calls), the reference-mirroring modules keep names / state_dict keys / flag defaults /
+error conventions, and device ops refuse CPU tensors loudly (no fallback)."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from lanedetection_end2end_b200 import _capi
+    assert os.path.exists(_capi.LIB_PATH), "run __graft_entry__.build() first"
+    hdr = open(os.path.join(ROOT, "include", "lanefit_b200.h")).read()
+    declared = set(re.findall(r"\b(lf_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    h = _capi.lib()
+    for name in declared:
+        assert hasattr(h, name), name
+    assert declared == set(_capi.PROTOTYPES), declared ^ set(_capi.PROTOTYPES)
+    # host-only entry points are callable without a GPU
+    assert h.lf_version() >= 100
+    assert h.lf_error_string(-2) == b"unsupported configuration"
+    assert h.lf_lsq_workspace_bytes(2, 2, 256, 512, 2) > 0
+    assert h.lf_bn_blocks(65536, 128) >= 148
+    assert h.lf_lsq_fwd(None, 0, None, None, None, 1, 1, 8, 8, 2, 0, 1, 0.0, 0, None, None, None, None, None, 0, None) == -1
+
+
+def test_ctypes_struct_layout_matches_header():
+    """Field order / count of the ctypes mirrors vs the C structs in the header."""
+    from lanedetection_end2end_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "lanefit_b200.h")).read()
+    for cname, cls in (("LfConvArgs", _capi.LfConvArgs), ("LfWgradArgs", _capi.LfWgradArgs),
+                       ("LfConvTcArgs", _capi.LfConvTcArgs)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(const\s+)?(float|int)\s*\*?", "", decl)
+            for part in decl.split(","):
+                names.append(re.sub(r"\[.*\]", "", part.replace("*", "")).strip())
+        mine = [f[0] for f in cls._fields_]
+        assert len(names) == len(mine), (cname, names, mine)
+        for a, b in zip(names, mine):
+            assert a == b or (a == "in" and b == "inp"), (cname, a, b)
+
+
+def test_state_dict_keys_match_reference():
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    from lanedetection_end2end_b200.Networks.LSQ_layer import Net
+    for name, L in (("net_l2_d2", 2), ("net_l4_d3", 4)):
+        ref = json.loads(str(np.load(os.path.join(GOLDEN, name + ".npz"))["state_dict_keys"]))
+        args = define_args().parse_args(["--image_dir", "x", "--gt_dir", "y", "--no_cuda", "--nclasses", str(L),
+                                         "--batch_size", "2"])
+        m = Net(args)
+        mine = [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()]
+        assert mine == ref
+        # plain attributes, not buffers (BP/Networks/LSQ_layer.py:77-83,231,238)
+        assert not any(k.startswith(("grid", "ls_layer", "idx_row")) for k in m.state_dict())
+        assert tuple(m.grid.shape) == (2, 256 * 512, 2)
+
+
+def test_grid_is_bit_identical_to_reference():
+    from lanedetection_end2end_b200.Networks.LSQ_layer import ProjectiveGridGenerator
+    from lanedetection_end2end_b200.Networks.utils import get_homography
+    M, Minv = get_homography(256)
+    g = np.load(os.path.join(GOLDEN, "homography.npz"))
+    np.testing.assert_array_equal(M, g["M_256"])          # same cv2 -> same matrix
+    np.testing.assert_array_equal(Minv, g["Minv_256"])
+    grid = ProjectiveGridGenerator(torch.Size([3, 2, 256, 512]), torch.from_numpy(M).float().unsqueeze(0).expand(3, 3, 3), True)
+    ref = np.load(os.path.join(GOLDEN, "lsq_bp_l2_d2.npz"))["grid0"]
+    np.testing.assert_array_equal(grid[0].numpy(), ref)
+    np.testing.assert_array_equal(grid[2].numpy(), ref)
+
+
+def test_flag_defaults_and_required_flags():
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    p = define_args()
+    with pytest.raises(SystemExit):
+        p.parse_args([])                                   # --image_dir / --gt_dir are required
+    a = p.parse_args(["--image_dir", "x", "--gt_dir", "y"])
+    assert (a.nclasses, a.order, a.resize, a.batch_size, a.mask_percentage) == (2, 2, 256, 8, 0.3)
+    assert a.activation_layer == "square" and a.reg_ls == 0 and a.use_cholesky is False and a.end_to_end is True
+    assert a.weight_init == "kaiming" and a.loss_policy == "area" and a.mod == "erfnet" and a.clas is False
+    assert p.parse_args(["--image_dir", "x", "--gt_dir", "y", "--use_cholesky", "1", "--end_to_end", "False"]).use_cholesky
+    with pytest.raises(SystemExit):
+        p.parse_args(["--image_dir", "x", "--gt_dir", "y", "--nclasses", "3"])
+
+
+def test_error_conventions_and_no_cpu_fallback():
+    from lanedetection_end2end_b200 import Networks
+    from lanedetection_end2end_b200.Networks import LSQ_layer, ERFNet
+    from lanedetection_end2end_b200._capi import LanefitError
+    with pytest.raises(KeyError):
+        Networks.define_model("segnet")
+    with pytest.raises(NotImplementedError):
+        LSQ_layer.activation_layer("tanh")
+    blk = ERFNet.non_bottleneck_1d(16, 0.0, 1)
+    with pytest.raises(LanefitError):
+        blk(torch.randn(1, 16, 8, 8))                      # CPU tensor: refused, never silently computed
+    ls = LSQ_layer.Weighted_least_squares(torch.Size([1, 2, 8, 16]), 2, 2, True)
+    with pytest.raises(LanefitError):
+        ls(torch.rand(1, 2, 8, 16), torch.rand(1, 128, 2))
+
+
+def test_loss_modules_match_oracle_on_cpu():
+    """The losses are O(B*56) float64 torch code and run anywhere; check them against the oracle."""
+    from types import SimpleNamespace
+    from lanedetection_end2end_b200.Loss_crit import backprojection_loss, Area_Loss
+    from oracle import lsq_oracle as lo
+    g = np.load(os.path.join(GOLDEN, "homography.npz"))
+    opt = SimpleNamespace(resize=256, no_mapping=False, order=2, batch_size=4, no_cuda=True)
+    crit = backprojection_loss(opt)
+    ref = lo.BackprojectionLoss(2, 256, M=g["M_256"], M_inv=g["Minv_256"])
+    beta = torch.tensor([[1e-3, -0.2, 260.0], [2e-3, 0.1, 250.0], [0.0, 0.0, 270.0], [-1e-3, 0.3, 240.0]],
+                        dtype=torch.float64).unsqueeze(-1).requires_grad_(True)
+    xgt = torch.rand(4, 56, dtype=torch.float64) * 500
+    valid = torch.ones(4, 56, dtype=torch.float64)
+    valid[:, :8] = 0
+    l1, x1 = crit(beta, xgt, valid)
+    l2, x2 = ref(beta.detach(), xgt, valid)
+    assert abs(float(l1.detach()) - float(l2)) <= 1e-12 * abs(float(l2))
+    torch.testing.assert_close(x1.detach(), x2, rtol=1e-12, atol=1e-9)
+    l1.backward()
+    assert torch.isfinite(beta.grad).all()
+    gt = torch.tensor([[1e-3, -0.2, 0.5], [0.0, 0.0, 0.0], [2e-3, 0.1, 0.4], [1e-3, 0.2, 0.6]], dtype=torch.float64)
+    for wf in ("none", "linear", "quadratic"):
+        a = Area_Loss(2, wf)(beta.detach() * 1e-3, gt)
+        b = lo.area_loss(beta.detach() * 1e-3, gt, 2, wf)
+        assert abs(float(a) - float(b)) <= 1e-12 * max(1.0, abs(float(b)))
+
+
+def test_reference_main_imports_resolve_with_package_dir_on_path():
+    """`from Networks.LSQ_layer import Net`, `from Loss_crit import define_loss_crit` ... -- the imports at
+    the top of the reference's main.py (BP/main.py:24-28) resolve against this package directory."""
+    code = ("import sys; sys.path.insert(0, %r);"
+            "from Loss_crit import define_loss_crit, backprojection_loss;"
+            "from Networks.LSQ_layer import Net;"
+            "from Networks.utils import define_args, save_weightmap, first_run, mkdir_if_missing, Logger, "
+            "define_init_weights, define_scheduler, define_optim, AverageMeter;"
+            "from Networks.gels import GELS; import Networks; print(sorted(Networks.model_dict))")
+    pkg = os.path.join(ROOT, "lanedetection_end2end_b200")
+    out = subprocess.run([sys.executable, "-c", code % pkg], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0, out.stderr
+    assert "erfnet" in out.stdout

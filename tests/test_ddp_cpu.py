@@ -1,0 +1,64 @@
+"""world_size-2 gloo test (CPU) of the data-parallel host logic: flat gradient bucket, zero-fill of
+None gradients, averaging, parameter broadcast (lanedetection_end2end_b200/ddp.py)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lanedetection_end2end_b200.ddp import FlatGradAllReduce, broadcast_parameters
+    torch.manual_seed(100 + rank)                     # replicas start different ...
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2), torch.nn.Linear(2, 2))
+    broadcast_parameters(net, 0)                      # ... and are made identical
+    p0 = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    x = torch.full((5, 4), float(rank + 1))
+    net[1](net[0](x)).sum().backward()                # net[2] never used -> its grads stay None
+    red = FlatGradAllReduce(net)
+    local = [None if p.grad is None else p.grad.clone() for p in net.parameters()]
+    flat = red()
+    q.put((rank, p0, [None if g is None else g for g in local], flat.clone(),
+           [None if p.grad is None else p.grad.clone() for p in net.parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (_, p0a, la, fa, ga), (_, p0b, lb, fb, gb) = res
+    assert torch.equal(p0a, p0b)                      # broadcast worked
+    assert torch.equal(fa, fb)                        # every rank holds the same reduced buffer
+    off = 0
+    for a, b, g in zip(la, lb, ga):
+        n = (a if a is not None else b if b is not None else torch.zeros(0)).numel()
+        if a is None:
+            assert g is None                          # stays None on the module ...
+            continue
+        want = (a + b) / 2
+        torch.testing.assert_close(g, want)
+        torch.testing.assert_close(fa[off:off + n].view_as(want), want)
+        off += n
+    # ... but the unused layer contributed zeros to the flat buffer (fixed layout on every rank)
+    assert float(fa[off:].abs().sum()) == 0.0 and fa.numel() - off == 2 * 2 + 2
