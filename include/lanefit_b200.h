@@ -155,6 +155,14 @@ typedef struct LfConvTcArgs {
 int lf_conv1d_tc_supported(int N, int H, int W, int C);
 int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream);
 
+/* tcgen05 weight gradient of the same 3-tap convolutions:
+ *   partial[cta][t][ci][co] = sum over this CTA's pixel range of x[n,y+dy[t],x+dx[t],ci] * dy[n,y,x,co]
+ * nctas = lf_wgrad3_tc_ctas(...) (0 = unsupported shape); finish with
+ * lf_wgrad_reduce(partial, nctas, 3, C, C, C, C, dst, st, sp, sq). */
+int lf_wgrad3_tc_ctas(int N, int H, int W, int C);
+int lf_wgrad3_tc(const float* x, const float* dy, int N, int H, int W, int C, const int* tap_dy, const int* tap_dx,
+                 float* partial, int nctas, lf_stream_t stream);
+
 /* Weight gradient as a split-K GEMM over pixels:
  *   partial[s][t][cp][cq] = sum_{(n,j,i) in split s} P[n, j*psy+pdy[t], i*psx+pdx[t], cp]
  *                                                  * Q[n, j*qsy+qdy[t], i*qsx+qdx[t], cq]

@@ -174,6 +174,29 @@ def conv3(x, w, vertical, dil, transposed, **epi):
     return run_conv(phases, x, pack_conv_fwd(w), C, out, C, **epi)
 
 
+def wgrad3(x_in, d_out, w, vertical, dil):
+    """Weight + bias gradient of one factorised 3-tap convolution -> (dw [Co,Ci,kh,kw], db [Co])."""
+    N, H, W, C = x_in.shape
+    dw, db = torch.empty_like(w), torch.empty(C, dtype=torch.float32, device=x_in.device)
+    lay = (1, 3, C * 3)                                   # (tap, ci, co) strides of [Co,Ci,3] weights
+    nctas = _lib().lf_wgrad3_tc_ctas(N, H, W, C) if (CONV_MODE == "tf32" and C in (64, 128)) else 0
+    if nctas > 0:
+        tdy = (ctypes.c_int * 3)(*[((k - 1) * dil if vertical else 0) for k in range(3)])
+        tdx = (ctypes.c_int * 3)(*[(0 if vertical else (k - 1) * dil) for k in range(3)])
+        partial = torch.empty(nctas * 3 * C * C, dtype=torch.float32, device=x_in.device)
+        st = _stream()
+        _capi.call("lf_wgrad3_tc", ptr(x_in), ptr(d_out), N, H, W, C, tdy, tdx, ptr(partial), nctas, st,
+                   flops=2 * N * H * W * 3 * C * C, nbytes=8 * N * H * W * C)
+        _capi.call("lf_wgrad_reduce", ptr(partial), nctas, 3, C, C, C, C, ptr(dw), lay[0], lay[1], lay[2], st)
+        run_colsum(d_out, C, 0, db)
+        return dw, db
+    kh, kw = (3, 1) if vertical else (1, 3)
+    ph, pw = (dil, 0) if vertical else (0, dil)
+    dh, dw_ = (dil, 1) if vertical else (1, dil)
+    run_wgrad(plans.conv_wgrad_plan(H, W, kh, kw, 1, ph, pw, dh, dw_), x_in, C, d_out, C, 0, N, dw, lay, db)
+    return dw, db
+
+
 def _nsplit_for(tiles, M):
     target = 148 * 6
     ns = max(1, min((target + tiles - 1) // tiles, max(1, M // 256)))
@@ -378,27 +401,22 @@ class Nb1dFunction(torch.autograd.Function):
         N, H, W, C = x.shape
         s1, s2 = BNState(), BNState()
         s1.mean, s1.invstd, s2.mean, s2.invstd = m1, is1, m2, is2
-        lay = lambda w: (1, w.shape[2] * w.shape[3], w.shape[1] * w.shape[2] * w.shape[3])  # (tap, ci, co) strides
 
         # y = relu(bn2(t5)*drop + x)
         d5, dg2, dbe2 = bn_backward(dy, y, drop, t5, s2, g2)
         # conv1x3_2 (dilated)
-        dw4, db4 = torch.empty_like(w4), _empty((C,), x)
-        run_wgrad(plans.conv_wgrad_plan(H, W, 1, 3, 1, 0, dil, 1, dil), t4, C, d5, C, 0, N, dw4, lay(w4), db4)
+        dw4, db4 = wgrad3(t4, d5, w4, False, dil)
         d4 = conv3(d5, w4, False, dil, True, mask_src=t4)
         # conv3x1_2 (dilated)
-        dw3, db3 = torch.empty_like(w3), _empty((C,), x)
-        run_wgrad(plans.conv_wgrad_plan(H, W, 3, 1, 1, dil, 0, dil, 1), t3, C, d4, C, 0, N, dw3, lay(w3), db3)
+        dw3, db3 = wgrad3(t3, d4, w3, True, dil)
         d3 = conv3(d4, w3, True, dil, True, mask_src=t3)
         # bn1 (+relu already applied through mask_src=t3)
         d2, dg1, dbe1 = bn_backward(d3, None, None, t2, s1, g1)
         # conv1x3_1
-        dw2, db2 = torch.empty_like(w2), _empty((C,), x)
-        run_wgrad(plans.conv_wgrad_plan(H, W, 1, 3, 1, 0, 1, 1, 1), t1, C, d2, C, 0, N, dw2, lay(w2), db2)
+        dw2, db2 = wgrad3(t1, d2, w2, False, 1)
         d1 = conv3(d2, w2, False, 1, True, mask_src=t1)
         # conv3x1_1, plus the residual branch: dx = dgrad + dy*(y>0)
-        dw1, db1 = torch.empty_like(w1), _empty((C,), x)
-        run_wgrad(plans.conv_wgrad_plan(H, W, 3, 1, 1, 1, 0, 1, 1), x, C, d1, C, 0, N, dw1, lay(w1), db1)
+        dw1, db1 = wgrad3(x, d1, w1, True, 1)
         dx = conv3(d1, w1, True, 1, True, add_src=dy, add_mask=y)
         return (dx, dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2, None, None, None, None, None, None,
                 None)
