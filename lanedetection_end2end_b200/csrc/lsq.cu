@@ -270,8 +270,8 @@ __device__ void lsq_chunk_tail(const LsqArgs& a, double (*red)[LSQ_MAXL][LSQ_MAX
             for (int w = 0; w < LSQ_WARPS; ++w) s += red[w][l][k];
             a.partials[((size_t)(b * a.L + l0 + l) * a.nchunks + chunk) * NM + k] = s;
         }
+        __threadfence();  // writers only: publish this chunk's partial before the ticket is taken
     }
-    __threadfence();
     __syncthreads();
     __shared__ int is_last;
     const int ticket_idx = b * gridDim.z + lg;
@@ -514,9 +514,14 @@ __global__ void __launch_bounds__(LSQ_THREADS) lsq_bwd_general_kernel(const LsqA
 }
 
 static int pick_rows_per_cta(int B, int groups, int H) {
-    int R = LSQ_WARPS;
-    while ((long long)B * groups * ((H + R - 1) / R) > 16384 && R < H) R *= 2;
-    return R;
+    // aim at ~2 waves of 4 resident CTAs per SM; every CTA pays a fixed tail (block reduction,
+    // fence, ticket), so rows per CTA grow with the problem instead of the CTA count
+    const long long target = 148LL * 4 * 2;
+    long long R = ((long long)B * groups * H + target - 1) / target;
+    R = ((R + LSQ_WARPS - 1) / LSQ_WARPS) * LSQ_WARPS;
+    if (R < LSQ_WARPS) R = LSQ_WARPS;
+    if (R > 64) R = 64;
+    return (int)R;
 }
 
 static int validate(const LsqArgs& a, int o_dtype) {
@@ -534,14 +539,17 @@ static int validate(const LsqArgs& a, int o_dtype) {
 
 using namespace lf;
 
+// Workspace = [ticket region: LSQ_TICKET_BYTES, fixed so that tickets never alias partials of a call
+// with another shape] [partials].  Tickets are left at zero by every launch.
+constexpr size_t LSQ_TICKET_BYTES = 64 * 1024;
+
 extern "C" size_t lf_lsq_workspace_bytes(int B, int L, int H, int W, int order) {
     (void)W;
     if (B <= 0 || L <= 0 || H <= 0 || order < 0 || order > LF_MAX_ORDER) return 0;
-    // worst case: rows_per_cta = 8 -> nchunks = ceil(H/8); tickets after the partials
+    if ((size_t)B * L * sizeof(int) > LSQ_TICKET_BYTES) return 0;
+    // worst case: rows_per_cta = 8 -> nchunks = ceil(H/8)
     const size_t nchunks = (size_t)(H + LSQ_WARPS - 1) / LSQ_WARPS;
-    const size_t partials = (size_t)B * L * nchunks * (3 * order + 2) * sizeof(double);
-    const size_t tickets = (size_t)B * L * sizeof(int);
-    return partials + ((tickets + 15) / 16) * 16 + 16;
+    return LSQ_TICKET_BYTES + (size_t)B * L * nchunks * (3 * order + 2) * sizeof(double);
 }
 
 #define LSQ_DISPATCH(KERNEL, grid, args)                                                   \
@@ -572,16 +580,16 @@ extern "C" int lf_lsq_fwd(const void* o, int o_dtype, const float* xtab, const f
     if (rc != LF_OK) return rc;
     LF_REQUIRE(beta && zinv && status && workspace);
     LF_REQUIRE(solver == LF_SOLVER_INVERSE || solver == LF_SOLVER_CHOLESKY);
-    if (workspace_bytes < lf_lsq_workspace_bytes(B, L, H, W, order)) return LF_ERR_WORKSPACE_TOO_SMALL;
+    const size_t need = lf_lsq_workspace_bytes(B, L, H, W, order);
+    if (need == 0) return LF_ERR_UNSUPPORTED;
+    if (workspace_bytes < need) return LF_ERR_WORKSPACE_TOO_SMALL;
     const bool rowsep = (yrow != nullptr) && (W % 4 == 0);
     if (!rowsep && !ytab) return LF_ERR_INVALID_ARGUMENT;
     const int groups = rowsep ? (L + LSQ_MAXL - 1) / LSQ_MAXL : L;
     a.rows_per_cta = pick_rows_per_cta(B, groups, H);
     a.nchunks = (H + a.rows_per_cta - 1) / a.rows_per_cta;
-    const size_t nchunks_max = (size_t)(H + LSQ_WARPS - 1) / LSQ_WARPS;
-    a.partials = reinterpret_cast<double*>(workspace);
-    const size_t partial_bytes = (size_t)B * L * nchunks_max * (3 * order + 2) * sizeof(double);
-    a.tickets = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + ((partial_bytes + 15) / 16) * 16);
+    a.tickets = reinterpret_cast<int*>(workspace);
+    a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + LSQ_TICKET_BYTES);
     dim3 grid(a.nchunks, B, groups);
     if (rowsep)
         LSQ_DISPATCH(lsq_fwd_rowsep_kernel, grid, a);

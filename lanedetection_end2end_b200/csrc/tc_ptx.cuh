@@ -6,7 +6,7 @@
 
 namespace lf {
 
-constexpr uint32_t TC_SPIN_LIMIT = 1u << 28;
+constexpr uint32_t TC_SPIN_LIMIT = 1u << 22;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -30,8 +30,10 @@ def _worker(rank, world, port, q):
     red = FlatGradAllReduce(net)
     local = [None if p.grad is None else p.grad.clone() for p in net.parameters()]
     flat = red()
-    q.put((rank, p0, [None if g is None else g for g in local], flat.clone(),
-           [None if p.grad is None else p.grad.clone() for p in net.parameters()]))
+    # numpy arrays are pickled by value (torch tensors would be passed as shared-memory fds, which die
+    # with this process)
+    q.put((rank, p0.numpy(), [None if g is None else g.numpy() for g in local], flat.numpy().copy(),
+           [None if p.grad is None else p.grad.numpy().copy() for p in net.parameters()]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -47,6 +49,8 @@ def test_flat_gradient_allreduce_two_ranks():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
+    t = lambda v: None if v is None else torch.from_numpy(v)
+    res = [(r, t(p0), [t(x) for x in l], t(f), [t(x) for x in g]) for r, p0, l, f, g in res]
     (_, p0a, la, fa, ga), (_, p0b, lb, fb, gb) = res
     assert torch.equal(p0a, p0b)                      # broadcast worked
     assert torch.equal(fa, fb)                        # every rank holds the same reduced buffer

@@ -57,12 +57,18 @@ def run_block(block, x_nchw, gy_seed=0):
 
 
 def check_grads(block, oracle_P, prefix, tol=TOL):
+    """Per-parameter norm-wise gate.  Biases of convs that feed a BatchNorm have an analytically zero
+    gradient (the BN removes the mean): both sides are pure round-off there, so those are gated against
+    the block's overall gradient scale instead of their own."""
+    gmax = max(float(q.grad.abs().max()) for q in oracle_P.values() if q.grad is not None)
     for n, p in block.named_parameters():
         ref = oracle_P[prefix + "." + n].grad
-        scale = max(float(ref.abs().max()), 1e-3 * max(float(q.grad.abs().max()) for q in oracle_P.values()
-                                                        if q.grad is not None))
         err = float((p.grad.double().cpu() - ref).abs().max())
-        assert err <= tol * scale, (n, err, scale)
+        if float(ref.abs().max()) < 1e-6 * gmax:
+            assert err <= 1e-3 * gmax, (n, err, gmax)
+        else:
+            scale = max(float(ref.abs().max()), 1e-3 * gmax)
+            assert err <= tol * scale, (n, err, scale)
 
 
 @pytest.mark.parametrize("cin,cout,H,W", [(3, 16, 32, 48), (16, 64, 16, 24), (64, 128, 8, 12)])
