@@ -194,6 +194,8 @@ def run_ours(a, cfg):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _capi.lib()     # fail loudly if the extension is missing
+    from lanedetection_end2end_b200 import ops_net
+    ops_net.set_conv_mode(a.conv_mode)
 
     args = build_args(cfg)
     L, B = cfg["nclasses"], cfg["batch"]
@@ -315,7 +317,7 @@ def run_ours(a, cfg):
                                    "note": "launch-latency regime at this size; see bench_lsq.py for the stress config"}
         outdir = os.path.join(ROOT, "gpurun_out")
         if os.path.isdir(outdir):
-            json.dump(table, open(os.path.join(outdir, "kernel_table_n%d.json" % world), "w"), indent=1)
+            json.dump(table, open(os.path.join(outdir, "kernel_table_%s_n%d.json" % (a.conv_mode, world)), "w"), indent=1)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -329,12 +331,13 @@ def run_ours(a, cfg):
         line = {"metric": "images/sec (fwd+bwd)", "value": imgs / (ms_dev * 1e-3), "unit": "images/sec",
                 "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "fp32", "data": "synthetic",
+                "dtype": "fp32" if a.conv_mode == "fp32" else "tf32 (fp32 storage and accumulate)", "data": "synthetic",
                 "config": {"workload": cfg["name"], "per_gpu_batch": B, "global_batch": world * B,
                            "resolution": "%dx%d" % (cfg["resize"], 2 * cfg["resize"]), "nclasses": L,
                            "order": cfg["order"], "parallelism": "dp%d" % world,
                            "l2": "no flush needed: ~6 GB of activations per step >> 126 MB L2",
-                           "conv_mode": "fp32 FFMA (parity mode)", "init": "kaiming, torch.manual_seed(0)"},
+                           "conv_mode": ("fp32 FFMA (parity mode)" if a.conv_mode == "fp32" else
+                                         "tcgen05 TF32 for the 3-tap convs of non_bottleneck_1d (C=64/128), fp32 FFMA elsewhere"), "init": "kaiming, torch.manual_seed(0)"},
                 "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / a.steps},
                 "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches,
@@ -356,6 +359,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
     ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=8, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-mode", dest="conv_mode", default=os.environ.get("LANEFIT_CONV_MODE", "fp32"),
+                    choices=["fp32", "tf32"], help="fp32 = CUDA-core parity mode, tf32 = tcgen05 tensor cores")
     a = ap.parse_args()
     cfg = dict(CONFIGS[a.config])
     if a.batch:
