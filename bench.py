@@ -137,24 +137,43 @@ def cpu_port_run(cfg, steps, warmup, sample_images):
     valid = torch.ones(Bs, 4, 56, dtype=torch.float64)
     valid[:, :, :8] = 0
     drop_p = {p: (0.03 if p.startswith("encoder.layers.") and int(p.split(".")[-1]) < 6 else 0.3) for p, _ in eo.ENC_NB}
+
+    def one_step(xb, xgtb, validb):
+        for p in P.values():
+            p.grad = None
+        nb = xb.shape[0]
+        masks = {k: (torch.rand(nb, P[k + ".bn2.weight"].numel()) >= pr).float() / (1 - pr) for k, pr in drop_p.items()}
+        # masked rows are skipped (identical to multiplying by zero for finite grids; at resize 320 the
+        # reference itself yields NaN, SURVEY.md 7.2 #10)
+        loss, _, _, _ = eo.full_step(xb, P, grid, order, L, zero_rows, xgtb, validb, drop_masks=masks, loss_obj=crit,
+                                     resize=R, skip_rows=zero_rows if R != 256 else 0)
+        loss.backward()
+
+    # "all the host threads it can use": pick the thread count that is actually fastest on this host
+    # (128 threads on small convolutions are far slower than 16-32), on a 2-image probe
+    best_nt, best_t = cores, None
+    for nt in sorted({n for n in (8, 16, 32, 64, cores) if n <= cores}):
+        torch.set_num_threads(nt)
+        one_step(x[:2], xgt[:2], valid[:2])
+        t0 = time.perf_counter()
+        one_step(x[:2], xgt[:2], valid[:2])
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best_nt, best_t = nt, dt
+    torch.set_num_threads(best_nt)
+    cores_used = best_nt
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        for p in P.values():
-            p.grad = None
-        masks = {k: (torch.rand(Bs, P[k + ".bn2.weight"].numel()) >= pr).float() / (1 - pr) for k, pr in drop_p.items()}
-        # masked rows are skipped (identical to multiplying by zero for finite grids; at resize 320 the
-        # reference itself yields NaN, SURVEY.md 7.2 #10)
-        loss, _, _, _ = eo.full_step(x, P, grid, order, L, zero_rows, xgt, valid, drop_masks=masks, loss_obj=crit,
-                                     resize=R, skip_rows=zero_rows if R != 256 else 0)
-        loss.backward()
+        one_step(x, xgt, valid)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
     med = statistics.median(times)
-    return {"value": Bs / med, "unit": "images/sec", "cores": cores, "kind": "port",
+    return {"value": Bs / med, "unit": "images/sec", "cores": cores_used, "kind": "port",
             "sample": "%d steps x %d images (of the %d-image batch), fwd+bwd fp32, torch-CPU oracle port of the "
-                      "reference modules, %d threads, median step %.3f s" % (steps, Bs, cfg["batch"], cores, med),
+                      "reference modules, %d threads (fastest of the tried counts; host has %d), median step %.3f s"
+                      % (steps, Bs, cfg["batch"], cores_used, cores, med),
             "ms_per_step": med * 1e3, "images_per_step": Bs}
 
 
