@@ -74,9 +74,9 @@ class backprojection_loss(nn.Module):
         x_cal = num / den
         x_err = (x_gt - x_cal) * valid_samples                          # (:214)
         nvalid = valid_samples.sum()
-        loss = torch.sum(x_err ** 2) / nvalid                           # (:215)
-        if nvalid == 0:
-            loss = 0
+        # loss = sum(err^2) / nvalid, and 0 when nothing is valid (:215-217) -- written without the
+        # reference's host-side `if nvalid == 0` so the step has no sync and can live in a CUDA graph
+        loss = torch.sum(x_err ** 2) / torch.where(nvalid == 0, torch.ones_like(nvalid), nvalid)
         return loss, x_cal * valid_samples
 
 

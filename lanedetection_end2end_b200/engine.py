@@ -1,0 +1,68 @@
+"""Whole-step CUDA graph for the training hot path.
+
+One step = zero grads -> ``Net.forward`` -> backprojection loss over the lanes -> backward
+(-> flat gradient all-reduce when data-parallel): ~600 kernel launches of a few microseconds
+each.  Eagerly, the Python/ctypes cost per launch bounds the step once the kernels
+are fast; captured once into a ``torch.cuda.CUDAGraph`` the step is a single replay.  Inputs live
+in static device buffers (``copy_`` new batches in, asynchronously from pinned host memory); the loss and
+the LSQ status word are static outputs the caller reads when it wants to (no sync inside the step).
+
+The graph only contains our C-ABI kernels, a handful of tiny float64 torch ops of the loss, torch's
+graph-safe Philox draws for the Dropout2d masks, and (optionally) the NCCL all-reduce.
+"""
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, criterion, nclasses, example_x, example_xgt, example_valid, reducer=None, warmup=3):
+        self.model = model
+        self.crit = criterion
+        self.L = nclasses
+        self.reducer = reducer
+        dev = example_x.device
+        self.x = example_x.clone()
+        self.xgt = example_xgt.clone()
+        self.valid = example_valid.clone()
+        self.gt_line = torch.zeros(example_x.shape[0], 4)
+        model.defer_status_check = True
+        self.params = [p for p in model.parameters() if p.requires_grad]
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._eager_step(first=True)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        # gradients now exist as persistent tensors; the captured step zeroes and re-accumulates them
+        self.grads = [p.grad for p in self.params if p.grad is not None]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager_step(first=False)
+        self.status = model.lsq_status
+
+    def _eager_step(self, first):
+        if first:
+            self.model.zero_grad(set_to_none=True)
+        else:
+            torch._foreach_zero_(self.grads)
+        out = self.model(self.x, self.gt_line, True)
+        loss = 0
+        for l in range(self.L):
+            ll, _ = self.crit(out[l], self.xgt[:, l], self.valid[:, l])
+            loss = loss + ll
+        loss = loss / self.L
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer()
+        return loss.detach()
+
+    def load(self, x, xgt, valid):
+        """Stage a new batch (device or pinned-host tensors) into the static input buffers."""
+        self.x.copy_(x, non_blocking=True)
+        self.xgt.copy_(xgt, non_blocking=True)
+        self.valid.copy_(valid, non_blocking=True)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.loss
