@@ -148,10 +148,13 @@ typedef struct LfConvTcArgs {
     const float* mask_src;
     const float* add_src;
     const float* add_mask;
+    float* colsum_partial; /* NULL, or [lf_conv1d_tc_supported(...)][C]: per-CTA column sums of `out`
+                              (the bias gradient when `out` is an output gradient); reduce with lf_vec_reduce */
     int N, H, W, C;
     int dy[3], dx[3];
     int relu;
 } LfConvTcArgs;
+/* 0 = unsupported shape, else the number of CTA rows of colsum_partial */
 int lf_conv1d_tc_supported(int N, int H, int W, int C);
 int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream);
 

@@ -38,6 +38,7 @@ struct TcArgs {
     const float* mask_src;
     const float* add_src;
     const float* add_mask;
+    float* colsum_partial;  // [gridDim.x / n_halves][Ctot] per-CTA column sums of the output, or NULL
     int N, H, W, Ctot;
     int bx, by;
     int dy[3], dx[3];
@@ -166,6 +167,9 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may access
         const int m = lane_base + lane;
         const int yy = m / a.bx, xx = m - yy * a.bx;
+        float csum[TC_BN];  // running column sums of this thread's pixel row over all tiles (bias gradient)
+#pragma unroll
+        for (int c = 0; c < TC_BN; ++c) csum[c] = 0.f;
         int it = 0;
         for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
             const int buf = it & 1;
@@ -208,11 +212,24 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
                     }
                     *reinterpret_cast<float4*>(a.out + off + c) = o;
+                    csum[c] += o.x; csum[c + 1] += o.y; csum[c + 2] += o.z; csum[c + 3] += o.w;
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+        if (a.colsum_partial) {
+            __shared__ float cs[4][TC_BN];
+#pragma unroll
+            for (int c = 0; c < TC_BN; ++c) {
+                const float v = warp_sum(csum[c]);
+                if (lane == 0) cs[warp & 3][c] = v;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+            const int t = threadIdx.x - 64;
+            if (t < TC_BN)
+                a.colsum_partial[(size_t)cta_m * a.Ctot + n_half * TC_BN + t] = (cs[0][t] + cs[1][t]) + (cs[2][t] + cs[3][t]);
         }
     }
     tc_fence_before();
@@ -243,11 +260,24 @@ static bool pick_patch(int H, int W, int* bx, int* by) {
 
 using namespace lf;
 
+static int tc_m_ctas(int N, int H, int W, int C, int bx, int by) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_halves = C / TC_BN;
+    const long long tiles = (long long)N * (H / by) * (W / bx);
+    long long m_ctas = sms / n_halves;
+    if (m_ctas > tiles) m_ctas = tiles;
+    return (int)(m_ctas < 1 ? 1 : m_ctas);
+}
+
+// returns 0 if the shape is unsupported, else the number of rows of the optional colsum_partial output
 extern "C" int lf_conv1d_tc_supported(int N, int H, int W, int C) {
     int bx, by;
     if (!(C == 64 || C == 128) || N <= 0) return 0;
     if (!pick_patch(H, W, &bx, &by)) return 0;
-    return tc_get_encode_fn() != nullptr;
+    if (tc_get_encode_fn() == nullptr) return 0;
+    return tc_m_ctas(N, H, W, C, bx, by);
 }
 
 extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
@@ -261,6 +291,7 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     TcEncodeTiledFn enc = tc_get_encode_fn();
     if (!enc) return LF_ERR_UNSUPPORTED;
     a.out = p.out; a.bias = p.bias; a.mask_src = p.mask_src; a.add_src = p.add_src; a.add_mask = p.add_mask;
+    a.colsum_partial = p.colsum_partial;
     a.N = p.N; a.H = p.H; a.W = p.W; a.Ctot = p.C; a.relu = p.relu;
     for (int t = 0; t < 3; ++t) {
         a.dy[t] = p.dy[t];
@@ -282,12 +313,7 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return LF_ERR_CUDA;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int m_ctas = sms / a.n_halves;
-    if (m_ctas > a.total_m_tiles) m_ctas = a.total_m_tiles;
-    if (m_ctas < 1) m_ctas = 1;
+    const int m_ctas = tc_m_ctas(p.N, p.H, p.W, p.C, a.bx, a.by);
     const int grid = m_ctas * a.n_halves;
     cudaError_t e;
     if (p.C == 128) {

@@ -132,13 +132,19 @@ def pack_tc_dgrad(w):
     return w.permute(1, 2, 3, 0).reshape(Ci, kh * kw * Co).contiguous()
 
 
-def tc_supported(x):
+def tc_rows(x):
+    """0 if the tcgen05 kernel does not take this shape, else the row count of its colsum partials."""
     N, H, W, C = x.shape
-    return bool(_lib().lf_conv1d_tc_supported(N, H, W, C))
+    return int(_lib().lf_conv1d_tc_supported(N, H, W, C))
 
 
-def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_src=None, add_mask=None):
-    """3-tap convolution on tcgen05.  taps: [(dy, dx)] * 3 in weight-slot order."""
+def tc_supported(x):
+    return tc_rows(x) > 0
+
+
+def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_src=None, add_mask=None, colsum=None):
+    """3-tap convolution on tcgen05.  taps: [(dy, dx)] * 3 in weight-slot order.  colsum: optional [C]
+    tensor receiving the column sums of `out` (bias gradient), accumulated in the kernel's epilogue."""
     N, H, W, C = x.shape
     a = LfConvTcArgs()
     a.inp, a.wpack, a.out = x.data_ptr(), wpack.data_ptr(), out.data_ptr()
@@ -146,38 +152,52 @@ def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_s
     a.mask_src = mask_src.data_ptr() if mask_src is not None else None
     a.add_src = add_src.data_ptr() if add_src is not None else None
     a.add_mask = add_mask.data_ptr() if add_mask is not None else None
+    part = None
+    if colsum is not None:
+        rows = tc_rows(x)
+        part = torch.empty(rows * C, dtype=torch.float32, device=x.device)
+        a.colsum_partial = part.data_ptr()
     a.N, a.H, a.W, a.C = N, H, W, C
     for t, (dy, dx) in enumerate(taps):
         a.dy[t], a.dx[t] = dy, dx
     a.relu = int(relu)
     _capi.call("lf_conv1d_tc", ctypes.byref(a), _stream(), flops=2 * N * H * W * 3 * C * C, nbytes=8 * N * H * W * C)
+    if part is not None:
+        _capi.call("lf_vec_reduce", ptr(part), rows, C, C, ptr(colsum), _stream())
     return out
 
 
-def conv3(x, w, vertical, dil, transposed, **epi):
+def conv3(x, w, vertical, dil, transposed, colsum=None, **epi):
     """One factorised 3-tap convolution of non_bottleneck_1d (or its input gradient when
-    ``transposed``): dispatches to the tcgen05 kernel in tf32 mode, else to the fp32 kernel."""
+    ``transposed``): dispatches to the tcgen05 kernel in tf32 mode, else to the fp32 kernel.
+    ``colsum`` ([C] tensor): also produce the per-channel sums of the result."""
     N, H, W, C = x.shape
     out = torch.empty_like(x)
     if CONV_MODE == "tf32" and C in (64, 128) and tc_supported(x):
         sgn = -1 if transposed else 1
         taps = [((sgn * (k - 1) * dil, 0) if vertical else (0, sgn * (k - 1) * dil)) for k in range(3)]
         wp = pack_tc_dgrad(w) if transposed else pack_tc_fwd(w)
-        return run_conv_tc(taps, x, wp, out, **epi)
+        return run_conv_tc(taps, x, wp, out, colsum=colsum, **epi)
     kh, kw = (3, 1) if vertical else (1, 3)
     ph, pw = (dil, 0) if vertical else (0, dil)
     dh, dw = (dil, 1) if vertical else (1, dil)
     if transposed:
         phases, _ = plans.conv_dgrad_plan_s1(H, W, kh, kw, ph, pw, dh, dw)
-        return run_conv(phases, x, pack_conv_dgrad(w), C, out, C, **epi)
-    phases, _ = plans.conv_fwd_plan(H, W, kh, kw, 1, ph, pw, dh, dw)
-    return run_conv(phases, x, pack_conv_fwd(w), C, out, C, **epi)
+        run_conv(phases, x, pack_conv_dgrad(w), C, out, C, **epi)
+    else:
+        phases, _ = plans.conv_fwd_plan(H, W, kh, kw, 1, ph, pw, dh, dw)
+        run_conv(phases, x, pack_conv_fwd(w), C, out, C, **epi)
+    if colsum is not None:
+        run_colsum(out, C, 0, colsum)
+    return out
 
 
-def wgrad3(x_in, d_out, w, vertical, dil):
-    """Weight + bias gradient of one factorised 3-tap convolution -> (dw [Co,Ci,kh,kw], db [Co])."""
+def wgrad3(x_in, d_out, w, vertical, dil, bias_grad="compute"):
+    """Weight + bias gradient of one factorised 3-tap convolution -> (dw [Co,Ci,kh,kw], db [Co] or None).
+    bias_grad: "compute" (column sums of d_out), or "skip" (the caller gets it elsewhere)."""
     N, H, W, C = x_in.shape
-    dw, db = torch.empty_like(w), torch.empty(C, dtype=torch.float32, device=x_in.device)
+    dw = torch.empty_like(w)
+    db = torch.empty(C, dtype=torch.float32, device=x_in.device) if bias_grad == "compute" else None
     lay = (1, 3, C * 3)                                   # (tap, ci, co) strides of [Co,Ci,3] weights
     nctas = _lib().lf_wgrad3_tc_ctas(N, H, W, C) if (CONV_MODE == "tf32" and C in (64, 128)) else 0
     if nctas > 0:
@@ -188,7 +208,8 @@ def wgrad3(x_in, d_out, w, vertical, dil):
         _capi.call("lf_wgrad3_tc", ptr(x_in), ptr(d_out), N, H, W, C, tdy, tdx, ptr(partial), nctas, st,
                    flops=2 * N * H * W * 3 * C * C, nbytes=8 * N * H * W * C)
         _capi.call("lf_wgrad_reduce", ptr(partial), nctas, 3, C, C, C, C, ptr(dw), lay[0], lay[1], lay[2], st)
-        run_colsum(d_out, C, 0, db)
+        if db is not None:
+            run_colsum(d_out, C, 0, db)
         return dw, db
     kh, kw = (3, 1) if vertical else (1, 3)
     ph, pw = (dil, 0) if vertical else (0, dil)
@@ -404,19 +425,25 @@ class Nb1dFunction(torch.autograd.Function):
 
         # y = relu(bn2(t5)*drop + x)
         d5, dg2, dbe2 = bn_backward(dy, y, drop, t5, s2, g2)
+        # Bias gradients.  conv1x3_1 / conv1x3_2 feed a BatchNorm: sum_pixels(BN backward output) == 0
+        # identically (the reference's autograd returns pure round-off there), so db2 = db4 = 0.
+        # conv3x1_1 / conv3x1_2 feed a ReLU: db = column sums of the masked input gradient, which the
+        # dgrad launch below accumulates in its epilogue (colsum=...).
+        db2, db4 = torch.zeros(C, device=x.device), torch.zeros(C, device=x.device)
+        db1, db3 = _empty((C,), x), _empty((C,), x)
         # conv1x3_2 (dilated)
-        dw4, db4 = wgrad3(t4, d5, w4, False, dil)
-        d4 = conv3(d5, w4, False, dil, True, mask_src=t4)
+        dw4, _ = wgrad3(t4, d5, w4, False, dil, bias_grad="skip")
+        d4 = conv3(d5, w4, False, dil, True, colsum=db3, mask_src=t4)
         # conv3x1_2 (dilated)
-        dw3, db3 = wgrad3(t3, d4, w3, True, dil)
+        dw3, _ = wgrad3(t3, d4, w3, True, dil, bias_grad="skip")
         d3 = conv3(d4, w3, True, dil, True, mask_src=t3)
         # bn1 (+relu already applied through mask_src=t3)
         d2, dg1, dbe1 = bn_backward(d3, None, None, t2, s1, g1)
         # conv1x3_1
-        dw2, db2 = wgrad3(t1, d2, w2, False, 1)
-        d1 = conv3(d2, w2, False, 1, True, mask_src=t1)
+        dw2, _ = wgrad3(t1, d2, w2, False, 1, bias_grad="skip")
+        d1 = conv3(d2, w2, False, 1, True, colsum=db1, mask_src=t1)
         # conv3x1_1, plus the residual branch: dx = dgrad + dy*(y>0)
-        dw1, db1 = wgrad3(x, d1, w1, True, 1)
+        dw1, _ = wgrad3(x, d1, w1, True, 1, bias_grad="skip")
         dx = conv3(d1, w1, True, 1, True, add_src=dy, add_mask=y)
         return (dx, dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2, None, None, None, None, None, None,
                 None)
