@@ -90,6 +90,41 @@ __device__ __forceinline__ float4 load_map4(const void* base, size_t elem_off) {
         return ld_stream_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off));
     }
 }
+// V consecutive map elements per lane and load: 4 fp32 (16 B) or 8 bf16 (16 B)
+template <bool BF16>
+struct MapVec {
+    static constexpr int V = BF16 ? 8 : 4;
+};
+template <bool BF16>
+__device__ __forceinline__ void load_mapv(const void* base, size_t elem_off, float (&v)[MapVec<BF16>::V]) {
+    if constexpr (BF16) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off));
+        const float4 a = bf16x4_to_f4(make_uint2(u.x, u.y)), b = bf16x4_to_f4(make_uint2(u.z, u.w));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ void store_mapv(void* base, size_t elem_off, const float (&v)[MapVec<BF16>::V]) {
+    if constexpr (BF16) {
+        const uint2 a = f4_to_bf16x4(make_float4(v[0], v[1], v[2], v[3]));
+        const uint2 b = f4_to_bf16x4(make_float4(v[4], v[5], v[6], v[7]));
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = make_uint4(a.x, a.y, b.x, b.y);
+    } else {
+        st_stream_f4(reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off), make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+template <int V>
+__device__ __forceinline__ void load_xv(const float* xrow, int cv, float (&x)[V]) {
+#pragma unroll
+    for (int q = 0; q < V / 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(xrow) + cv * (V / 4) + q);
+        x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
+    }
+}
+
 template <bool BF16>
 __device__ __forceinline__ float load_map1(const void* base, size_t elem_off) {
     if (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[elem_off]);
@@ -297,7 +332,8 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const Ls
     const int l0 = lg * LSQ_MAXL;
     const int nl = min(LSQ_MAXL, a.L - l0);
     const int d = a.order, NM = 3 * d + 2;
-    const int W4 = a.W >> 2;
+    constexpr int V = MapVec<BF16>::V;
+    const int WV = a.W / V;
     // lane k owns moment k:  k <= 2d -> S_k (power k of y, times A);  else T_{k-2d-1} (times B)
     const bool useB = lane > 2 * d;
     const int ek = useB ? lane - (2 * d + 1) : lane;
@@ -313,7 +349,7 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const Ls
             if (a.masked) {
                 for (int l = 0; l < nl; ++l) {
                     float* m = a.masked + ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff;
-                    for (int c4 = lane; c4 < W4; c4 += 32)
+                    for (int c4 = lane; c4 < (a.W >> 2); c4 += 32)
                         st_stream_f4(reinterpret_cast<float4*>(m) + c4, make_float4(0.f, 0.f, 0.f, 0.f));
                 }
             }
@@ -323,22 +359,31 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const Ls
 #pragma unroll
         for (int l = 0; l < LSQ_MAXL; ++l) A[l] = Bx[l] = 0.f;
 #pragma unroll 2
-        for (int c4 = lane; c4 < W4; c4 += 32) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(a.xtab + rowoff) + c4);
+        for (int cv = lane; cv < WV; cv += 32) {
+            float x[V];
+            load_xv<V>(a.xtab + rowoff, cv, x);
 #pragma unroll
             for (int l = 0; l < LSQ_MAXL; ++l) {
                 if (l < nl) {
-                    const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff + 4 * (size_t)c4;
-                    const float4 o = load_map4<BF16>(a.o, off);
-                    float4 v;
-                    v.x = act_fn<ACT_T>(o.x, a.act);
-                    v.y = act_fn<ACT_T>(o.y, a.act);
-                    v.z = act_fn<ACT_T>(o.z, a.act);
-                    v.w = act_fn<ACT_T>(o.w, a.act);
-                    if (a.masked) st_stream_f4(reinterpret_cast<float4*>(a.masked + off), v);
-                    const float wx = v.x * v.x, wy = v.y * v.y, wz = v.z * v.z, ww = v.w * v.w;
-                    A[l] += (wx + wy) + (wz + ww);
-                    Bx[l] += fmaf(wx, x.x, wy * x.y) + fmaf(wz, x.z, ww * x.w);
+                    const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff + (size_t)V * cv;
+                    float o[V];
+                    load_mapv<BF16>(a.o, off, o);
+                    float sa = 0.f, sb = 0.f;
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        o[e] = act_fn<ACT_T>(o[e], a.act);
+                        const float w = o[e] * o[e];
+                        sa += w;
+                        sb = fmaf(w, x[e], sb);
+                    }
+                    if (a.masked) {
+#pragma unroll
+                        for (int q = 0; q < V / 4; ++q)
+                            st_stream_f4(reinterpret_cast<float4*>(a.masked + off) + q,
+                                         make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+                    }
+                    A[l] += sa;
+                    Bx[l] += sb;
                 }
             }
         }
@@ -440,15 +485,19 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const Ls
     const int l0 = lg * LSQ_MAXL;
     const int nl = min(LSQ_MAXL, a.L - l0);
     const int d = a.order;
-    const int W4 = a.W >> 2;
+    constexpr int V = MapVec<BF16>::V;
+    const int WV = a.W / V;
     lsq_bwd_load_coeffs(a, b, l0, nl, bs, zs);
     const int r_end = min(a.H, (chunk + 1) * a.rows_per_cta);
     for (int r = chunk * a.rows_per_cta + warp; r < r_end; r += LSQ_WARPS) {
         const size_t rowoff = (size_t)r * a.W;
         if (r < a.mask_rows) {
+            float z[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) z[e] = 0.f;
             for (int l = 0; l < nl; ++l) {
                 const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff;
-                for (int c4 = lane; c4 < W4; c4 += 32) store_map4<BF16>(a.d_o, off + 4 * (size_t)c4, make_float4(0.f, 0.f, 0.f, 0.f));
+                for (int cv = lane; cv < WV; cv += 32) store_mapv<BF16>(a.d_o, off + (size_t)V * cv, z);
             }
             continue;
         }
@@ -468,19 +517,19 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const Ls
             }
         }
 #pragma unroll 2
-        for (int c4 = lane; c4 < W4; c4 += 32) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(a.xtab + rowoff) + c4);
+        for (int cv = lane; cv < WV; cv += 32) {
+            float x[V];
+            load_xv<V>(a.xtab + rowoff, cv, x);
 #pragma unroll
             for (int l = 0; l < LSQ_MAXL; ++l) {
                 if (l < nl) {
-                    const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff + 4 * (size_t)c4;
-                    const float4 o = load_map4<BF16>(a.o, off);
-                    float4 g;
-                    g.x = dact_times_act<ACT_T>(o.x, a.act) * (((x.x - qh[l]) - ql[l]) * sf[l]);
-                    g.y = dact_times_act<ACT_T>(o.y, a.act) * (((x.y - qh[l]) - ql[l]) * sf[l]);
-                    g.z = dact_times_act<ACT_T>(o.z, a.act) * (((x.z - qh[l]) - ql[l]) * sf[l]);
-                    g.w = dact_times_act<ACT_T>(o.w, a.act) * (((x.w - qh[l]) - ql[l]) * sf[l]);
-                    store_map4<BF16>(a.d_o, off, g);
+                    const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff + (size_t)V * cv;
+                    float o[V], g[V];
+                    load_mapv<BF16>(a.o, off, o);
+#pragma unroll
+                    for (int e = 0; e < V; ++e)
+                        g[e] = dact_times_act<ACT_T>(o[e], a.act) * (((x[e] - qh[l]) - ql[l]) * sf[l]);
+                    store_mapv<BF16>(a.d_o, off, g);
                 }
             }
         }
@@ -583,7 +632,7 @@ extern "C" int lf_lsq_fwd(const void* o, int o_dtype, const float* xtab, const f
     const size_t need = lf_lsq_workspace_bytes(B, L, H, W, order);
     if (need == 0) return LF_ERR_UNSUPPORTED;
     if (workspace_bytes < need) return LF_ERR_WORKSPACE_TOO_SMALL;
-    const bool rowsep = (yrow != nullptr) && (W % 4 == 0);
+    const bool rowsep = (yrow != nullptr) && (W % (o_dtype == LF_BF16 ? 8 : 4) == 0);
     if (!rowsep && !ytab) return LF_ERR_INVALID_ARGUMENT;
     const int groups = rowsep ? (L + LSQ_MAXL - 1) / LSQ_MAXL : L;
     a.rows_per_cta = pick_rows_per_cta(B, groups, H);
@@ -609,7 +658,7 @@ extern "C" int lf_lsq_bwd(const void* o, int o_dtype, const float* xtab, const f
     int rc = validate(a, o_dtype);
     if (rc != LF_OK) return rc;
     LF_REQUIRE(beta && zinv && gbeta && d_o);
-    const bool rowsep = (yrow != nullptr) && (W % 4 == 0);
+    const bool rowsep = (yrow != nullptr) && (W % (o_dtype == LF_BF16 ? 8 : 4) == 0);
     if (!rowsep && !ytab) return LF_ERR_INVALID_ARGUMENT;
     const int groups = rowsep ? (L + LSQ_MAXL - 1) / LSQ_MAXL : L;
     a.rows_per_cta = pick_rows_per_cta(B, groups, H);
