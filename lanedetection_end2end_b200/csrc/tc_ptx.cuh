@@ -115,13 +115,13 @@ inline TcEncodeTiledFn tc_get_encode_fn() {
 // dense NHWC fp32 activations [N,H,W,C] viewed as (ci:32, cblk:C/32, x:W, y:H, n:N); one box =
 // [bx*by pixels] x [32 channels] = rows of 128 bytes, 128B-swizzled; out-of-bounds -> zeros
 inline bool tc_encode_nhwc_map(TcEncodeTiledFn enc, CUtensorMap* tm, const float* base, int N, int H, int W, int C, int bx,
-                               int by) {
+                               int by, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     cuuint64_t dims[5] = {32, (cuuint64_t)(C / 32), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[4] = {128, (cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
     cuuint32_t box[5] = {32, 1, (cuuint32_t)bx, (cuuint32_t)by, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

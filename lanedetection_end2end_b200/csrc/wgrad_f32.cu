@@ -7,67 +7,110 @@
 
 namespace lf {
 
-constexpr int WG_TILE = 64;
-constexpr int WG_PX = 16;
+constexpr int WG_TILE = 64;       // padding granularity of the partial buffers
 constexpr int WG_THREADS = 256;
 
+// CTA tile TP x TQ of the weight gradient; every thread owns a 4x4 micro-tile.  When the tile needs
+// fewer than 256 threads (small channel counts: stem, C=16 blocks, 64->16 upsampler) the CTA splits
+// its pixels over G = 256 / ((TP/4)*(TQ/4)) thread groups and reduces them through shared memory at
+// the end, so no FMA is spent on zero padding.
+template <int TP, int TQ>
+struct WgCfg {
+    static constexpr int TPG = (TP / 4) * (TQ / 4);   // threads per pixel group
+    static constexpr int G = WG_THREADS / TPG;        // pixel groups
+    static constexpr int PXG = (TP == 16 && TQ == 16) ? 8 : 16;  // pixels per group and step
+    static constexpr int PXS = PXG * G;               // pixels per step
+    static constexpr int PF4 = PXS * TP / 4, QF4 = PXS * TQ / 4;  // float4 per tile
+    static constexpr int PL = (PF4 + WG_THREADS - 1) / WG_THREADS, QL = (QF4 + WG_THREADS - 1) / WG_THREADS;
+    static constexpr int SMEM_FLOATS = 2 * PXS * (TP + TQ);
+    static_assert(TPG * G == WG_THREADS, "tile");
+    static_assert(SMEM_FLOATS * 4 <= 48 * 1024, "smem");
+    static_assert(G == 1 || G * TP * TQ <= SMEM_FLOATS, "group reduction reuses the tile buffers");
+};
+
+template <int TP, int TQ>
 __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const WgradArgs a) {
-    __shared__ __align__(16) float Ps[2][WG_PX][WG_TILE];
-    __shared__ __align__(16) float Qs[2][WG_PX][WG_TILE];
+    using Cfg = WgCfg<TP, TQ>;
+    __shared__ __align__(16) float smem[Cfg::SMEM_FLOATS];
+    float(*Ps)[Cfg::PXS][TP] = reinterpret_cast<float(*)[Cfg::PXS][TP]>(smem);
+    float(*Qs)[Cfg::PXS][TQ] = reinterpret_cast<float(*)[Cfg::PXS][TQ]>(smem + 2 * Cfg::PXS * TP);
     const int tid = threadIdx.x;
-    const int tilesQ = a.CqPad / WG_TILE, tilesP = a.CpPad / WG_TILE;
+    // 16-wide tiles cover the (<= 16) real channels of a 64-padded buffer with ONE tile (host agrees)
+    const int tilesQ = (TQ == 16) ? 1 : a.CqPad / TQ, tilesP = (TP == 16) ? 1 : a.CpPad / TP;
     const int tq = blockIdx.x % tilesQ;
     const int tp = (blockIdx.x / tilesQ) % tilesP;
     const int t = blockIdx.x / (tilesQ * tilesP);
     const int split = blockIdx.y;
     const long long M = (long long)a.N * a.Hs * a.Ws;
     long long per = (M + a.nsplit - 1) / a.nsplit;
-    per = ((per + WG_PX - 1) / WG_PX) * WG_PX;
+    per = ((per + Cfg::PXS - 1) / Cfg::PXS) * Cfg::PXS;
     const long long m_begin = (long long)split * per;
     const long long m_end = min(M, m_begin + per);
 
-    const int lp = tid >> 4;   // pixel within the chunk
-    const int c4 = tid & 15;   // float4 column
-    const int tx = tid & 15, ty = tid >> 4;
-    const int cp0 = tp * WG_TILE + 4 * c4;
-    const int cq0 = tq * WG_TILE + 4 * c4;
-    const bool p_ch_ok = cp0 < a.Cp, q_ch_ok = cq0 < a.Cq;
+    const int g = tid / Cfg::TPG, r = tid % Cfg::TPG;
+    const int tx = r % (TQ / 4), ty = r / (TQ / 4);
     const int pdy = a.pdy[t], pdx = a.pdx[t], qdy = a.qdy[t], qdx = a.qdx[t];
     const bool do_qsum = (a.qsum_partial != nullptr) && t == 0 && tp == 0 && ty == 0;
 
     float acc[4][4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+        for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
     float qs[4] = {0.f, 0.f, 0.f, 0.f};
 
-    float4 rp, rq;
+    float4 rp[Cfg::PL], rq[Cfg::QL];
     auto load = [&](long long m0) {
-        const long long m = m0 + lp;
-        rp = make_float4(0.f, 0.f, 0.f, 0.f);
-        rq = rp;
-        if (m < m_end) {
-            const int n = (int)(m / (a.Hs * a.Ws));
-            const int rem = (int)(m - (long long)n * (a.Hs * a.Ws));
-            const int j = rem / a.Ws;
-            const int i = rem - j * a.Ws;
-            const int py = j * a.psy + pdy, px = i * a.psx + pdx;
-            const int qy = j * a.qsy + qdy, qx = i * a.qsx + qdx;
-            const bool pin = py >= 0 && py < a.Hp && px >= 0 && px < a.Wp;
-            const bool qin = qy >= 0 && qy < a.Hq && qx >= 0 && qx < a.Wq;
-            // out-of-tensor operands are zero, so a product term exists only where both are inside
-            if (pin && p_ch_ok)
-                rp = __ldg(reinterpret_cast<const float4*>(
-                    a.P + ((size_t)(n * a.Hp + py) * a.Wp + px) * a.p_cstride + a.p_coff + cp0));
-            if (qin && q_ch_ok)
-                rq = __ldg(reinterpret_cast<const float4*>(
-                    a.Q + ((size_t)(n * a.Hq + qy) * a.Wq + qx) * a.q_cstride + a.q_coff + cq0));
+#pragma unroll
+        for (int q = 0; q < Cfg::PL; ++q) {
+            rp[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int f = tid + q * WG_THREADS;
+            if (f < Cfg::PF4) {
+                const int lp = f / (TP / 4), c4 = f % (TP / 4);
+                const long long m = m0 + lp;
+                const int cp0 = tp * TP + 4 * c4;
+                if (m < m_end && cp0 < a.Cp) {
+                    const int n = (int)(m / (a.Hs * a.Ws));
+                    const int rem = (int)(m - (long long)n * (a.Hs * a.Ws));
+                    const int j = rem / a.Ws, i = rem - j * a.Ws;
+                    const int py = j * a.psy + pdy, px = i * a.psx + pdx;
+                    if (py >= 0 && py < a.Hp && px >= 0 && px < a.Wp)
+                        rp[q] = __ldg(reinterpret_cast<const float4*>(
+                            a.P + ((size_t)(n * a.Hp + py) * a.Wp + px) * a.p_cstride + a.p_coff + cp0));
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Cfg::QL; ++q) {
+            rq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int f = tid + q * WG_THREADS;
+            if (f < Cfg::QF4) {
+                const int lp = f / (TQ / 4), c4 = f % (TQ / 4);
+                const long long m = m0 + lp;
+                const int cq0 = tq * TQ + 4 * c4;
+                if (m < m_end && cq0 < a.Cq) {
+                    const int n = (int)(m / (a.Hs * a.Ws));
+                    const int rem = (int)(m - (long long)n * (a.Hs * a.Ws));
+                    const int j = rem / a.Ws, i = rem - j * a.Ws;
+                    const int qy = j * a.qsy + qdy, qx = i * a.qsx + qdx;
+                    if (qy >= 0 && qy < a.Hq && qx >= 0 && qx < a.Wq)
+                        rq[q] = __ldg(reinterpret_cast<const float4*>(
+                            a.Q + ((size_t)(n * a.Hq + qy) * a.Wq + qx) * a.q_cstride + a.q_coff + cq0));
+                }
+            }
         }
     };
     auto store = [&](int buf) {
-        *reinterpret_cast<float4*>(&Ps[buf][lp][4 * c4]) = rp;
-        *reinterpret_cast<float4*>(&Qs[buf][lp][4 * c4]) = rq;
+#pragma unroll
+        for (int q = 0; q < Cfg::PL; ++q) {
+            const int f = tid + q * WG_THREADS;
+            if (f < Cfg::PF4) *reinterpret_cast<float4*>(&Ps[buf][f / (TP / 4)][4 * (f % (TP / 4))]) = rp[q];
+        }
+#pragma unroll
+        for (int q = 0; q < Cfg::QL; ++q) {
+            const int f = tid + q * WG_THREADS;
+            if (f < Cfg::QF4) *reinterpret_cast<float4*>(&Qs[buf][f / (TQ / 4)][4 * (f % (TQ / 4))]) = rq[q];
+        }
     };
 
     if (m_begin < m_end) {
@@ -76,20 +119,21 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const WgradArgs a
     }
     __syncthreads();
     int it = 0;
-    for (long long m0 = m_begin; m0 < m_end; m0 += WG_PX, ++it) {
+    for (long long m0 = m_begin; m0 < m_end; m0 += Cfg::PXS, ++it) {
         const int buf = it & 1;
-        const bool more = (m0 + WG_PX) < m_end;
-        if (more) load(m0 + WG_PX);
+        const bool more = (m0 + Cfg::PXS) < m_end;
+        if (more) load(m0 + Cfg::PXS);
 #pragma unroll
-        for (int p = 0; p < WG_PX; ++p) {
+        for (int pp = 0; pp < Cfg::PXG; ++pp) {
+            const int p = pp * Cfg::G + g;  // groups interleave the pixels of a step
             const float4 av = *reinterpret_cast<const float4*>(&Ps[buf][p][4 * ty]);
             const float4 bv = *reinterpret_cast<const float4*>(&Qs[buf][p][4 * tx]);
             const float aa[4] = {av.x, av.y, av.z, av.w};
             const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(aa[r], bb[c], acc[r][c]);
+                for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(aa[i], bb[c], acc[i][c]);
             if (do_qsum) {
                 qs[0] += bb[0]; qs[1] += bb[1]; qs[2] += bb[2]; qs[3] += bb[3];
             }
@@ -97,14 +141,40 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const WgradArgs a
         if (more) store(buf ^ 1);
         __syncthreads();
     }
-    float* dst = a.partial + (((size_t)split * a.ntaps + t) * a.CpPad + tp * WG_TILE + 4 * ty) * a.CqPad +
-                 tq * WG_TILE + 4 * tx;
+    float* dst = a.partial + (((size_t)split * a.ntaps + t) * a.CpPad + tp * TP) * a.CqPad + tq * TQ;
+    float* qdst = a.qsum_partial ? a.qsum_partial + (size_t)split * a.CqPad + tq * TQ : nullptr;
+    if (Cfg::G == 1) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-        *reinterpret_cast<float4*>(dst + (size_t)r * a.CqPad) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-    if (do_qsum)
-        *reinterpret_cast<float4*>(a.qsum_partial + (size_t)split * a.CqPad + tq * WG_TILE + 4 * tx) =
-            make_float4(qs[0], qs[1], qs[2], qs[3]);
+        for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(dst + (size_t)(4 * ty + i) * a.CqPad + 4 * tx) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (do_qsum) *reinterpret_cast<float4*>(qdst + 4 * tx) = make_float4(qs[0], qs[1], qs[2], qs[3]);
+    } else {
+        // fixed-order reduction over the G pixel groups through shared memory (tiles are free now)
+        float* red = smem;  // [G][TP][TQ]
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(&red[((size_t)g * TP + 4 * ty + i) * TQ + 4 * tx]) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        __syncthreads();
+        for (int e = tid; e < TP * TQ; e += WG_THREADS) {
+            float sum = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < Cfg::G; ++gg) sum += red[(size_t)gg * TP * TQ + e];
+            dst[(size_t)(e / TQ) * a.CqPad + (e % TQ)] = sum;
+        }
+        if (a.qsum_partial != nullptr && t == 0 && tp == 0) {
+            __syncthreads();
+            if (ty == 0) *reinterpret_cast<float4*>(&red[g * TQ + 4 * tx]) = make_float4(qs[0], qs[1], qs[2], qs[3]);
+            __syncthreads();
+            for (int e = tid; e < TQ; e += WG_THREADS) {
+                float sum = 0.f;
+#pragma unroll
+                for (int gg = 0; gg < Cfg::G; ++gg) sum += red[gg * TQ + e];
+                qdst[e] = sum;
+            }
+        }
+    }
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int ntaps, int Cp, int Cq, int CpPad,
@@ -131,23 +201,34 @@ __global__ void vec_reduce_kernel(const float* __restrict__ partial, int nsplit,
 }
 
 constexpr int COLSUM_THREADS = 256;
-constexpr int COLSUM_PIX_PER_BLOCK = 2048;
+constexpr int COLSUM_MAX_BLOCKS = 148 * 4;
+constexpr int COLSUM_MIN_PIX = 128;
 
+// partial[blk][c] = sum over the block's pixel range of src[p*cstride + coff + c].
+// Thread -> (pixel lane, channel); channels fastest so a warp reads contiguous memory.
 __global__ void __launch_bounds__(COLSUM_THREADS) colsum_kernel(const float* __restrict__ src, long long npix, int C,
                                                                  int cstride, int coff, float* __restrict__ partial, int Cpad) {
-    // thread -> (pixel lane, channel); channels fastest so global reads are contiguous
     __shared__ float red[COLSUM_THREADS];
     const int tid = threadIdx.x;
-    const long long p0 = (long long)blockIdx.x * COLSUM_PIX_PER_BLOCK;
-    const long long p1 = min(npix, p0 + COLSUM_PIX_PER_BLOCK);
+    const long long per = (npix + gridDim.x - 1) / gridDim.x;
+    const long long p0 = (long long)blockIdx.x * per;
+    const long long p1 = min(npix, p0 + per);
     for (int cbase = 0; cbase < C; cbase += COLSUM_THREADS) {
-        const int cw = min(C - cbase, COLSUM_THREADS);   // channels handled this pass
-        const int lanes = COLSUM_THREADS / cw > 0 ? COLSUM_THREADS / cw : 1;
+        const int cw = min(C - cbase, COLSUM_THREADS);
+        const int lanes = COLSUM_THREADS / cw;
         const int c = tid % cw, pl = tid / cw;
-        float s = 0.f;
-        if (pl < lanes)
-            for (long long p = p0 + pl; p < p1; p += lanes) s += src[(size_t)p * cstride + coff + cbase + c];
-        red[tid] = (pl < lanes) ? s : 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // 4 independent chains hide the load latency
+        if (pl < lanes) {
+            long long p = p0 + pl;
+            for (; p + 3LL * lanes < p1; p += 4LL * lanes) {
+                s0 += src[(size_t)p * cstride + coff + cbase + c];
+                s1 += src[(size_t)(p + lanes) * cstride + coff + cbase + c];
+                s2 += src[(size_t)(p + 2LL * lanes) * cstride + coff + cbase + c];
+                s3 += src[(size_t)(p + 3LL * lanes) * cstride + coff + cbase + c];
+            }
+            for (; p < p1; p += lanes) s0 += src[(size_t)p * cstride + coff + cbase + c];
+        }
+        red[tid] = (pl < lanes) ? (s0 + s1) + (s2 + s3) : 0.f;
         __syncthreads();
         if (tid < cw) {
             float tot = 0.f;
@@ -171,8 +252,20 @@ extern "C" int lf_wgrad_f32(const LfWgradArgs* args, lf_stream_t stream_) {
     LF_REQUIRE(a.Cp % 4 == 0 && a.Cq % 4 == 0 && a.p_cstride % 4 == 0 && a.q_cstride % 4 == 0);
     LF_REQUIRE(a.p_coff % 4 == 0 && a.q_coff % 4 == 0);
     LF_REQUIRE(a.CpPad % WG_TILE == 0 && a.CqPad % WG_TILE == 0 && a.CpPad >= a.Cp && a.CqPad >= a.Cq);
-    dim3 grid((a.CpPad / WG_TILE) * (a.CqPad / WG_TILE) * a.ntaps, a.nsplit);
-    wgrad_f32_kernel<<<grid, WG_THREADS, 0, stream>>>(a);
+    const bool smallP = a.Cp <= 16, smallQ = a.Cq <= 16;
+    const int TP = smallP ? 16 : 64, TQ = smallQ ? 16 : 64;
+    // small tiles only cover the first 16 channels of the 64-padded buffers: one tile in that dimension
+    const int tilesP = smallP ? 1 : a.CpPad / 64, tilesQ = smallQ ? 1 : a.CqPad / 64;
+    const WgradArgs& b = a;
+    dim3 grid(tilesP * tilesQ * a.ntaps, a.nsplit);
+    if (smallP && smallQ)
+        wgrad_f32_kernel<16, 16><<<grid, WG_THREADS, 0, stream>>>(b);
+    else if (smallP)
+        wgrad_f32_kernel<16, 64><<<grid, WG_THREADS, 0, stream>>>(b);
+    else if (smallQ)
+        wgrad_f32_kernel<64, 16><<<grid, WG_THREADS, 0, stream>>>(b);
+    else
+        wgrad_f32_kernel<64, 64><<<grid, WG_THREADS, 0, stream>>>(b);
     return check_launch();
 }
 
@@ -194,7 +287,9 @@ extern "C" int lf_vec_reduce(const float* partial, int nsplit, int C, int Cpad, 
 }
 
 extern "C" int lf_colsum_blocks(long long npix) {
-    return (int)((npix + COLSUM_PIX_PER_BLOCK - 1) / COLSUM_PIX_PER_BLOCK);
+    long long b = (npix + COLSUM_MIN_PIX - 1) / COLSUM_MIN_PIX;
+    if (b > COLSUM_MAX_BLOCKS) b = COLSUM_MAX_BLOCKS;
+    return (int)(b < 1 ? 1 : b);
 }
 
 extern "C" int lf_colsum(const float* src, long long npix, int C, int cstride, int coff, float* partial, int Cpad,

@@ -2,8 +2,11 @@
 //     dW[t][ci][co] = sum_{n,y,x} X[n, y+dy[t], x+dx[t], ci] * dY[n, y, x, co]
 // = three GEMMs D_t[ci][co] = A_t[ci][px] * B[co][px]^T whose K dimension is the pixel index.
 // Both operands are MN-major for the tensor core: a TMA box [KP pixels x 32 channels] lands in shared
-// memory as KP rows of 128 bytes (128B swizzle) = one UMMA MN-major swizzle atom column (32 channels
-// contiguous, pixels along K); channel blocks of 32 sit KP*128 bytes apart (the descriptor's LBO).
+// memory as KP rows of 128 bytes = a column of UMMA MN-major swizzle atoms (32 channels contiguous,
+// pixels along K); channel blocks of 32 sit KP*128 bytes apart (the descriptor's LBO).  For 32-bit
+// MN-major operands the only legal shared-memory layout is the 128B swizzle with 32-byte atoms
+// (UMMA LayoutType SWIZZLE_128B_BASE32B <-> CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: 32B chunk index ^=
+// row & 3, 4 K-rows per atom); the plain 16-byte-atom swizzle silently yields zeros.
 // The SAME fp32 NHWC tensors feed it that feed the forward kernel -- TF32 multiply, fp32 accumulate.
 //
 // One persistent CTA owns a contiguous range of pixel patches (split-K), streams
@@ -49,11 +52,12 @@ struct WtCfg {
         (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
 };
 
-// MN-major, 128B-swizzled operand: 32 MN-elements (128 B) per row, 8 K-rows per atom (1024 B),
-// next 32-element MN block `lbo_bytes` further, next 8 K-rows 1024 B further.
+// MN-major operand, SWIZZLE_128B_BASE32B: 32 MN-elements (128 B) per K-row, 4 K-rows per swizzle atom
+// (SBO = 512 B between atoms), next 32-element MN block `lbo_bytes` further.
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout 1 <<61)
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
 template <int C>
@@ -249,8 +253,8 @@ extern "C" int lf_wgrad3_tc(const float* x, const float* dy, int N, int H, int W
     }
     a.total_patches = N * (H / a.by) * (W / a.bx);
     CUtensorMap tmX, tmDY;
-    if (!tc_encode_nhwc_map(enc, &tmX, x, N, H, W, C, a.bx, a.by)) return LF_ERR_CUDA;
-    if (!tc_encode_nhwc_map(enc, &tmDY, dy, N, H, W, C, a.bx, a.by)) return LF_ERR_CUDA;
+    if (!tc_encode_nhwc_map(enc, &tmX, x, N, H, W, C, a.bx, a.by, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return LF_ERR_CUDA;
+    if (!tc_encode_nhwc_map(enc, &tmDY, dy, N, H, W, C, a.bx, a.by, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return LF_ERR_CUDA;
     cudaError_t e;
     if (C == 128) {
         e = cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WtCfg<128>::SMEM_BYTES);
