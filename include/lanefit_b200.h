@@ -157,6 +157,9 @@ typedef struct LfConvTcArgs {
 /* 0 = unsupported shape, else the number of CTA rows of colsum_partial */
 int lf_conv1d_tc_supported(int N, int H, int W, int C);
 int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream);
+/* 2 (default) = halo-slab kernel (one TMA slab per 32-channel chunk shared by the three taps);
+ * 1 = first version (one TMA box per tap).  Same results; process-wide switch for A/B measurements. */
+void lf_conv1d_tc_set_variant(int variant);
 
 /* tcgen05 weight gradient of the same 3-tap convolutions:
  *   partial[cta][t][ci][co] = sum over this CTA's pixel range of x[n,y+dy[t],x+dx[t],ci] * dy[n,y,x,co]

@@ -3,19 +3,25 @@
 // their input gradients, C in {64, 128}, NHWC fp32 activations, TF32 multiply / fp32 accumulate
 // (the arithmetic cuDNN uses for the reference's fp32 convs on Ampere+).
 //
-//   out[n,y,x,co] = epi( sum_{t<3} sum_{ci} in[n, y+dy[t], x+dx[t], ci] * Wp[co][t*C + ci] )
+//   out[n,y,x,co] = epi( sum_{t<3} sum_{ci} in[n, (y,x) + o_t along the conv axis, ci] * Wp[co][t*C + ci] )
+//   with o_t in {-d, 0, +d} (forward) or {+d, 0, -d} (input gradient).
 //
-// GEMM view per CTA tile: M = 128 pixels (a bx x by patch), N = 64 output channels, K = 3*C.
+// GEMM view per CTA tile: M = 128 pixels = TA positions along the conv axis x TB across it
+// (TA x TB = 16x8 or 8x16), N = 64 output channels, K = 3*C.
 //  * B (all 3 taps of this CTA's 64 output channels, 48/96 KB) is TMA-loaded ONCE per CTA and
 //    stays in shared memory (persistent CTA, one per SM); tiles stream through it.
-//  * A: one TMA box per (tap, 32-channel chunk): [128 px x 32 ch] = 16 KB, 128B-swizzled; the tap
-//    shift is a coordinate offset of the box, out-of-image pixels are zero-filled by TMA (this is
-//    the conv padding, for any dilation).  6-8 stage mbarrier ring.
+//  * A: ONE TMA "slab" per 32-channel chunk: [(TA+2d) x TB pixels] x 32 ch, 128B-swizzled, with the
+//    cross axis fastest in shared memory.  The three taps are three VIEWS of the same slab, shifted by
+//    d*TB rows (TB is a multiple of 8, so every view starts on a 1024-byte boundary and keeps the 8-row
+//    swizzle phase): the input crosses the L2->SM fabric (TA+2d)/TA times instead of 3 times -- the
+//    first version of this kernel (conv_tc_v1.cu, one box per tap) was measured L2->SM bound
+//    (216 MB / 35 us = 6.2 TB/s, profiles/r01).  Image borders (the conv zero padding, any dilation)
+//    are TMA out-of-bounds fill.  Multi-stage mbarrier ring.
 //  * MMA: tcgen05.mma.cta_group::1.kind::tf32, M=128 N=64 K=8, issued by one elected thread;
 //    accumulators in TMEM, double-buffered (2 x 64 columns) so the epilogue of tile i overlaps
 //    the MMAs of tile i+1.
 //  * Epilogue: 4 warps, tcgen05.ld 32x32b (thread = pixel row), + bias, ReLU, ReLU-backward mask,
-//    residual-gradient add, 128-bit stores.
+//    residual-gradient add, running column sums (bias gradient), 128-bit stores.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
 #include <cuda.h>
 
@@ -23,14 +29,21 @@
 #include "lf_net.h"
 #include "tc_ptx.cuh"
 
+// variant 1 (conv_tc_v1.cu)
+int lf_conv1d_tc_supported_v1(int N, int H, int W, int C);
+int lf_conv1d_tc_v1(const LfConvTcArgs* args, lf_stream_t stream_);
+
 namespace lf {
+
+static int g_tc_variant = 2;  // 2 = halo slab (this file), 1 = one box per tap (conv_tc_v1.cu)
 
 constexpr int TC_THREADS = 192;
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 64;
-constexpr int TC_KCH = 32;                        // fp32 elements per 128-byte swizzle row
-constexpr int TC_A_STAGE_BYTES = TC_BM * 128;     // 16 KB
-constexpr int TC_B_ATOM_BYTES = TC_BN * 128;      // 8 KB
+constexpr int TC_KCH = 32;                    // fp32 elements per 128-byte swizzle row
+constexpr int TC_B_ATOM_BYTES = TC_BN * 128;  // 8 KB
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_LIMIT = 226 * 1024;  // 227 KB opt-in maximum minus the 1 KB static epilogue scratch
 
 struct TcArgs {
     float* out;
@@ -40,11 +53,15 @@ struct TcArgs {
     const float* add_mask;
     float* colsum_partial;  // [gridDim.x / n_halves][Ctot] per-CTA column sums of the output, or NULL
     int N, H, W, Ctot;
-    int bx, by;
-    int dy[3], dx[3];
+    int vertical;           // conv axis: 1 = y (3x1), 0 = x (1x3)
+    int TA, TB;             // tile extent along / across the conv axis (TA*TB = 128)
+    int dil;                // tap spacing d
+    int tap_row[3];         // first slab row (128-byte rows) of the view used by weight slot t
+    int tiles_a, tiles_b;
     int relu;
     int n_halves;
     int total_m_tiles;
+    int stages, stage_bytes;
 };
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
@@ -57,11 +74,8 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3)
 
 template <int C>
 struct TcCfg {
-    static constexpr int KCHUNKS = C / TC_KCH;         // 32-channel chunks per tap
-    static constexpr int KSTEPS = 3 * KCHUNKS;         // pipeline steps per tile
-    static constexpr int B_BYTES = KSTEPS * TC_B_ATOM_BYTES;
-    static constexpr int STAGES = (C == 128) ? 6 : 8;
-    static constexpr int SMEM_BYTES = 1024 + B_BYTES + STAGES * TC_A_STAGE_BYTES + 256;
+    static constexpr int KCHUNKS = C / TC_KCH;  // 32-channel chunks (= slabs per tile)
+    static constexpr int B_BYTES = 3 * KCHUNKS * TC_B_ATOM_BYTES;
 };
 
 template <int C>
@@ -72,10 +86,10 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sB = smem;
     uint8_t* sA = smem + Cfg::B_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + Cfg::STAGES * TC_A_STAGE_BYTES);
-    uint64_t* full = bars;                       // [STAGES]
-    uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
-    uint64_t* bfull = bars + 2 * Cfg::STAGES;    // [1]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)a.stages * a.stage_bytes);
+    uint64_t* full = bars;                       // [TC_MAX_STAGES]
+    uint64_t* empty = bars + TC_MAX_STAGES;      // [TC_MAX_STAGES]
+    uint64_t* bfull = bars + 2 * TC_MAX_STAGES;  // [1]
     uint64_t* tfull = bfull + 1;                 // [2]
     uint64_t* tempty = tfull + 2;                // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
@@ -84,12 +98,11 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_half = blockIdx.x % a.n_halves;
     const int cta_m = blockIdx.x / a.n_halves;
     const int m_stride = gridDim.x / a.n_halves;
-    const int tiles_x = a.W / a.bx, tiles_y = a.H / a.by;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < Cfg::STAGES; ++s) {
+        for (int s = 0; s < a.stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -110,24 +123,23 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================= TMA producer =================
         if (lane == 0) {
             mbar_arrive_expect_tx(bfull, Cfg::B_BYTES);
-            for (int kb = 0; kb < Cfg::KSTEPS; ++kb)
+            for (int kb = 0; kb < 3 * Cfg::KCHUNKS; ++kb)
                 tma_load_2d(&tmB, bfull, sB + kb * TC_B_ATOM_BYTES, kb * TC_KCH, n_half * TC_BN);
             int stage = 0;
             uint32_t phase = 0;
             for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride) {
-                const int tx = mt % tiles_x;
-                const int ty = (mt / tiles_x) % tiles_y;
-                const int n = mt / (tiles_x * tiles_y);
-                for (int t = 0; t < 3; ++t) {
-                    const int x0 = tx * a.bx + a.dx[t], y0 = ty * a.by + a.dy[t];
-                    for (int cb = 0; cb < Cfg::KCHUNKS; ++cb) {
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&full[stage], TC_A_STAGE_BYTES);
-                        tma_load_5d(&tmA, &full[stage], sA + stage * TC_A_STAGE_BYTES, 0, cb, x0, y0, n);
-                        if (++stage == Cfg::STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                const int ta = mt % a.tiles_a;
+                const int tb = (mt / a.tiles_a) % a.tiles_b;
+                const int n = mt / (a.tiles_a * a.tiles_b);
+                const int a0 = ta * a.TA - a.dil, b0 = tb * a.TB;
+                for (int cb = 0; cb < Cfg::KCHUNKS; ++cb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], a.stage_bytes);
+                    // tensor map dims: (ci, cblk, cross axis, conv axis, n)
+                    tma_load_5d(&tmA, &full[stage], sA + (size_t)stage * a.stage_bytes, 0, cb, b0, a0, n);
+                    if (++stage == a.stages) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
             }
@@ -145,16 +157,21 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&tempty[buf], use_parity ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * TC_BN;
-                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                for (int cb = 0; cb < Cfg::KCHUNKS; ++cb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * TC_A_STAGE_BYTES));
-                    const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + ks * TC_B_ATOM_BYTES));
+                    const uint32_t slab = smem_u32(sA + (size_t)stage * a.stage_bytes);
 #pragma unroll
-                    for (int k8 = 0; k8 < TC_KCH / 8; ++k8)  // 8 tf32 = 32 bytes = 2 x 16B per MMA
-                        umma_tf32(d_tmem, adesc + 2 * k8, bdesc + 2 * k8, TC_IDESC, (ks | k8) != 0 ? 1u : 0u);
-                    umma_commit(&empty[stage]);  // frees the A stage when these MMAs have read it
-                    if (++stage == Cfg::STAGES) {
+                    for (int t = 0; t < 3; ++t) {
+                        // tap t = the slab shifted by tap_row[t] rows of 128 B (a multiple of 8 rows)
+                        const uint64_t adesc = umma_desc_sw128(slab + a.tap_row[t] * 128);
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (t * Cfg::KCHUNKS + cb) * TC_B_ATOM_BYTES));
+#pragma unroll
+                        for (int k8 = 0; k8 < TC_KCH / 8; ++k8)  // 8 tf32 = 32 bytes = 2 x 16B per MMA
+                            umma_tf32(d_tmem, adesc + 2 * k8, bdesc + 2 * k8, TC_IDESC, (cb | t | k8) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);  // frees the slab when these MMAs have read it
+                    if (++stage == a.stages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -166,7 +183,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================= epilogue (warps 2..5) =================
         const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may access
         const int m = lane_base + lane;
-        const int yy = m / a.bx, xx = m - yy * a.bx;
+        const int ap = m / a.TB, bp = m - ap * a.TB;  // slab order: cross axis fastest
         float csum[TC_BN];  // running column sums of this thread's pixel row over all tiles (bias gradient)
 #pragma unroll
         for (int c = 0; c < TC_BN; ++c) csum[c] = 0.f;
@@ -174,10 +191,12 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
             const int buf = it & 1;
             const uint32_t use_parity = (it >> 1) & 1;
-            const int tx = mt % tiles_x;
-            const int ty = (mt / tiles_x) % tiles_y;
-            const int n = mt / (tiles_x * tiles_y);
-            const size_t off = ((size_t)(n * a.H + ty * a.by + yy) * a.W + tx * a.bx + xx) * a.Ctot + n_half * TC_BN;
+            const int ta = mt % a.tiles_a;
+            const int tb = (mt / a.tiles_a) % a.tiles_b;
+            const int n = mt / (a.tiles_a * a.tiles_b);
+            const int pa = ta * a.TA + ap, pb = tb * a.TB + bp;
+            const int y = a.vertical ? pa : pb, x = a.vertical ? pb : pa;
+            const size_t off = ((size_t)(n * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN;
             mbar_wait(&tfull[buf], use_parity);
             tc_fence_after();
 #pragma unroll
@@ -243,65 +262,104 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static bool pick_patch(int H, int W, int* bx, int* by) {
-    // bx * by = 128 pixels, bx | W, by | H; prefer wide patches (longer contiguous runs)
-    for (int x = 128; x >= 1; x >>= 1) {
-        const int y = 128 / x;
-        if (W % x == 0 && H % y == 0) {
-            *bx = x;
-            *by = y;
-            return true;
-        }
+struct TcPlan {
+    int vertical, dil, fwd_order;  // fwd_order: weight slot t reads offset (t-1)*d (1) or -(t-1)*d (0)
+    int TA, TB, tiles_a, tiles_b, stages, stage_bytes, smem_bytes, m_ctas;
+};
+
+// Derive the plan from the public arguments; false = shape / tap pattern not served by this kernel.
+static bool tc_make_plan(int N, int H, int W, int C, const int* dy, const int* dx, TcPlan* p) {
+    if (!(C == 64 || C == 128) || N <= 0) return false;
+    const bool vert = dy[0] != 0 || dy[2] != 0;
+    const int* o = vert ? dy : dx;
+    const int* z = vert ? dx : dy;
+    if (z[0] || z[1] || z[2] || o[1] != 0 || o[0] != -o[2] || o[0] == 0) return false;
+    p->vertical = vert ? 1 : 0;
+    p->dil = o[0] < 0 ? -o[0] : o[0];
+    p->fwd_order = o[0] < 0 ? 1 : 0;
+    const int ext_a = vert ? H : W, ext_b = vert ? W : H;
+    if (ext_a % 16 == 0 && ext_b % 8 == 0) {
+        p->TA = 16;
+        p->TB = 8;
+    } else if (ext_a % 8 == 0 && ext_b % 16 == 0) {
+        p->TA = 8;
+        p->TB = 16;
+    } else {
+        return false;
     }
-    return false;
+    if (p->TA + 2 * p->dil > 256) return false;  // TMA box limit
+    p->tiles_a = ext_a / p->TA;
+    p->tiles_b = ext_b / p->TB;
+    p->stage_bytes = (p->TA + 2 * p->dil) * p->TB * 128;
+    const int b_bytes = 3 * (C / 32) * TC_B_ATOM_BYTES;
+    const int fixed = 1024 + b_bytes + 512;  // alignment slack + B + barriers
+    int stages = (TC_SMEM_LIMIT - fixed) / p->stage_bytes;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) return false;
+    p->stages = stages;
+    p->smem_bytes = fixed + stages * p->stage_bytes;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_halves = C / TC_BN;
+    const long long tiles = (long long)N * p->tiles_a * p->tiles_b;
+    long long m_ctas = sms / n_halves;
+    if (m_ctas > tiles) m_ctas = tiles;
+    p->m_ctas = (int)(m_ctas < 1 ? 1 : m_ctas);
+    return tc_get_encode_fn() != nullptr;
 }
 
 }  // namespace lf
 
 using namespace lf;
 
-static int tc_m_ctas(int N, int H, int W, int C, int bx, int by) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int n_halves = C / TC_BN;
-    const long long tiles = (long long)N * (H / by) * (W / bx);
-    long long m_ctas = sms / n_halves;
-    if (m_ctas > tiles) m_ctas = tiles;
-    return (int)(m_ctas < 1 ? 1 : m_ctas);
-}
+extern "C" void lf_conv1d_tc_set_variant(int v) { g_tc_variant = (v == 1) ? 1 : 2; }
 
 // returns 0 if the shape is unsupported, else the number of rows of the optional colsum_partial output
+// (an upper bound over the dilations 1..16 and both conv axes)
 extern "C" int lf_conv1d_tc_supported(int N, int H, int W, int C) {
-    int bx, by;
-    if (!(C == 64 || C == 128) || N <= 0) return 0;
-    if (!pick_patch(H, W, &bx, &by)) return 0;
-    if (tc_get_encode_fn() == nullptr) return 0;
-    return tc_m_ctas(N, H, W, C, bx, by);
+    if (g_tc_variant == 1) return lf_conv1d_tc_supported_v1(N, H, W, C);
+    TcPlan ph, pv;
+    const int zero[3] = {0, 0, 0}, far[3] = {-16, 0, 16};
+    if (!tc_make_plan(N, H, W, C, zero, far, &ph)) return 0;
+    if (!tc_make_plan(N, H, W, C, far, zero, &pv)) return 0;
+    return ph.m_ctas > pv.m_ctas ? ph.m_ctas : pv.m_ctas;
 }
 
 extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
+    if (g_tc_variant == 1) return lf_conv1d_tc_v1(args, stream_);
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!args) return LF_ERR_INVALID_ARGUMENT;
     const LfConvTcArgs& p = *args;
     LF_REQUIRE(p.in && p.wpack && p.out);
-    if (!(p.C == 64 || p.C == 128)) return LF_ERR_UNSUPPORTED;
-    TcArgs a{};
-    if (!pick_patch(p.H, p.W, &a.bx, &a.by)) return LF_ERR_UNSUPPORTED;
+    TcPlan pl;
+    if (!tc_make_plan(p.N, p.H, p.W, p.C, p.dy, p.dx, &pl)) return LF_ERR_UNSUPPORTED;
     TcEncodeTiledFn enc = tc_get_encode_fn();
-    if (!enc) return LF_ERR_UNSUPPORTED;
+    TcArgs a{};
     a.out = p.out; a.bias = p.bias; a.mask_src = p.mask_src; a.add_src = p.add_src; a.add_mask = p.add_mask;
     a.colsum_partial = p.colsum_partial;
     a.N = p.N; a.H = p.H; a.W = p.W; a.Ctot = p.C; a.relu = p.relu;
-    for (int t = 0; t < 3; ++t) {
-        a.dy[t] = p.dy[t];
-        a.dx[t] = p.dx[t];
-    }
+    a.vertical = pl.vertical; a.TA = pl.TA; a.TB = pl.TB; a.dil = pl.dil;
+    a.tiles_a = pl.tiles_a; a.tiles_b = pl.tiles_b;
+    a.stages = pl.stages; a.stage_bytes = pl.stage_bytes;
+    for (int t = 0; t < 3; ++t) a.tap_row[t] = (pl.fwd_order ? t : 2 - t) * pl.dil * pl.TB;
     a.n_halves = p.C / TC_BN;
-    a.total_m_tiles = p.N * (p.H / a.by) * (p.W / a.bx);
+    a.total_m_tiles = p.N * pl.tiles_a * pl.tiles_b;
 
     CUtensorMap tmA, tmB;
-    if (!tc_encode_nhwc_map(enc, &tmA, p.in, p.N, p.H, p.W, p.C, a.bx, a.by)) return LF_ERR_CUDA;
+    {
+        // activations [N,H,W,C] viewed as (ci:32, cblk:C/32, cross axis, conv axis, n); one box = the slab
+        const cuuint64_t sx = (cuuint64_t)p.C * 4, sy = (cuuint64_t)p.W * p.C * 4;
+        cuuint64_t dims[5] = {32, (cuuint64_t)(p.C / 32), (cuuint64_t)(pl.vertical ? p.W : p.H),
+                              (cuuint64_t)(pl.vertical ? p.H : p.W), (cuuint64_t)p.N};
+        cuuint64_t strides[4] = {128, pl.vertical ? sx : sy, pl.vertical ? sy : sx, (cuuint64_t)p.H * p.W * p.C * 4};
+        cuuint32_t box[5] = {32, 1, (cuuint32_t)pl.TB, (cuuint32_t)(pl.TA + 2 * pl.dil), 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(p.in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return LF_ERR_CUDA;
+    }
     {
         // packed weights [Cout][3*C] (K contiguous)
         cuuint64_t dims[2] = {(cuuint64_t)(3 * p.C), (cuuint64_t)p.C};
@@ -313,17 +371,16 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return LF_ERR_CUDA;
     }
-    const int m_ctas = tc_m_ctas(p.N, p.H, p.W, p.C, a.bx, a.by);
-    const int grid = m_ctas * a.n_halves;
+    const int grid = pl.m_ctas * a.n_halves;
     cudaError_t e;
     if (p.C == 128) {
-        e = cudaFuncSetAttribute(conv1d_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
+        e = cudaFuncSetAttribute(conv1d_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+        conv1d_tc_kernel<128><<<grid, TC_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
     } else {
-        e = cudaFuncSetAttribute(conv1d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES);
+        e = cudaFuncSetAttribute(conv1d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+        conv1d_tc_kernel<64><<<grid, TC_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
     }
     return check_launch();
 }

@@ -38,9 +38,18 @@ CASES = [
 ]
 
 
+@pytest.fixture(params=[2, 1], ids=["slab", "per_tap"])
+def variant(request):
+    """Both implementations of lf_conv1d_tc: 2 = halo slab (default), 1 = one TMA box per tap."""
+    from lanedetection_end2end_b200 import _capi
+    _capi.lib().lf_conv1d_tc_set_variant(request.param)
+    yield request.param
+    _capi.lib().lf_conv1d_tc_set_variant(2)
+
+
 @pytest.mark.parametrize("N,C,H,W,vertical,dil", CASES)
 @pytest.mark.parametrize("exact", [True, False])
-def test_tc_forward_matches_fp32_kernel(N, C, H, W, vertical, dil, exact):
+def test_tc_forward_matches_fp32_kernel(N, C, H, W, vertical, dil, exact, variant):
     o = ops()
     g = torch.Generator().manual_seed(N * 1000 + C + dil)
     x = torch.randn(N, H, W, C, generator=g).cuda()
@@ -70,7 +79,7 @@ def test_tc_forward_matches_fp32_kernel(N, C, H, W, vertical, dil, exact):
 
 
 @pytest.mark.parametrize("C,H,W,dil", [(64, 16, 128, 1), (128, 32, 64, 8)])
-def test_tc_epilogues_and_dgrad(C, H, W, dil):
+def test_tc_epilogues_and_dgrad(C, H, W, dil, variant):
     o = ops()
     g = torch.Generator().manual_seed(7)
     N = 2
@@ -92,6 +101,16 @@ def test_tc_epilogues_and_dgrad(C, H, W, dil):
             o.set_conv_mode("fp32")
     for a, r in zip(outs["tf32"], outs["fp32"]):
         assert float((a - r).abs().max()) <= 2e-6 * float(r.abs().max())
+    # fused column sums (bias gradient) of the masked input gradient
+    o.set_conv_mode("tf32")
+    try:
+        cs = torch.empty(C, device="cuda")
+        d = o.conv3(x, w, False, dil, True, colsum=cs, mask_src=mask)
+        torch.cuda.synchronize()
+    finally:
+        o.set_conv_mode("fp32")
+    want = d.double().sum(dim=(0, 1, 2))
+    assert float((cs.double() - want).abs().max()) <= 1e-4 * float(want.abs().max())
 
 
 def test_tc_block_level_tf32_tolerance():

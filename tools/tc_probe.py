@@ -19,6 +19,9 @@ CASES = {
     "fwd128_identity": ("fwd", 1, 128, 4, 64, False, 1, "identity"),
     "fwd128_full": ("fwd", 2, 128, 32, 64, True, 4, "full"),
     "fwd128_many": ("fwd", 32, 128, 32, 64, False, 2, "full"),
+    "fwd128_d16": ("fwd", 2, 128, 32, 64, False, 16, "full"),
+    "fwd128_v8": ("fwd", 2, 128, 32, 64, True, 8, "full"),
+    "fwd128_320": ("fwd", 1, 128, 40, 80, True, 4, "full"),
     "wgrad128": ("wgrad", 2, 128, 32, 64, False, 1, None),
     "wgrad128_vert": ("wgrad", 4, 128, 32, 64, True, 8, None),
     "wgrad64": ("wgrad", 2, 64, 16, 128, False, 1, None),
@@ -31,6 +34,8 @@ def run_case(name):
     import torch
     from lanedetection_end2end_b200 import ops_net as o
     kind, N, C, H, W, vertical, dil, wk = CASES[name]
+    from lanedetection_end2end_b200 import _capi
+    _capi.lib().lf_conv1d_tc_set_variant(int(os.environ.get("TC_VARIANT", "2")))
     g = torch.Generator().manual_seed(1)
 
     def tfx(t):
