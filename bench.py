@@ -280,10 +280,16 @@ def run_ours(a, cfg):
     gstep = None
     if a.graph:
         from lanedetection_end2end_b200.engine import GraphedTrainStep
-        gstep = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, reducer)
-        for _ in range(max(a.warmup, 3)):
-            gstep()
-        barrier()
+        try:
+            gstep = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, reducer)
+            for _ in range(max(a.warmup, 3)):
+                gstep()
+            barrier()
+        except Exception as e:        # capture failed: report it and measure eagerly instead
+            sys.stderr.write("CUDA graph capture failed (%s: %s); falling back to eager launches\n" % (type(e).__name__, e))
+            gstep = None
+            a.graph = False
+            torch.cuda.synchronize()
 
     def dev_step():
         if gstep is not None:

@@ -20,7 +20,9 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--modes", nargs="+", default=["fp32", "tf32"])
     ap.add_argument("--shapes", nargs="+", default=["128,32,64,2", "64,64,128,1"])   # C,H,W,dil
+    ap.add_argument("--variant", type=int, default=2, help="tcgen05 conv variant (2 = halo slab, 1 = per-tap boxes)")
     a = ap.parse_args()
+    _capi.lib().lf_conv1d_tc_set_variant(a.variant)
     for shp in a.shapes:
         C, H, W, dil = [int(v) for v in shp.split(",")]
         torch.manual_seed(0)
@@ -49,7 +51,7 @@ def main():
                 d["ms"] += s.elapsed_time(e)
                 d["flops"] += flops
                 d["bytes"] += nbytes
-            out = {"bench": "nb1d_block", "C": C, "H": H, "W": W, "dil": dil, "batch": a.batch, "mode": mode,
+            out = {"bench": "nb1d_block", "C": C, "H": H, "W": W, "dil": dil, "batch": a.batch, "mode": mode, "tc_variant": a.variant,
                    "ms_per_iter_traced": e0.elapsed_time(e1) / a.iters, "kernels": {}}
             for k, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
                 ms = d["ms"] / a.iters
