@@ -323,14 +323,17 @@ __device__ void lsq_chunk_tail(const LsqArgs& a, double (*red)[LSQ_MAXL][LSQ_MAX
 // ---------------------------------------------------------------------------------
 // Forward, row-separable fast path.  grid = (nchunks, B, ceil(L/4)), 256 threads.
 // ---------------------------------------------------------------------------------
-template <int ACT_T, bool BF16>
+// NL = lanes per CTA (compile time, so the loads of all lanes and column steps of a row are in flight
+// together: the kernel is latency-bound otherwise -- ncu: long_scoreboard stalls, profiles/r01).
+template <int ACT_T, bool BF16, int NL>
 __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const LsqArgs a) {
     __shared__ double red[LSQ_WARPS][LSQ_MAXL][LSQ_MAXNM];
     __shared__ double mom[LSQ_MAXL][LSQ_MAXNM];
     const int chunk = blockIdx.x, b = blockIdx.y, lg = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int l0 = lg * LSQ_MAXL;
-    const int nl = min(LSQ_MAXL, a.L - l0);
+    const int l0 = lg * NL;
+    const int nl = min(NL, a.L - l0);
+    constexpr int UNR = (NL <= 2) ? 4 : 2;
     const int d = a.order, NM = 3 * d + 2;
     constexpr int V = MapVec<BF16>::V;
     const int WV = a.W / V;
@@ -338,9 +341,9 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const Ls
     const bool useB = lane > 2 * d;
     const int ek = useB ? lane - (2 * d + 1) : lane;
 
-    double acc[LSQ_MAXL];
+    double acc[NL];
 #pragma unroll
-    for (int l = 0; l < LSQ_MAXL; ++l) acc[l] = 0.0;
+    for (int l = 0; l < NL; ++l) acc[l] = 0.0;
 
     const int r_end = min(a.H, (chunk + 1) * a.rows_per_cta);
     for (int r = chunk * a.rows_per_cta + warp; r < r_end; r += LSQ_WARPS) {
@@ -355,15 +358,15 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const Ls
             }
             continue;
         }
-        float A[LSQ_MAXL], Bx[LSQ_MAXL];
+        float A[NL], Bx[NL];
 #pragma unroll
-        for (int l = 0; l < LSQ_MAXL; ++l) A[l] = Bx[l] = 0.f;
-#pragma unroll 2
+        for (int l = 0; l < NL; ++l) A[l] = Bx[l] = 0.f;
+#pragma unroll UNR
         for (int cv = lane; cv < WV; cv += 32) {
             float x[V];
             load_xv<V>(a.xtab + rowoff, cv, x);
 #pragma unroll
-            for (int l = 0; l < LSQ_MAXL; ++l) {
+            for (int l = 0; l < NL; ++l) {
                 if (l < nl) {
                     const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff + (size_t)V * cv;
                     float o[V];
@@ -391,7 +394,7 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const Ls
         double pw = 1.0;
         for (int i = 0; i < ek && i < 2 * LF_MAX_ORDER; ++i) pw *= y;
 #pragma unroll
-        for (int l = 0; l < LSQ_MAXL; ++l) {
+        for (int l = 0; l < NL; ++l) {
             if (l < nl) {
                 const double As = warp_sum((double)A[l]);
                 const double Bs = warp_sum((double)Bx[l]);
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const Ls
     }
     if (lane < LSQ_MAXNM) {
 #pragma unroll
-        for (int l = 0; l < LSQ_MAXL; ++l) red[warp][l][lane] = (lane < NM && l < nl) ? acc[l] : 0.0;
+        for (int l = 0; l < NL; ++l) red[warp][l][lane] = (lane < NM && l < nl) ? acc[l] : 0.0;
     }
     lsq_chunk_tail(a, red, mom, chunk, b, lg, l0, nl);
 }
@@ -477,13 +480,14 @@ __device__ __forceinline__ void lsq_bwd_load_coeffs(const LsqArgs& a, int b, int
     __syncthreads();
 }
 
-template <int ACT_T, bool BF16>
+template <int ACT_T, bool BF16, int NL>
 __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const LsqArgs a) {
     __shared__ double bs[LSQ_MAXL][LF_MAX_ORDER + 1], zs[LSQ_MAXL][LF_MAX_ORDER + 1];
     const int chunk = blockIdx.x, b = blockIdx.y, lg = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int l0 = lg * LSQ_MAXL;
-    const int nl = min(LSQ_MAXL, a.L - l0);
+    const int l0 = lg * NL;
+    const int nl = min(NL, a.L - l0);
+    constexpr int UNR = (NL <= 2) ? 4 : 2;
     const int d = a.order;
     constexpr int V = MapVec<BF16>::V;
     const int WV = a.W / V;
@@ -502,9 +506,9 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const Ls
             continue;
         }
         const double y = (double)__ldg(a.yrow + r);
-        float qh[LSQ_MAXL], ql[LSQ_MAXL], sf[LSQ_MAXL];
+        float qh[NL], ql[NL], sf[NL];
 #pragma unroll
-        for (int l = 0; l < LSQ_MAXL; ++l) {
+        for (int l = 0; l < NL; ++l) {
             if (l < nl) {
                 double q = bs[l][0], s = zs[l][0];
                 for (int i = 1; i <= d; ++i) {
@@ -516,12 +520,12 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const Ls
                 sf[l] = (float)s;
             }
         }
-#pragma unroll 2
+#pragma unroll UNR
         for (int cv = lane; cv < WV; cv += 32) {
             float x[V];
             load_xv<V>(a.xtab + rowoff, cv, x);
 #pragma unroll
-            for (int l = 0; l < LSQ_MAXL; ++l) {
+            for (int l = 0; l < NL; ++l) {
                 if (l < nl) {
                     const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff + (size_t)V * cv;
                     float o[V], g[V];
@@ -616,6 +620,37 @@ extern "C" size_t lf_lsq_workspace_bytes(int B, int L, int H, int W, int order) 
         }                                                                                  \
     } while (0)
 
+#define LSQ_DISPATCH_NL2(KERNEL, NL, grid, args)                                               \
+    do {                                                                                       \
+        if (args.act == LF_ACT_SQUARE) {                                                       \
+            if (o_dtype == LF_BF16)                                                            \
+                KERNEL<LF_ACT_SQUARE, true, NL><<<grid, LSQ_THREADS, 0, stream>>>(args);       \
+            else                                                                               \
+                KERNEL<LF_ACT_SQUARE, false, NL><<<grid, LSQ_THREADS, 0, stream>>>(args);      \
+        } else {                                                                               \
+            if (o_dtype == LF_BF16)                                                            \
+                KERNEL<LSQ_ACT_RUNTIME, true, NL><<<grid, LSQ_THREADS, 0, stream>>>(args);     \
+            else                                                                               \
+                KERNEL<LSQ_ACT_RUNTIME, false, NL><<<grid, LSQ_THREADS, 0, stream>>>(args);    \
+        }                                                                                      \
+    } while (0)
+
+#define LSQ_DISPATCH_NL(KERNEL, nlg, grid, args)                       \
+    do {                                                               \
+        switch (nlg) {                                                 \
+            case 1: LSQ_DISPATCH_NL2(KERNEL, 1, grid, args); break;    \
+            case 2: LSQ_DISPATCH_NL2(KERNEL, 2, grid, args); break;    \
+            case 3: LSQ_DISPATCH_NL2(KERNEL, 3, grid, args); break;    \
+            default: LSQ_DISPATCH_NL2(KERNEL, 4, grid, args); break;   \
+        }                                                              \
+    } while (0)
+
+// lanes per CTA: balanced groups of at most LSQ_MAXL (L=6 -> 2 groups of 3, not 4+2)
+static void lsq_lane_groups(int L, int* groups, int* nlg) {
+    *groups = (L + LSQ_MAXL - 1) / LSQ_MAXL;
+    *nlg = (L + *groups - 1) / *groups;
+}
+
 extern "C" int lf_lsq_fwd(const void* o, int o_dtype, const float* xtab, const float* ytab, const float* yrow, int B,
                           int L, int H, int W, int order, int mask_rows, int act, double reg_ls, int solver,
                           double* beta, double* zinv, float* masked, int* status, void* workspace,
@@ -634,14 +669,15 @@ extern "C" int lf_lsq_fwd(const void* o, int o_dtype, const float* xtab, const f
     if (workspace_bytes < need) return LF_ERR_WORKSPACE_TOO_SMALL;
     const bool rowsep = (yrow != nullptr) && (W % (o_dtype == LF_BF16 ? 8 : 4) == 0);
     if (!rowsep && !ytab) return LF_ERR_INVALID_ARGUMENT;
-    const int groups = rowsep ? (L + LSQ_MAXL - 1) / LSQ_MAXL : L;
+    int groups = L, nlg = 1;
+    if (rowsep) lsq_lane_groups(L, &groups, &nlg);
     a.rows_per_cta = pick_rows_per_cta(B, groups, H);
     a.nchunks = (H + a.rows_per_cta - 1) / a.rows_per_cta;
     a.tickets = reinterpret_cast<int*>(workspace);
     a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + LSQ_TICKET_BYTES);
     dim3 grid(a.nchunks, B, groups);
     if (rowsep)
-        LSQ_DISPATCH(lsq_fwd_rowsep_kernel, grid, a);
+        LSQ_DISPATCH_NL(lsq_fwd_rowsep_kernel, nlg, grid, a);
     else
         LSQ_DISPATCH(lsq_fwd_general_kernel, grid, a);
     return check_launch();
@@ -660,12 +696,13 @@ extern "C" int lf_lsq_bwd(const void* o, int o_dtype, const float* xtab, const f
     LF_REQUIRE(beta && zinv && gbeta && d_o);
     const bool rowsep = (yrow != nullptr) && (W % (o_dtype == LF_BF16 ? 8 : 4) == 0);
     if (!rowsep && !ytab) return LF_ERR_INVALID_ARGUMENT;
-    const int groups = rowsep ? (L + LSQ_MAXL - 1) / LSQ_MAXL : L;
+    int groups = L, nlg = 1;
+    if (rowsep) lsq_lane_groups(L, &groups, &nlg);
     a.rows_per_cta = pick_rows_per_cta(B, groups, H);
     a.nchunks = (H + a.rows_per_cta - 1) / a.rows_per_cta;
     dim3 grid(a.nchunks, B, groups);
     if (rowsep)
-        LSQ_DISPATCH(lsq_bwd_rowsep_kernel, grid, a);
+        LSQ_DISPATCH_NL(lsq_bwd_rowsep_kernel, nlg, grid, a);
     else
         LSQ_DISPATCH(lsq_bwd_general_kernel, grid, a);
     return check_launch();

@@ -177,19 +177,43 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const WgradArgs a
     }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int ntaps, int Cp, int Cq, int CpPad,
-                                    int CqPad, float* __restrict__ dst, int st, int sp, int sq) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = ntaps * Cp * Cq;
-    if (idx >= total) return;
-    const int cq = idx % Cq;
-    const int cp = (idx / Cq) % Cp;
-    const int t = idx / (Cq * Cp);
-    const size_t stride = (size_t)ntaps * CpPad * CqPad;
-    const float* p = partial + ((size_t)t * CpPad + cp) * CqPad + cq;
-    float s = 0.f;
-    for (int k = 0; k < nsplit; ++k) s += p[(size_t)k * stride];
-    dst[(size_t)t * st + (size_t)cp * sp + (size_t)cq * sq] = s;
+// dst[t*st + cp*sp + cq*sq] = sum_k partial[k][t][cp][cq], fixed order.  One thread = 4 consecutive cq
+// (float4 loads) x one of 8 split lanes (k = lane, lane+8, ...); the 8 lanes are combined through
+// shared memory in lane order -> deterministic, 8x shorter dependent chains than one thread per output.
+constexpr int WR_LANES = 8;
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int ntaps, int Cp,
+                                                            int Cq, int CpPad, int CqPad, float* __restrict__ dst, int st, int sp,
+                                                            int sq) {
+    __shared__ float4 red[256];
+    const int Cq4 = (Cq + 3) >> 2;
+    const int total4 = ntaps * Cp * Cq4;
+    const int o = blockIdx.x * (256 / WR_LANES) + (threadIdx.x / WR_LANES);
+    const int lane = threadIdx.x % WR_LANES;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cq = 0, cp = 0, t = 0;
+    if (o < total4) {
+        cq = (o % Cq4) * 4;
+        cp = (o / Cq4) % Cp;
+        t = o / (Cq4 * Cp);
+        const size_t stride = (size_t)ntaps * CpPad * CqPad;
+        const float* p = partial + ((size_t)t * CpPad + cp) * CqPad + cq;   // CqPad % 64 == 0 -> 16B aligned
+        for (int k = lane; k < nsplit; k += WR_LANES) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)k * stride));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (lane == 0 && o < total4) {
+        float4 s4 = red[threadIdx.x];
+#pragma unroll
+        for (int l = 1; l < WR_LANES; ++l) {
+            const float4 v = red[threadIdx.x + l];
+            s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+        }
+        const float vals[4] = {s4.x, s4.y, s4.z, s4.w};
+        for (int e = 0; e < 4 && cq + e < Cq; ++e) dst[(size_t)t * st + (size_t)cp * sp + (size_t)(cq + e) * sq] = vals[e];
+    }
 }
 
 __global__ void vec_reduce_kernel(const float* __restrict__ partial, int nsplit, int C, int Cpad, float* __restrict__ dst) {
@@ -273,9 +297,11 @@ extern "C" int lf_wgrad_reduce(const float* partial, int nsplit, int ntaps, int 
                                float* dst, int st, int sp, int sq, lf_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     LF_REQUIRE(partial && dst && nsplit >= 1 && ntaps >= 1 && Cp >= 1 && Cq >= 1);
-    const int total = ntaps * Cp * Cq;
-    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(partial, nsplit, ntaps, Cp, Cq, CpPad, CqPad, dst, st,
-                                                                 sp, sq);
+    LF_REQUIRE(CqPad % 4 == 0);
+    const int total4 = ntaps * Cp * ((Cq + 3) / 4);
+    const int per_block = 256 / WR_LANES;
+    wgrad_reduce_kernel<<<(total4 + per_block - 1) / per_block, 256, 0, stream>>>(partial, nsplit, ntaps, Cp, Cq, CpPad, CqPad,
+                                                                                   dst, st, sp, sq);
     return check_launch();
 }
 
