@@ -150,6 +150,9 @@ typedef struct LfConvTcArgs {
     const float* add_mask;
     float* colsum_partial; /* NULL, or [lf_conv1d_tc_supported(...)][C]: per-CTA column sums of `out`
                               (the bias gradient when `out` is an output gradient); reduce with lf_vec_reduce */
+    double* stats_partial; /* NULL, or [lf_conv1d_tc_supported(...)][2][C]: per-CTA sum and sum of squares of `out`
+                              = the `partial` input of lf_bn_finalize (replaces an lf_bn_stats pass over `out`);
+                              LF_ERR_UNSUPPORTED when the launch has to use the per-tap variant */
     int N, H, W, C;
     int dy[3], dx[3];
     int relu;

@@ -55,7 +55,7 @@ class LfConvArgs(ctypes.Structure):
 
 class LfConvTcArgs(ctypes.Structure):
     _fields_ = [("inp", _p), ("wpack", _p), ("bias", _p), ("out", _p), ("mask_src", _p), ("add_src", _p),
-                ("add_mask", _p), ("colsum_partial", _p), ("N", _i), ("H", _i), ("W", _i), ("C", _i), ("dy", _i * 3),
+                ("add_mask", _p), ("colsum_partial", _p), ("stats_partial", _p), ("N", _i), ("H", _i), ("W", _i), ("C", _i), ("dy", _i * 3),
                 ("dx", _i * 3), ("relu", _i)]
 
 

@@ -25,11 +25,14 @@ constexpr int CONV_APAD = 4;
 
 template <int BN>
 struct ConvTile {
+    // 16-channel layers are bandwidth-bound: a 256-pixel tile doubles the FMAs per shared-memory load
+    static constexpr int BM = (BN == 16) ? 256 : CONV_BM;
+    static constexpr int AH = BM / 64;            // float4 A loads per thread and K step
     static constexpr int TN = (BN >= 128) ? 8 : 4;
     static constexpr int TX = BN / TN;            // threads along N
     static constexpr int TY = CONV_THREADS / TX;  // threads along M
-    static constexpr int TM = CONV_BM / TY;
-    static_assert(TM * TY == CONV_BM, "tile");
+    static constexpr int TM = BM / TY;
+    static_assert(TM * TY == BM, "tile");
     static constexpr int B_F4 = CONV_BK * BN / 4;  // float4 per B tile
     static constexpr int B_PER_THREAD = (B_F4 + CONV_THREADS - 1) / CONV_THREADS;
 };
@@ -38,12 +41,13 @@ template <int BN>
 __global__ void __launch_bounds__(CONV_THREADS) conv_igemm_f32_kernel(const ConvArgs a) {
     using T = ConvTile<BN>;
     constexpr int TM = T::TM, TN = T::TN;
-    __shared__ __align__(16) float As[2][CONV_BK][CONV_BM + CONV_APAD];
+    constexpr int BM = T::BM, AH = T::AH;
+    __shared__ __align__(16) float As[2][CONV_BK][BM + CONV_APAD];
     __shared__ __align__(16) float Bs[2][CONV_BK][BN];
 
     const int tid = threadIdx.x;
     const int tx = tid % T::TX, ty = tid / T::TX;
-    const int m_tile = blockIdx.x * CONV_BM;
+    const int m_tile = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int M = a.N * a.Hs * a.Ws;
     const int K = a.ntaps * a.Cin;
@@ -51,10 +55,10 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_igemm_f32_kernel(const Conv
 
     // --- A loader bookkeeping: this thread loads float4 (4 k's) for pixels m_a[0], m_a[1]
     const int kq = tid & 3;
-    int a_n[2], a_iy0[2], a_ix0[2];
-    bool a_valid[2];
+    int a_n[AH], a_iy0[AH], a_ix0[AH];
+    bool a_valid[AH];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < AH; ++h) {
         const int m = m_tile + (tid >> 2) + 64 * h;
         a_valid[h] = m < M;
         const int mm = a_valid[h] ? m : 0;
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_igemm_f32_kernel(const Conv
         a_iy0[h] = j * a.isy;
         a_ix0[h] = i * a.isx;
     }
-    float4 ra[2];
+    float4 ra[AH];
     float4 rb[T::B_PER_THREAD];
 
     auto load_tiles = [&](int kt) {
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_igemm_f32_kernel(const Conv
         const bool kok = kg < K;
         const int dy = kok ? a.dy[t] : 0, dx = kok ? a.dx[t] : 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < AH; ++h) {
             const int iy = a_iy0[h] + dy, ix = a_ix0[h] + dx;
             const bool ok = kok && a_valid[h] && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
             if (ok) {
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_igemm_f32_kernel(const Conv
     };
     auto store_tiles = [&](int buf) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < AH; ++h) {
             const int m = (tid >> 2) + 64 * h;
             As[buf][4 * kq + 0][m] = ra[h].x;
             As[buf][4 * kq + 1][m] = ra[h].y;
@@ -238,7 +242,8 @@ extern "C" int lf_conv_f32(const LfConvArgs* args, lf_stream_t stream_) {
     if (a.CoutPad % 128 == 0) BN = 128;
     else if (a.CoutPad % 64 == 0) BN = 64;
     else if (a.CoutPad % 32 == 0) BN = 32;
-    dim3 grid((unsigned)((M + CONV_BM - 1) / CONV_BM), a.CoutPad / BN);
+    const int BMsel = (BN == 16) ? 256 : CONV_BM;
+    dim3 grid((unsigned)((M + BMsel - 1) / BMsel), a.CoutPad / BN);
     switch (BN) {
         case 128: conv_igemm_f32_kernel<128><<<grid, CONV_THREADS, 0, stream>>>(a); break;
         case 64: conv_igemm_f32_kernel<64><<<grid, CONV_THREADS, 0, stream>>>(a); break;

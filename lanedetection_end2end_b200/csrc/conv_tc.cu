@@ -20,8 +20,12 @@
 //  * MMA: tcgen05.mma.cta_group::1.kind::tf32, M=128 N=64 K=8, issued by one elected thread;
 //    accumulators in TMEM, double-buffered (2 x 64 columns) so the epilogue of tile i overlaps
 //    the MMAs of tile i+1.
-//  * Epilogue: 4 warps, tcgen05.ld 32x32b (thread = pixel row), + bias, ReLU, ReLU-backward mask,
-//    residual-gradient add, running column sums (bias gradient), 128-bit stores.
+//  * Epilogue: 4 warps, two phases per tile.  (1) tcgen05.ld 32x32b (thread = pixel row) + bias + ReLU,
+//    staged into a padded shared-memory tile, TMEM buffer released.  (2) the tile is walked row-major so
+//    that 16 consecutive threads cover one pixel's 64 channels: ReLU-backward mask, residual-gradient add,
+//    column sums (bias gradient) and the output stores are fully coalesced 128-bit accesses.  (Writing
+//    straight from the pixel-row registers made every store instruction touch 32 different 512-byte-strided
+//    rows: ~8K L1 wavefronts per tile, 5x the MMA time -- measured in profiles/r01.)
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
 #include <cuda.h>
 
@@ -43,6 +47,8 @@ constexpr int TC_BN = 64;
 constexpr int TC_KCH = 32;                    // fp32 elements per 128-byte swizzle row
 constexpr int TC_B_ATOM_BYTES = TC_BN * 128;  // 8 KB
 constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_STG_LD = TC_BN + 4;                      // staging row stride in floats (bank spread)
+constexpr int TC_STG_BYTES = TC_BM * TC_STG_LD * 4;       // 34 KB
 constexpr int TC_SMEM_LIMIT = 226 * 1024;  // 227 KB opt-in maximum minus the 1 KB static epilogue scratch
 
 struct TcArgs {
@@ -52,6 +58,7 @@ struct TcArgs {
     const float* add_src;
     const float* add_mask;
     float* colsum_partial;  // [gridDim.x / n_halves][Ctot] per-CTA column sums of the output, or NULL
+    double* stats_partial;  // [gridDim.x / n_halves][2][Ctot] per-CTA sum and sum of squares (BatchNorm), or NULL
     int N, H, W, Ctot;
     int vertical;           // conv axis: 1 = y (3x1), 0 = x (1x3)
     int TA, TB;             // tile extent along / across the conv axis (TA*TB = 128)
@@ -86,7 +93,8 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sB = smem;
     uint8_t* sA = smem + Cfg::B_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)a.stages * a.stage_bytes);
+    float* stg = reinterpret_cast<float*>(sA + (size_t)a.stages * a.stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg) + TC_STG_BYTES);
     uint64_t* full = bars;                       // [TC_MAX_STAGES]
     uint64_t* empty = bars + TC_MAX_STAGES;      // [TC_MAX_STAGES]
     uint64_t* bfull = bars + 2 * TC_MAX_STAGES;  // [1]
@@ -182,11 +190,11 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else {
         // ================= epilogue (warps 2..5) =================
         const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may access
-        const int m = lane_base + lane;
-        const int ap = m / a.TB, bp = m - ap * a.TB;  // slab order: cross axis fastest
-        float csum[TC_BN];  // running column sums of this thread's pixel row over all tiles (bias gradient)
-#pragma unroll
-        for (int c = 0; c < TC_BN; ++c) csum[c] = 0.f;
+        const int m = lane_base + lane;         // phase 1: this thread's pixel row of the tile
+        const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
+        const int c4 = et & 15;                 // phase 2: this thread's float4 column (fixed for all tiles)
+        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // running column sums (bias gradient / BN mean)
+        float4 csq = make_float4(0.f, 0.f, 0.f, 0.f);   // running column sums of squares (BN variance)
         int it = 0;
         for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
             const int buf = it & 1;
@@ -194,11 +202,9 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int ta = mt % a.tiles_a;
             const int tb = (mt / a.tiles_a) % a.tiles_b;
             const int n = mt / (a.tiles_a * a.tiles_b);
-            const int pa = ta * a.TA + ap, pb = tb * a.TB + bp;
-            const int y = a.vertical ? pa : pb, x = a.vertical ? pb : pa;
-            const size_t off = ((size_t)(n * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN;
             mbar_wait(&tfull[buf], use_parity);
             tc_fence_after();
+            // ---- phase 1: TMEM -> registers -> (+bias, ReLU) -> staging tile, one pixel row per thread
 #pragma unroll
             for (int c0 = 0; c0 < TC_BN; c0 += 16) {
                 uint32_t v[16];
@@ -208,47 +214,70 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int q = 0; q < 4; ++q) {
                     float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                            __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                    const int c = c0 + 4 * q;
                     if (a.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n_half * TC_BN + c));
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n_half * TC_BN + c0 + 4 * q));
                         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                     }
                     if (a.relu) {
                         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                     }
-                    if (a.mask_src) {
-                        const float4 mk = __ldg(reinterpret_cast<const float4*>(a.mask_src + off + c));
-                        o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
-                        o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
-                    }
-                    if (a.add_src) {
-                        float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + off + c));
-                        if (a.add_mask) {
-                            const float4 mk = __ldg(reinterpret_cast<const float4*>(a.add_mask + off + c));
-                            ad.x = mk.x > 0.f ? ad.x : 0.f; ad.y = mk.y > 0.f ? ad.y : 0.f;
-                            ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
-                        }
-                        o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
-                    }
-                    *reinterpret_cast<float4*>(a.out + off + c) = o;
-                    csum[c] += o.x; csum[c + 1] += o.y; csum[c + 2] += o.z; csum[c + 3] += o.w;
+                    *reinterpret_cast<float4*>(&stg[m * TC_STG_LD + c0 + 4 * q]) = o;
                 }
             }
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);
-        }
-        if (a.colsum_partial) {
-            __shared__ float cs[4][TC_BN];
-#pragma unroll
-            for (int c = 0; c < TC_BN; ++c) {
-                const float v = warp_sum(csum[c]);
-                if (lane == 0) cs[warp & 3][c] = v;
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // staging complete (epilogue warps only)
+            if (et == 0) mbar_arrive(&tempty[buf]);          // TMEM buffer free for the MMA warp
+            if (et == 32) mbar_arrive(&tempty[buf]);
+            if (et == 64) mbar_arrive(&tempty[buf]);
+            if (et == 96) mbar_arrive(&tempty[buf]);
+            // ---- phase 2: row-major walk, 16 consecutive threads = one pixel's 64 channels (256 B)
+#pragma unroll 4
+            for (int r = et >> 4; r < TC_BM; r += 8) {
+                const int ap = r / a.TB, bp = r - ap * a.TB;  // slab order: cross axis fastest
+                const int pa = ta * a.TA + ap, pb = tb * a.TB + bp;
+                const int y = a.vertical ? pa : pb, x = a.vertical ? pb : pa;
+                const size_t off = ((size_t)(n * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN + 4 * c4;
+                float4 o = *reinterpret_cast<const float4*>(&stg[r * TC_STG_LD + 4 * c4]);
+                if (a.mask_src) {
+                    const float4 mk = __ldg(reinterpret_cast<const float4*>(a.mask_src + off));
+                    o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
+                    o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+                }
+                if (a.add_src) {
+                    float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + off));
+                    if (a.add_mask) {
+                        const float4 mk = __ldg(reinterpret_cast<const float4*>(a.add_mask + off));
+                        ad.x = mk.x > 0.f ? ad.x : 0.f; ad.y = mk.y > 0.f ? ad.y : 0.f;
+                        ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
+                    }
+                    o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+                }
+                *reinterpret_cast<float4*>(a.out + off) = o;
+                csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w;
+                csq.x = fmaf(o.x, o.x, csq.x); csq.y = fmaf(o.y, o.y, csq.y);
+                csq.z = fmaf(o.z, o.z, csq.z); csq.w = fmaf(o.w, o.w, csq.w);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
-            const int t = threadIdx.x - 64;
-            if (t < TC_BN)
-                a.colsum_partial[(size_t)cta_m * a.Ctot + n_half * TC_BN + t] = (cs[0][t] + cs[1][t]) + (cs[2][t] + cs[3][t]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile may be overwritten
+        }
+        if (a.colsum_partial || a.stats_partial) {
+            // 8 threads share each float4 column: combine them through the (now free) staging tile
+            *reinterpret_cast<float4*>(&stg[(et >> 4) * TC_STG_LD + 4 * c4]) = csum;
+            *reinterpret_cast<float4*>(&stg[(8 + (et >> 4)) * TC_STG_LD + 4 * c4]) = csq;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et < TC_BN) {
+                double tot = 0.0, tsq = 0.0;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    tot += (double)stg[g * TC_STG_LD + et];
+                    tsq += (double)stg[(8 + g) * TC_STG_LD + et];
+                }
+                if (a.colsum_partial) a.colsum_partial[(size_t)cta_m * a.Ctot + n_half * TC_BN + et] = (float)tot;
+                if (a.stats_partial) {
+                    double* sp = a.stats_partial + (size_t)cta_m * 2 * a.Ctot + n_half * TC_BN + et;
+                    sp[0] = tot;
+                    sp[a.Ctot] = tsq;
+                }
+            }
         }
     }
     tc_fence_before();
@@ -292,7 +321,7 @@ static bool tc_make_plan(int N, int H, int W, int C, const int* dy, const int* d
     p->tiles_b = ext_b / p->TB;
     p->stage_bytes = (p->TA + 2 * p->dil) * p->TB * 128;
     const int b_bytes = 3 * (C / 32) * TC_B_ATOM_BYTES;
-    const int fixed = 1024 + b_bytes + 512;  // alignment slack + B + barriers
+    const int fixed = 1024 + b_bytes + TC_STG_BYTES + 512;  // alignment slack + B + epilogue staging + barriers
     int stages = (TC_SMEM_LIMIT - fixed) / p->stage_bytes;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return false;
@@ -315,16 +344,10 @@ using namespace lf;
 
 extern "C" void lf_conv1d_tc_set_variant(int v) { g_tc_variant = (v == 1) ? 1 : 2; }
 
-// returns 0 if the shape is unsupported, else the number of rows of the optional colsum_partial output
-// (an upper bound over the dilations 1..16 and both conv axes)
-extern "C" int lf_conv1d_tc_supported(int N, int H, int W, int C) {
-    if (g_tc_variant == 1) return lf_conv1d_tc_supported_v1(N, H, W, C);
-    TcPlan ph, pv;
-    const int zero[3] = {0, 0, 0}, far[3] = {-16, 0, 16};
-    if (!tc_make_plan(N, H, W, C, zero, far, &ph)) return 0;
-    if (!tc_make_plan(N, H, W, C, far, zero, &pv)) return 0;
-    return ph.m_ctas > pv.m_ctas ? ph.m_ctas : pv.m_ctas;
-}
+// returns 0 if the shape is unsupported, else the number of rows of the optional colsum_partial output.
+// Every shape the slab kernel takes is also taken by the per-tap kernel (and both use the same number of
+// CTAs), which serves as the per-call fallback when a slab does not fit (large dilation on small maps).
+extern "C" int lf_conv1d_tc_supported(int N, int H, int W, int C) { return lf_conv1d_tc_supported_v1(N, H, W, C); }
 
 extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     if (g_tc_variant == 1) return lf_conv1d_tc_v1(args, stream_);
@@ -333,11 +356,12 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     const LfConvTcArgs& p = *args;
     LF_REQUIRE(p.in && p.wpack && p.out);
     TcPlan pl;
-    if (!tc_make_plan(p.N, p.H, p.W, p.C, p.dy, p.dx, &pl)) return LF_ERR_UNSUPPORTED;
+    if (!tc_make_plan(p.N, p.H, p.W, p.C, p.dy, p.dx, &pl)) return lf_conv1d_tc_v1(args, stream_);
     TcEncodeTiledFn enc = tc_get_encode_fn();
     TcArgs a{};
     a.out = p.out; a.bias = p.bias; a.mask_src = p.mask_src; a.add_src = p.add_src; a.add_mask = p.add_mask;
     a.colsum_partial = p.colsum_partial;
+    a.stats_partial = p.stats_partial;
     a.N = p.N; a.H = p.H; a.W = p.W; a.Ctot = p.C; a.relu = p.relu;
     a.vertical = pl.vertical; a.TA = pl.TA; a.TB = pl.TB; a.dil = pl.dil;
     a.tiles_a = pl.tiles_a; a.tiles_b = pl.tiles_b;

@@ -41,11 +41,13 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const WgradArgs a
     const int tp = (blockIdx.x / tilesQ) % tilesP;
     const int t = blockIdx.x / (tilesQ * tilesP);
     const int split = blockIdx.y;
-    const long long M = (long long)a.N * a.Hs * a.Ws;
-    long long per = (M + a.nsplit - 1) / a.nsplit;
+    // 32-bit pixel arithmetic (the host guarantees N*Hs*Ws < 2^31): the index math is on the critical path
+    const int M = a.N * a.Hs * a.Ws;
+    int per = (M + a.nsplit - 1) / a.nsplit;
     per = ((per + Cfg::PXS - 1) / Cfg::PXS) * Cfg::PXS;
-    const long long m_begin = (long long)split * per;
-    const long long m_end = min(M, m_begin + per);
+    const int m_begin = min(M, split * per);
+    const int m_end = min(M, m_begin + per);
+    const int HW = a.Hs * a.Ws;
 
     const int g = tid / Cfg::TPG, r = tid % Cfg::TPG;
     const int tx = r % (TQ / 4), ty = r / (TQ / 4);
@@ -60,18 +62,18 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const WgradArgs a
     float qs[4] = {0.f, 0.f, 0.f, 0.f};
 
     float4 rp[Cfg::PL], rq[Cfg::QL];
-    auto load = [&](long long m0) {
+    auto load = [&](int m0) {
 #pragma unroll
         for (int q = 0; q < Cfg::PL; ++q) {
             rp[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             const int f = tid + q * WG_THREADS;
             if (f < Cfg::PF4) {
                 const int lp = f / (TP / 4), c4 = f % (TP / 4);
-                const long long m = m0 + lp;
+                const int m = m0 + lp;
                 const int cp0 = tp * TP + 4 * c4;
                 if (m < m_end && cp0 < a.Cp) {
-                    const int n = (int)(m / (a.Hs * a.Ws));
-                    const int rem = (int)(m - (long long)n * (a.Hs * a.Ws));
+                    const int n = m / HW;
+                    const int rem = m - n * HW;
                     const int j = rem / a.Ws, i = rem - j * a.Ws;
                     const int py = j * a.psy + pdy, px = i * a.psx + pdx;
                     if (py >= 0 && py < a.Hp && px >= 0 && px < a.Wp)
@@ -86,11 +88,11 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const WgradArgs a
             const int f = tid + q * WG_THREADS;
             if (f < Cfg::QF4) {
                 const int lp = f / (TQ / 4), c4 = f % (TQ / 4);
-                const long long m = m0 + lp;
+                const int m = m0 + lp;
                 const int cq0 = tq * TQ + 4 * c4;
                 if (m < m_end && cq0 < a.Cq) {
-                    const int n = (int)(m / (a.Hs * a.Ws));
-                    const int rem = (int)(m - (long long)n * (a.Hs * a.Ws));
+                    const int n = m / HW;
+                    const int rem = m - n * HW;
                     const int j = rem / a.Ws, i = rem - j * a.Ws;
                     const int qy = j * a.qsy + qdy, qx = i * a.qsx + qdx;
                     if (qy >= 0 && qy < a.Hq && qx >= 0 && qx < a.Wq)
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const WgradArgs a
     }
     __syncthreads();
     int it = 0;
-    for (long long m0 = m_begin; m0 < m_end; m0 += Cfg::PXS, ++it) {
+    for (int m0 = m_begin; m0 < m_end; m0 += Cfg::PXS, ++it) {
         const int buf = it & 1;
         const bool more = (m0 + Cfg::PXS) < m_end;
         if (more) load(m0 + Cfg::PXS);
@@ -276,6 +278,7 @@ extern "C" int lf_wgrad_f32(const LfWgradArgs* args, lf_stream_t stream_) {
     LF_REQUIRE(a.Cp % 4 == 0 && a.Cq % 4 == 0 && a.p_cstride % 4 == 0 && a.q_cstride % 4 == 0);
     LF_REQUIRE(a.p_coff % 4 == 0 && a.q_coff % 4 == 0);
     LF_REQUIRE(a.CpPad % WG_TILE == 0 && a.CqPad % WG_TILE == 0 && a.CpPad >= a.Cp && a.CqPad >= a.Cq);
+    LF_REQUIRE((long long)a.N * a.Hs * a.Ws + 4096 < (1ll << 31));
     const bool smallP = a.Cp <= 16, smallQ = a.Cq <= 16;
     const int TP = smallP ? 16 : 64, TQ = smallQ ? 16 : 64;
     // small tiles only cover the first 16 channels of the 64-padded buffers: one tile in that dimension
