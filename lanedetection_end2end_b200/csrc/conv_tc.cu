@@ -349,6 +349,14 @@ extern "C" void lf_conv1d_tc_set_variant(int v) { g_tc_variant = (v == 1) ? 1 : 
 // CTAs), which serves as the per-call fallback when a slab does not fit (large dilation on small maps).
 extern "C" int lf_conv1d_tc_supported(int N, int H, int W, int C) { return lf_conv1d_tc_supported_v1(N, H, W, C); }
 
+// 1 if a call with these taps runs on the slab kernel (and may therefore request stats_partial)
+extern "C" int lf_conv1d_tc_slab_ok(int N, int H, int W, int C, int vertical, int dil) {
+    if (g_tc_variant == 1 || dil < 1) return 0;
+    TcPlan pl;
+    const int zero[3] = {0, 0, 0}, off[3] = {-dil, 0, dil};
+    return tc_make_plan(N, H, W, C, vertical ? off : zero, vertical ? zero : off, &pl) ? 1 : 0;
+}
+
 extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     if (g_tc_variant == 1) return lf_conv1d_tc_v1(args, stream_);
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -142,7 +142,8 @@ def tc_supported(x):
     return tc_rows(x) > 0
 
 
-def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_src=None, add_mask=None, colsum=None):
+def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_src=None, add_mask=None, colsum=None,
+                stats_partial=None):
     """3-tap convolution on tcgen05.  taps: [(dy, dx)] * 3 in weight-slot order.  colsum: optional [C]
     tensor receiving the column sums of `out` (bias gradient), accumulated in the kernel's epilogue."""
     N, H, W, C = x.shape
@@ -157,6 +158,8 @@ def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_s
         rows = tc_rows(x)
         part = torch.empty(rows * C, dtype=torch.float32, device=x.device)
         a.colsum_partial = part.data_ptr()
+    if stats_partial is not None:
+        a.stats_partial = stats_partial.data_ptr()
     a.N, a.H, a.W, a.C = N, H, W, C
     for t, (dy, dx) in enumerate(taps):
         a.dy[t], a.dx[t] = dy, dx
@@ -277,27 +280,51 @@ class BNState:
     __slots__ = ("mean", "invstd", "scale", "shift")
 
 
+def _bn_state(C, device):
+    s = BNState()
+    buf = torch.empty(4, C, dtype=torch.float32, device=device)
+    s.mean, s.invstd, s.scale, s.shift = buf[0], buf[1], buf[2], buf[3]
+    return s
+
+
+def bn_finalize(part, nblk, npix, C, gamma, beta, running_mean, running_var):
+    """part: float64 [nblk][2][C] partial sums / sums of squares -> BNState (+ running-stat update)."""
+    s = _bn_state(C, part.device)
+    _capi.call("lf_bn_finalize", ptr(part), nblk, npix, C, ptr(gamma), ptr(beta), BN_EPS, BN_MOMENTUM,
+               ptr(running_mean), ptr(running_var), ptr(s.mean), ptr(s.invstd), ptr(s.scale), ptr(s.shift), _stream())
+    return s
+
+
 def bn_forward_stats(x, gamma, beta, running_mean, running_var, training):
     """x: dense NHWC.  Returns BNState; updates running stats in training mode
     (nn.BatchNorm2d(eps=1e-3, momentum=0.1), ERFNet.py:17,33,39,102)."""
     h = _lib()
     C = x.shape[-1]
     npix = x.numel() // C
-    s = BNState()
-    buf = torch.empty(4, C, dtype=torch.float32, device=x.device)
-    s.mean, s.invstd, s.scale, s.shift = buf[0], buf[1], buf[2], buf[3]
-    st = _stream()
     if training:
         nblk = h.lf_bn_blocks(npix, C)
         part = torch.empty(nblk * 2 * C, dtype=torch.float64, device=x.device)
-        _capi.call("lf_bn_stats", ptr(x), npix, C, ptr(part), st)
-        _capi.call("lf_bn_finalize", ptr(part), nblk, npix, C, ptr(gamma), ptr(beta), BN_EPS, BN_MOMENTUM,
-                                     ptr(running_mean), ptr(running_var), ptr(s.mean), ptr(s.invstd), ptr(s.scale),
-                                     ptr(s.shift), st)
-    else:
-        _capi.call("lf_bn_eval_prepare", C, ptr(gamma), ptr(beta), BN_EPS, ptr(running_mean), ptr(running_var),
-                                         ptr(s.scale), ptr(s.shift), st)
+        _capi.call("lf_bn_stats", ptr(x), npix, C, ptr(part), _stream())
+        return bn_finalize(part, nblk, npix, C, gamma, beta, running_mean, running_var)
+    s = _bn_state(C, x.device)
+    _capi.call("lf_bn_eval_prepare", C, ptr(gamma), ptr(beta), BN_EPS, ptr(running_mean), ptr(running_var),
+               ptr(s.scale), ptr(s.shift), _stream())
     return s
+
+
+def conv3_bn_stats(x, w, vertical, dil, bias, gamma, beta, running_mean, running_var, training):
+    """conv (forward) followed by the BatchNorm statistics of its output -> (out, BNState).  On the tcgen05 slab
+    kernel the per-channel sums are accumulated in the conv epilogue, saving a full pass over `out`."""
+    N, H, W, C = x.shape
+    if (training and CONV_MODE == "tf32" and C in (64, 128) and tc_supported(x)
+            and _lib().lf_conv1d_tc_slab_ok(N, H, W, C, int(vertical), dil)):
+        rows = tc_rows(x)
+        part = torch.empty(rows * 2 * C, dtype=torch.float64, device=x.device)
+        taps = [(((k - 1) * dil, 0) if vertical else (0, (k - 1) * dil)) for k in range(3)]
+        out = run_conv_tc(taps, x, pack_tc_fwd(w), torch.empty_like(x), bias=bias, stats_partial=part)
+        return out, bn_finalize(part, rows, N * H * W, C, gamma, beta, running_mean, running_var)
+    out = conv3(x, w, vertical, dil, False, bias=bias)
+    return out, bn_forward_stats(out, gamma, beta, running_mean, running_var, training)
 
 
 def bn_apply(x, s, relu, drop=None, res=None):
@@ -400,12 +427,10 @@ class Nb1dFunction(torch.autograd.Function):
         _capi.require_cuda(x)
         N, H, W, C = x.shape
         t1 = conv3(x, w1, True, 1, False, bias=b1, relu=True)
-        t2 = conv3(t1, w2, False, 1, False, bias=b2)
-        s1 = bn_forward_stats(t2, g1, be1, rm1, rv1, training)
+        t2, s1 = conv3_bn_stats(t1, w2, False, 1, b2, g1, be1, rm1, rv1, training)
         t3 = bn_apply(t2, s1, relu=True)
         t4 = conv3(t3, w3, True, dil, False, bias=b3, relu=True)
-        t5 = conv3(t4, w4, False, dil, False, bias=b4)
-        s2 = bn_forward_stats(t5, g2, be2, rm2, rv2, training)
+        t5, s2 = conv3_bn_stats(t4, w4, False, dil, b4, g2, be2, rm2, rv2, training)
         y = bn_apply(t5, s2, relu=True, drop=drop, res=x)
         ctx.save_for_backward(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1.mean, s1.invstd, s2.mean, s2.invstd,
                               drop if drop is not None else x.new_empty(0))

@@ -140,3 +140,28 @@ def test_tc_block_level_tf32_tolerance():
         rel_l2 = float((a - r).norm() / r.norm())
         frac_bad = float(((a - r).abs() > 1e-2 * r.abs().max()).float().mean())
         assert rel_l2 <= 2e-2 and frac_bad <= 2e-3, (rel_l2, frac_bad)
+
+
+@pytest.mark.parametrize("C,H,W,vertical,dil", [(64, 64, 128, False, 1), (128, 32, 64, False, 4), (128, 32, 64, True, 16)])
+def test_tc_fused_bn_statistics(C, H, W, vertical, dil):
+    """BatchNorm statistics accumulated in the conv epilogue == statistics of the stored output."""
+    o = ops()
+    g = torch.Generator().manual_seed(3)
+    N = 4
+    x = torch.randn(N, H, W, C, generator=g).cuda()
+    kh, kw = (3, 1) if vertical else (1, 3)
+    w = (torch.randn(C, C, kh, kw, generator=g) / (3 * C) ** 0.5).cuda()
+    b = torch.randn(C, generator=g).cuda()
+    gamma, beta = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    o.set_conv_mode("tf32")
+    try:
+        out, s = o.conv3_bn_stats(x, w, vertical, dil, b, gamma, beta, rm, rv, True)
+        torch.cuda.synchronize()
+    finally:
+        o.set_conv_mode("fp32")
+    mean = out.double().mean(dim=(0, 1, 2))
+    var = out.double().var(dim=(0, 1, 2), unbiased=False)
+    assert float((s.mean.double() - mean).abs().max()) <= 1e-5 * float(mean.abs().max() + 1)
+    assert float((s.invstd.double() - (var + 1e-3).rsqrt()).abs().max()) <= 1e-5
+    assert float((rm.double() - 0.1 * mean).abs().max()) <= 1e-5
