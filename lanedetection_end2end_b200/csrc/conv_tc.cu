@@ -20,10 +20,12 @@
 //  * MMA: tcgen05.mma.cta_group::1.kind::tf32, M=128 N=64 K=8, issued by one elected thread;
 //    accumulators in TMEM, double-buffered (2 x 64 columns) so the epilogue of tile i overlaps
 //    the MMAs of tile i+1.
-//  * Epilogue: 4 warps, two phases per tile.  (1) tcgen05.ld 32x32b (thread = pixel row) + bias + ReLU,
-//    staged into a padded shared-memory tile, TMEM buffer released.  (2) the tile is walked row-major so
-//    that 16 consecutive threads cover one pixel's 64 channels: ReLU-backward mask, residual-gradient add,
-//    column sums (bias gradient) and the output stores are fully coalesced 128-bit accesses.  (Writing
+//  * Epilogue: 4 warps, two phases per 32-channel half of the tile.  (1) tcgen05.ld 32x32b (thread = pixel
+//    row) + bias + ReLU, staged into a padded shared-memory half-tile (18 KB).  (2) the half-tile is walked
+//    row-major so that 8 consecutive threads cover one pixel's 32 channels (one 128-byte line): ReLU-backward
+//    mask, residual-gradient add, column sums / sums of squares (bias gradient, BatchNorm statistics) and the
+//    output stores are fully coalesced 128-bit accesses.  The mask / residual operands of a tile are
+//    prefetched into registers BEFORE waiting for its accumulator, so their latency hides behind the MMAs.  (Writing
 //    straight from the pixel-row registers made every store instruction touch 32 different 512-byte-strided
 //    rows: ~8K L1 wavefronts per tile, 5x the MMA time -- measured in profiles/r01.)
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
@@ -47,8 +49,8 @@ constexpr int TC_BN = 64;
 constexpr int TC_KCH = 32;                    // fp32 elements per 128-byte swizzle row
 constexpr int TC_B_ATOM_BYTES = TC_BN * 128;  // 8 KB
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_STG_LD = TC_BN + 4;                      // staging row stride in floats (bank spread)
-constexpr int TC_STG_BYTES = TC_BM * TC_STG_LD * 4;       // 34 KB
+constexpr int TC_STG_LD = 32 + 4;                         // staging row stride in floats: a 32-channel half + bank spread
+constexpr int TC_STG_BYTES = TC_BM * TC_STG_LD * 4;       // 18 KB
 constexpr int TC_SMEM_LIMIT = 226 * 1024;  // 227 KB opt-in maximum minus the 1 KB static epilogue scratch
 
 struct TcArgs {
@@ -192,9 +194,14 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may access
         const int m = lane_base + lane;         // phase 1: this thread's pixel row of the tile
         const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
-        const int c4 = et & 15;                 // phase 2: this thread's float4 column (fixed for all tiles)
-        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // running column sums (bias gradient / BN mean)
-        float4 csq = make_float4(0.f, 0.f, 0.f, 0.f);   // running column sums of squares (BN variance)
+        const int c4 = et & 7;                  // phase 2: float4 column inside a 32-channel half (fixed)
+        const int r0 = et >> 3;                 // phase 2: first of this thread's 8 rows (r0, r0+16, ...)
+        const int tb_shift = (a.TB == 8) ? 3 : 4;
+        const bool pre_mask = a.mask_src != nullptr;
+        const bool pre_add = (a.add_src != nullptr) && !pre_mask;  // both given: add_src is read in the loop
+        float4 csum[2], csq[2];                 // running column sums / sums of squares, per channel half
+#pragma unroll
+        for (int h = 0; h < 2; ++h) csum[h] = csq[h] = make_float4(0.f, 0.f, 0.f, 0.f);
         int it = 0;
         for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
             const int buf = it & 1;
@@ -202,74 +209,109 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int ta = mt % a.tiles_a;
             const int tb = (mt / a.tiles_a) % a.tiles_b;
             const int n = mt / (a.tiles_a * a.tiles_b);
-            mbar_wait(&tfull[buf], use_parity);
-            tc_fence_after();
-            // ---- phase 1: TMEM -> registers -> (+bias, ReLU) -> staging tile, one pixel row per thread
+            // global offsets of this thread's 8 phase-2 rows (channel 4*c4 of half 0)
+            size_t roff[8];
 #pragma unroll
-            for (int c0 = 0; c0 < TC_BN; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + buf * TC_BN + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                           __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                    if (a.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n_half * TC_BN + c0 + 4 * q));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
-                    if (a.relu) {
-                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                    }
-                    *reinterpret_cast<float4*>(&stg[m * TC_STG_LD + c0 + 4 * q]) = o;
-                }
-            }
-            tc_fence_before();
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // staging complete (epilogue warps only)
-            if (et == 0) mbar_arrive(&tempty[buf]);          // TMEM buffer free for the MMA warp
-            if (et == 32) mbar_arrive(&tempty[buf]);
-            if (et == 64) mbar_arrive(&tempty[buf]);
-            if (et == 96) mbar_arrive(&tempty[buf]);
-            // ---- phase 2: row-major walk, 16 consecutive threads = one pixel's 64 channels (256 B)
-#pragma unroll 4
-            for (int r = et >> 4; r < TC_BM; r += 8) {
-                const int ap = r / a.TB, bp = r - ap * a.TB;  // slab order: cross axis fastest
+            for (int j = 0; j < 8; ++j) {
+                const int r = r0 + 16 * j;
+                const int ap = r >> tb_shift, bp = r & (a.TB - 1);  // slab order: cross axis fastest
                 const int pa = ta * a.TA + ap, pb = tb * a.TB + bp;
                 const int y = a.vertical ? pa : pb, x = a.vertical ? pb : pa;
-                const size_t off = ((size_t)(n * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN + 4 * c4;
-                float4 o = *reinterpret_cast<const float4*>(&stg[r * TC_STG_LD + 4 * c4]);
-                if (a.mask_src) {
-                    const float4 mk = __ldg(reinterpret_cast<const float4*>(a.mask_src + off));
-                    o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
-                    o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
-                }
-                if (a.add_src) {
-                    float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + off));
-                    if (a.add_mask) {
-                        const float4 mk = __ldg(reinterpret_cast<const float4*>(a.add_mask + off));
-                        ad.x = mk.x > 0.f ? ad.x : 0.f; ad.y = mk.y > 0.f ? ad.y : 0.f;
-                        ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
-                    }
-                    o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
-                }
-                *reinterpret_cast<float4*>(a.out + off) = o;
-                csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w;
-                csq.x = fmaf(o.x, o.x, csq.x); csq.y = fmaf(o.y, o.y, csq.y);
-                csq.z = fmaf(o.z, o.z, csq.z); csq.w = fmaf(o.w, o.w, csq.w);
+                roff[j] = ((size_t)(n * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN + 4 * c4;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile may be overwritten
+            // Prefetch the ReLU mask (or the gated residual gradient) of this tile while the MMAs are still
+            // running: the loads' latency hides behind the wait for the accumulator.
+            float4 pre[2][8];
+            if (pre_mask || pre_add) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (pre_mask) {
+                            pre[h][j] = __ldg(reinterpret_cast<const float4*>(a.mask_src + roff[j] + 32 * h));
+                        } else {
+                            float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + roff[j] + 32 * h));
+                            if (a.add_mask) {
+                                const float4 mk = __ldg(reinterpret_cast<const float4*>(a.add_mask + roff[j] + 32 * h));
+                                ad.x = mk.x > 0.f ? ad.x : 0.f; ad.y = mk.y > 0.f ? ad.y : 0.f;
+                                ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
+                            }
+                            pre[h][j] = ad;
+                        }
+                    }
+            }
+            mbar_wait(&tfull[buf], use_parity);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                // ---- phase 1: TMEM -> registers -> (+bias, ReLU) -> staging half-tile, one pixel row per thread
+#pragma unroll
+                for (int c0 = 0; c0 < 32; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + buf * TC_BN + 32 * h + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                               __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                        if (a.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n_half * TC_BN + 32 * h + c0 + 4 * q));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        if (a.relu) {
+                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                        }
+                        *reinterpret_cast<float4*>(&stg[m * TC_STG_LD + c0 + 4 * q]) = o;
+                    }
+                }
+                if (h == 1) tc_fence_before();
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // staging complete (epilogue warps only)
+                if (h == 1 && lane == 0) mbar_arrive(&tempty[buf]);  // all TMEM reads done: buffer free for the MMA warp
+                // ---- phase 2: row-major walk, 8 consecutive threads = one pixel's 32 channels (128 B)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = r0 + 16 * j;
+                    const size_t off = roff[j] + 32 * h;
+                    float4 o = *reinterpret_cast<const float4*>(&stg[r * TC_STG_LD + 4 * c4]);
+                    if (pre_mask) {
+                        const float4 mk = pre[h][j];
+                        o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
+                        o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+                    }
+                    if (pre_add) {
+                        o.x += pre[h][j].x; o.y += pre[h][j].y; o.z += pre[h][j].z; o.w += pre[h][j].w;
+                    } else if (a.add_src) {
+                        float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + off));
+                        if (a.add_mask) {
+                            const float4 mk = __ldg(reinterpret_cast<const float4*>(a.add_mask + off));
+                            ad.x = mk.x > 0.f ? ad.x : 0.f; ad.y = mk.y > 0.f ? ad.y : 0.f;
+                            ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
+                        }
+                        o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+                    }
+                    *reinterpret_cast<float4*>(a.out + off) = o;
+                    csum[h].x += o.x; csum[h].y += o.y; csum[h].z += o.z; csum[h].w += o.w;
+                    csq[h].x = fmaf(o.x, o.x, csq[h].x); csq[h].y = fmaf(o.y, o.y, csq[h].y);
+                    csq[h].z = fmaf(o.z, o.z, csq[h].z); csq[h].w = fmaf(o.w, o.w, csq[h].w);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // staging half-tile may be overwritten
+            }
         }
         if (a.colsum_partial || a.stats_partial) {
-            // 8 threads share each float4 column: combine them through the (now free) staging tile
-            *reinterpret_cast<float4*>(&stg[(et >> 4) * TC_STG_LD + 4 * c4]) = csum;
-            *reinterpret_cast<float4*>(&stg[(8 + (et >> 4)) * TC_STG_LD + 4 * c4]) = csq;
+            // 16 threads share each (half, float4 column): combine them through the (now free) staging tile
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                *reinterpret_cast<float4*>(&stg[(h * 16 + r0) * TC_STG_LD + 4 * c4]) = csum[h];
+                *reinterpret_cast<float4*>(&stg[(32 + h * 16 + r0) * TC_STG_LD + 4 * c4]) = csq[h];
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et < TC_BN) {
+                const int h = et >> 5, c = et & 31;
                 double tot = 0.0, tsq = 0.0;
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    tot += (double)stg[g * TC_STG_LD + et];
-                    tsq += (double)stg[(8 + g) * TC_STG_LD + et];
+                for (int g = 0; g < 16; ++g) {
+                    tot += (double)stg[(h * 16 + g) * TC_STG_LD + c];
+                    tsq += (double)stg[(32 + h * 16 + g) * TC_STG_LD + c];
                 }
                 if (a.colsum_partial) a.colsum_partial[(size_t)cta_m * a.Ctot + n_half * TC_BN + et] = (float)tot;
                 if (a.stats_partial) {
