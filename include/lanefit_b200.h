@@ -163,6 +163,9 @@ int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream);
 /* 2 (default) = halo-slab kernel (one TMA slab per 32-channel chunk shared by the three taps);
  * 1 = first version (one TMA box per tap).  Same results; process-wide switch for A/B measurements. */
 void lf_conv1d_tc_set_variant(int variant);
+/* timing experiments only (tools/tc_ablate.py): bit0 skips the epilogue body, bit1 skips the TMA loads;
+ * outputs are meaningless while bits are set.  0 = normal operation. */
+void lf_conv1d_tc_set_debug(int bits);
 /* 1 if a call with taps {-dil,0,+dil} along y (vertical) or x runs on the slab kernel, i.e. may ask for stats_partial */
 int lf_conv1d_tc_slab_ok(int N, int H, int W, int C, int vertical, int dil);
 

@@ -75,6 +75,7 @@ _NET_PROTOS = {
     "lf_conv1d_tc": (_i, [ctypes.POINTER(LfConvTcArgs), _p]),
     "lf_conv1d_tc_supported": (_i, [_i, _i, _i, _i]),
     "lf_conv1d_tc_set_variant": (None, [_i]),
+    "lf_conv1d_tc_set_debug": (None, [_i]),
     "lf_conv1d_tc_slab_ok": (_i, [_i, _i, _i, _i, _i, _i]),
     "lf_wgrad3_tc_ctas": (_i, [_i, _i, _i, _i]),
     "lf_wgrad3_tc": (_i, [_p, _p, _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), _p, _i, _p]),

@@ -42,6 +42,7 @@ int lf_conv1d_tc_v1(const LfConvTcArgs* args, lf_stream_t stream_);
 namespace lf {
 
 static int g_tc_variant = 2;  // 2 = halo slab (this file), 1 = one box per tap (conv_tc_v1.cu)
+static int g_tc_debug = 0;    // timing experiments only: bit0 = skip the epilogue body, bit1 = skip the TMA loads
 
 constexpr int TC_THREADS = 192;
 constexpr int TC_BM = 128;
@@ -71,6 +72,7 @@ struct TcArgs {
     int n_halves;
     int total_m_tiles;
     int stages, stage_bytes;
+    int debug;              // timing experiments (lf_conv1d_tc_set_debug): results are garbage when != 0
 };
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
@@ -144,9 +146,13 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int a0 = ta * a.TA - a.dil, b0 = tb * a.TB;
                 for (int cb = 0; cb < Cfg::KCHUNKS; ++cb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], a.stage_bytes);
-                    // tensor map dims: (ci, cblk, cross axis, conv axis, n)
-                    tma_load_5d(&tmA, &full[stage], sA + (size_t)stage * a.stage_bytes, 0, cb, b0, a0, n);
+                    if (a.debug & 2) {
+                        mbar_arrive(&full[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&full[stage], a.stage_bytes);
+                        // tensor map dims: (ci, cblk, cross axis, conv axis, n)
+                        tma_load_5d(&tmA, &full[stage], sA + (size_t)stage * a.stage_bytes, 0, cb, b0, a0, n);
+                    }
                     if (++stage == a.stages) {
                         stage = 0;
                         phase ^= 1;
@@ -242,6 +248,12 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             mbar_wait(&tfull[buf], use_parity);
             tc_fence_after();
+            if (a.debug & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+                continue;
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 // ---- phase 1: TMEM -> registers -> (+bias, ReLU) -> staging half-tile, one pixel row per thread
@@ -385,6 +397,7 @@ static bool tc_make_plan(int N, int H, int W, int C, const int* dy, const int* d
 using namespace lf;
 
 extern "C" void lf_conv1d_tc_set_variant(int v) { g_tc_variant = (v == 1) ? 1 : 2; }
+extern "C" void lf_conv1d_tc_set_debug(int bits) { g_tc_debug = bits; }
 
 // returns 0 if the shape is unsupported, else the number of rows of the optional colsum_partial output.
 // Every shape the slab kernel takes is also taken by the per-tap kernel (and both use the same number of
@@ -416,6 +429,7 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     a.vertical = pl.vertical; a.TA = pl.TA; a.TB = pl.TB; a.dil = pl.dil;
     a.tiles_a = pl.tiles_a; a.tiles_b = pl.tiles_b;
     a.stages = pl.stages; a.stage_bytes = pl.stage_bytes;
+    a.debug = g_tc_debug;
     for (int t = 0; t < 3; ++t) a.tap_row[t] = (pl.fwd_order ? t : 2 - t) * pl.dil * pl.TB;
     a.n_halves = p.C / TC_BN;
     a.total_m_tiles = p.N * pl.tiles_a * pl.tiles_b;

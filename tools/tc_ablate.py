@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Where does the tcgen05 conv kernel spend its time?  Times lf_conv1d_tc (CUDA events, 20 launches) with parts
+switched off: full / no epilogue body / no TMA loads / neither (MMA issue + barriers only)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lanedetection_end2end_b200 import _capi, ops_net as o  # noqa: E402
+
+h = _capi.lib()
+o.set_conv_mode("tf32")
+for (N, C, H, W, vertical, dil) in [(32, 128, 32, 64, False, 2), (32, 128, 32, 64, True, 8), (32, 64, 64, 128, False, 1),
+                                    (32, 64, 64, 128, True, 1)]:
+    x = torch.randn(N, H, W, C, device="cuda")
+    kh, kw = (3, 1) if vertical else (1, 3)
+    w = torch.randn(C, C, kh, kw, device="cuda") * 0.05
+    mask = torch.randn(N, H, W, C, device="cuda")
+    for variant in (2, 1):
+        h.lf_conv1d_tc_set_variant(variant)
+        for name, kw_ in (("fwd", {}), ("dgrad+mask", {"mask_src": mask})):
+            res = {}
+            for dbg in ((0, 1, 2, 3) if variant == 2 else (0,)):
+                h.lf_conv1d_tc_set_debug(dbg)
+                for _ in range(3):
+                    o.conv3(x, w, vertical, dil, name != "fwd", **kw_)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                # pre-pack outside the timed region: time only the kernel
+                sgn = -1 if name != "fwd" else 1
+                taps = [((sgn * (k - 1) * dil, 0) if vertical else (0, sgn * (k - 1) * dil)) for k in range(3)]
+                wp = o.pack_tc_dgrad(w) if name != "fwd" else o.pack_tc_fwd(w)
+                out = torch.empty_like(x)
+                e0.record()
+                for _ in range(20):
+                    o.run_conv_tc(taps, x, wp, out, **kw_)
+                e1.record()
+                torch.cuda.synchronize()
+                res["dbg%d" % dbg] = round(e0.elapsed_time(e1) / 20 * 1e3, 1)
+            h.lf_conv1d_tc_set_debug(0)
+            print(json.dumps({"C": C, "HxW": [H, W], "vertical": vertical, "dil": dil, "variant": variant, "op": name,
+                              "us_per_launch": res, "GFLOP": 2 * N * H * W * 3 * C * C / 1e9}), flush=True)
+h.lf_conv1d_tc_set_variant(2)
