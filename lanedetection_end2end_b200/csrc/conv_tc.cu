@@ -183,8 +183,15 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const uint64_t adesc = umma_desc_sw128(slab + a.tap_row[t] * 128);
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (t * Cfg::KCHUNKS + cb) * TC_B_ATOM_BYTES));
 #pragma unroll
-                        for (int k8 = 0; k8 < TC_KCH / 8; ++k8)  // 8 tf32 = 32 bytes = 2 x 16B per MMA
-                            umma_tf32(d_tmem, adesc + 2 * k8, bdesc + 2 * k8, TC_IDESC, (cb | t | k8) != 0 ? 1u : 0u);
+                        for (int k8 = 0; k8 < TC_KCH / 8; ++k8) {  // 8 tf32 = 32 bytes = 2 x 16B per MMA
+                            if (a.debug & 4)        // experiment: alternate between two accumulators (garbage results)
+                                umma_tf32(tmem_base + (k8 & 1) * TC_BN, adesc + 2 * k8, bdesc + 2 * k8, TC_IDESC, 1u);
+                            else if (a.debug & 8) { // experiment: N=128 instructions, half as many (garbage results)
+                                if (k8 & 1) umma_tf32(tmem_base, adesc + 2 * k8, bdesc + 2 * k8,
+                                                      (TC_IDESC & ~(0x3Fu << 17)) | ((128u >> 3) << 17), 1u);
+                            } else
+                                umma_tf32(d_tmem, adesc + 2 * k8, bdesc + 2 * k8, TC_IDESC, (cb | t | k8) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty[stage]);  // frees the slab when these MMAs have read it
                     if (++stage == a.stages) {

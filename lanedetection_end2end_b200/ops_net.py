@@ -132,6 +132,83 @@ def pack_tc_dgrad(w):
     return w.permute(1, 2, 3, 0).reshape(Ci, kh * kw * Co).contiguous()
 
 
+# ----------------------------------------------------------------------------------------
+# C = 16 layers on the tensor-core kernels: "super-pixel" packing.
+# A [N,H,W,16] tensor IS a [N,H,W/4,64] tensor in memory (4 neighbouring x positions x 16 channels = 64
+# super-channels).  A 3-tap convolution of the original is a 3-tap convolution of the super-pixel grid
+# with 64x64 weight blocks built from the 16x16 ones: block-diagonal for the vertical (3x1) conv, banded
+# for the horizontal (1x3) conv whose x-1 / x+1 taps cross into the neighbouring super-pixel.  3/4 of the
+# MMA work multiplies zeros, but the tcgen05 kernels are ~3x faster than the CUDA-core kernels on these
+# bandwidth-bound layers and nothing new runs on the device.
+# ----------------------------------------------------------------------------------------
+SUPER = 4
+
+
+def _super_map(vertical, transposed):
+    """[(T, s_in, s_out, t)] : super tap T / sub-positions for every original tap t and output sub-position."""
+    out = []
+    for s in range(SUPER):
+        for t in range(3):
+            off = (t - 1) * (-1 if transposed else 1)      # input offset of weight slot t along the conv axis
+            if vertical:
+                out.append((t, s, s, t))                   # rows are not packed: same tap, same sub-position
+            else:
+                xs = s + off
+                T_in = xs // SUPER                          # -1, 0, +1 super-pixel offset
+                out.append((((-T_in if transposed else T_in) + 1), xs % SUPER, s, t))
+    return out
+
+
+_SUPER_IDX = {}
+
+
+def _super_indices(c, vertical, transposed, device):
+    """Cached gather indices (one device op per packing instead of 12 slice updates)."""
+    key = (c, vertical, transposed, str(device))
+    if key not in _SUPER_IDX:
+        nsrc = c * c * 3                                     # blk[out][in][t] flattened; slot nsrc = 0.0
+        pack = torch.full((SUPER * c, 3 * SUPER * c), nsrc, dtype=torch.long)
+        unpack = torch.full((c, c, 3, SUPER), SUPER * c * SUPER * c * 3, dtype=torch.long)
+        o = torch.arange(c).view(c, 1)
+        i = torch.arange(c).view(1, c)
+        for T, s_in, s_out, t in _super_map(vertical, transposed):
+            pack[s_out * c:(s_out + 1) * c, T * SUPER * c + s_in * c:T * SUPER * c + (s_in + 1) * c] = (o * c + i) * 3 + t
+        for T, s_in, s_out, t in _super_map(vertical, False):
+            # dws[co_s][ci_s][T] flattened, co_s = s_out*c + co, ci_s = s_in*c + ci
+            unpack[:, :, t, s_out] = ((s_out * c + o) * (SUPER * c) + (s_in * c + i)) * 3 + T
+        _SUPER_IDX[key] = (pack.to(device), unpack.to(device))
+    return _SUPER_IDX[key]
+
+
+def pack_tc_super(w, vertical, transposed):
+    """3-tap 16->16 weight [16,16,kh,kw] -> packed [64][3*64] operand of lf_conv1d_tc on the super-pixel
+    grid (layout of pack_tc_fwd / pack_tc_dgrad: row = output super-channel, column = T*64 + input
+    super-channel).  Weight slot T of the packed operand reads the super-pixel at (T-1) (forward) or
+    -(T-1) (transposed), matching the tap lists conv3() builds."""
+    c = w.shape[0]
+    w3 = w.reshape(c, c, 3)                                  # [co][ci][t]
+    blk = w3.permute(1, 0, 2) if transposed else w3          # [out][in][t] of the convolution actually run
+    pack, _ = _super_indices(c, vertical, transposed, w.device)
+    src = torch.cat([blk.reshape(-1), blk.new_zeros(1)])
+    return src[pack]
+
+
+def unpack_wgrad_super(dw_super, vertical):
+    """dw_super [64(co_s),64(ci_s),3] (weight-gradient of the super-pixel conv in Conv2d layout) ->
+    dw [16,16,3]: sum of the (up to 4) blocks each original weight occupies in the packed operand."""
+    c = dw_super.shape[0] // SUPER
+    _, unpack = _super_indices(c, vertical, False, dw_super.device)
+    src = torch.cat([dw_super.reshape(-1), dw_super.new_zeros(1)])
+    return src[unpack].sum(-1)
+
+
+def super_ok(x, dil):
+    N, H, W, C = x.shape
+    if not (CONV_MODE == "tf32" and C == 16 and dil == 1 and W % SUPER == 0 and x.is_contiguous()):
+        return False
+    return int(_lib().lf_conv1d_tc_supported(N, H, W // SUPER, SUPER * C)) > 0
+
+
 def tc_rows(x):
     """0 if the tcgen05 kernel does not take this shape, else the row count of its colsum partials."""
     N, H, W, C = x.shape
@@ -176,6 +253,19 @@ def conv3(x, w, vertical, dil, transposed, colsum=None, **epi):
     ``colsum`` ([C] tensor): also produce the per-channel sums of the result."""
     N, H, W, C = x.shape
     out = torch.empty_like(x)
+    if super_ok(x, dil):
+        xs = x.view(N, H, W // SUPER, SUPER * C)
+        sgn = -1 if transposed else 1
+        taps = [((sgn * (k - 1), 0) if vertical else (0, sgn * (k - 1))) for k in range(3)]
+        epi_s = {k: (v.view(N, H, W // SUPER, SUPER * C) if (v is not None and v.dim() == 4) else v) for k, v in epi.items()}
+        if epi_s.get("bias") is not None:
+            epi_s["bias"] = epi_s["bias"].repeat(SUPER)
+        cs = torch.empty(SUPER * C, dtype=torch.float32, device=x.device) if colsum is not None else None
+        run_conv_tc(taps, xs, pack_tc_super(w, vertical, transposed), out.view(N, H, W // SUPER, SUPER * C), colsum=cs,
+                    **epi_s)
+        if colsum is not None:
+            colsum.copy_(cs.view(SUPER, C).sum(0))
+        return out
     if CONV_MODE == "tf32" and C in (64, 128) and tc_supported(x):
         sgn = -1 if transposed else 1
         taps = [((sgn * (k - 1) * dil, 0) if vertical else (0, sgn * (k - 1) * dil)) for k in range(3)]
@@ -199,6 +289,24 @@ def wgrad3(x_in, d_out, w, vertical, dil, bias_grad="compute"):
     """Weight + bias gradient of one factorised 3-tap convolution -> (dw [Co,Ci,kh,kw], db [Co] or None).
     bias_grad: "compute" (column sums of d_out), or "skip" (the caller gets it elsewhere)."""
     N, H, W, C = x_in.shape
+    if super_ok(x_in, dil) and d_out.is_contiguous():
+        Cs, Ws = SUPER * C, W // SUPER
+        nctas = _lib().lf_wgrad3_tc_ctas(N, H, Ws, Cs)
+        if nctas > 0:
+            tdy = (ctypes.c_int * 3)(*[((k - 1) if vertical else 0) for k in range(3)])
+            tdx = (ctypes.c_int * 3)(*[(0 if vertical else (k - 1)) for k in range(3)])
+            partial = torch.empty(nctas * 3 * Cs * Cs, dtype=torch.float32, device=x_in.device)
+            dws = torch.empty(Cs, Cs, 3, dtype=torch.float32, device=x_in.device)
+            st = _stream()
+            _capi.call("lf_wgrad3_tc", ptr(x_in), ptr(d_out), N, H, Ws, Cs, tdy, tdx, ptr(partial), nctas, st,
+                       flops=2 * N * H * W * 3 * C * C, nbytes=8 * N * H * W * C)
+            _capi.call("lf_wgrad_reduce", ptr(partial), nctas, 3, Cs, Cs, Cs, Cs, ptr(dws), 1, 3, Cs * 3, st)
+            dw = unpack_wgrad_super(dws, vertical).reshape(w.shape)
+            db = None
+            if bias_grad == "compute":
+                db = torch.empty(C, dtype=torch.float32, device=x_in.device)
+                run_colsum(d_out, C, 0, db)
+            return dw, db
     dw = torch.empty_like(w)
     db = torch.empty(C, dtype=torch.float32, device=x_in.device) if bias_grad == "compute" else None
     lay = (1, 3, C * 3)                                   # (tap, ci, co) strides of [Co,Ci,3] weights

@@ -166,3 +166,34 @@ def test_tc_fused_bn_statistics(C, H, W, vertical, dil):
     assert float((s.mean.double() - mean).abs().max()) <= 1e-5 * float(mean.abs().max() + 1)
     assert float((s.invstd.double() - (var + 1e-3).rsqrt()).abs().max()) <= 1e-5
     assert float((rm.double() - 0.1 * mean).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("vertical", [True, False])
+def test_c16_layers_on_tensor_cores_via_super_pixels(vertical):
+    """C = 16 decoder blocks: [N,H,W,16] viewed as [N,H,W/4,64] with packed 64x64 weight blocks
+    (ops_net.pack_tc_super).  TF32-exact operands -> agreement with the fp32 kernels to round-off."""
+    o = ops()
+    g = torch.Generator().manual_seed(11)
+    N, C, H, W = 2, 16, 128, 256
+    x = tf32_exact(torch.randn(N, H, W, C, generator=g).cuda())
+    dy = tf32_exact(torch.randn(N, H, W, C, generator=g).cuda())
+    kh, kw = (3, 1) if vertical else (1, 3)
+    w = tf32_exact((torch.randn(C, C, kh, kw, generator=g) / 7).cuda())
+    b = torch.randn(C, generator=g).cuda()
+    mask = torch.randn(N, H, W, C, generator=g).cuda()
+    res = {}
+    for mode in ("fp32", "tf32"):
+        o.set_conv_mode(mode)
+        try:
+            if mode == "tf32":
+                assert o.super_ok(x, 1)
+            cs = torch.empty(C, device="cuda")
+            res[mode] = (o.conv3(x, w, vertical, 1, False, bias=b, relu=True),
+                         o.conv3(dy, w, vertical, 1, True, colsum=cs, mask_src=mask), cs,
+                         *o.wgrad3(x, dy, w, vertical, 1))
+            torch.cuda.synchronize()
+        finally:
+            o.set_conv_mode("fp32")
+    for i, (a, r) in enumerate(zip(res["tf32"], res["fp32"])):
+        tol = 2e-6 if i < 2 else 1e-4
+        assert float((a - r).abs().max()) <= tol * float(r.abs().max()), i

@@ -161,3 +161,39 @@ def test_tc_kernel_contract_fwd_and_dgrad(vertical, dil):
 
     torch.testing.assert_close(nchw(emulate(nhwc(x.detach()), ops.pack_tc_fwd(w), 1)), y.detach())
     torch.testing.assert_close(nchw(emulate(nhwc(gy), ops.pack_tc_dgrad(w), -1)), gx)
+
+
+@pytest.mark.parametrize("vertical", [True, False])
+@pytest.mark.parametrize("transposed", [False, True])
+def test_super_pixel_packing_of_16_channel_convs(vertical, transposed):
+    """ops_net.pack_tc_super: a 3-tap 16->16 conv on [N,H,W,16] == the lf_conv1d_tc contract on the
+    [N,H,W/4,64] view with the packed 64x(3*64) operand; and unpack_wgrad_super inverts the weight-gradient."""
+    N, C, H, W = 2, 16, 6, 16
+    kh, kw = (3, 1) if vertical else (1, 3)
+    pad = (1, 0) if vertical else (0, 1)
+    x = torch.randn(N, C, H, W, dtype=DT, requires_grad=True)
+    w = torch.randn(C, C, kh, kw, dtype=DT, requires_grad=True)
+    y = F.conv2d(x, w, None, 1, pad)
+    gy = torch.randn_like(y)
+    gx, gw = torch.autograd.grad(y, (x, w), gy)
+    inp, ref = (nhwc(gy), gx) if transposed else (nhwc(x.detach()), y.detach())
+    xs = inp.reshape(N, H, W // 4, 64)
+    wp = ops.pack_tc_super(w.detach(), vertical, transposed)
+    sgn = -1 if transposed else 1
+    out = torch.zeros(N, H, W // 4, 64, dtype=DT)
+    for t in range(3):
+        dy, dx = ((sgn * (t - 1), 0) if vertical else (0, sgn * (t - 1)))
+        for yy in range(H):
+            for xx in range(W // 4):
+                iy, ix = yy + dy, xx + dx
+                if 0 <= iy < H and 0 <= ix < W // 4:
+                    out[:, yy, xx] += xs[:, iy, ix] @ wp[:, t * 64:(t + 1) * 64].t()
+    torch.testing.assert_close(nchw(out.reshape(N, H, W, C)), ref)
+    if not transposed:
+        # weight gradient of the super conv (Conv2d layout [co_s][ci_s][T]) -> original
+        xsup = xs.permute(0, 3, 1, 2).contiguous().requires_grad_(False)
+        wsup = torch.zeros(64, 64, kh, kw, dtype=DT, requires_grad=True)
+        ysup = F.conv2d(xsup, wsup, None, 1, pad)
+        (gws,) = torch.autograd.grad(ysup, wsup, nhwc(gy).reshape(N, H, W // 4, 64).permute(0, 3, 1, 2))
+        got = ops.unpack_wgrad_super(gws.reshape(64, 64, 3), vertical).reshape(C, C, kh, kw)
+        torch.testing.assert_close(got, gw)

@@ -19,11 +19,11 @@ for (N, C, H, W, vertical, dil) in [(32, 128, 32, 64, False, 2), (32, 128, 32, 6
     kh, kw = (3, 1) if vertical else (1, 3)
     w = torch.randn(C, C, kh, kw, device="cuda") * 0.05
     mask = torch.randn(N, H, W, C, device="cuda")
-    for variant in (2, 1):
+    for variant in (2,):
         h.lf_conv1d_tc_set_variant(variant)
         for name, kw_ in (("fwd", {}), ("dgrad+mask", {"mask_src": mask})):
             res = {}
-            for dbg in ((0, 1, 2, 3) if variant == 2 else (0,)):
+            for dbg in ((0, 1, 2, 3, 7, 11) if variant == 2 else (0,)):
                 h.lf_conv1d_tc_set_debug(dbg)
                 for _ in range(3):
                     o.conv3(x, w, vertical, dil, name != "fwd", **kw_)
