@@ -14,9 +14,17 @@ from ._pkg import submodule
 _ops = submodule("ops_net")
 
 
+_PENDING_COUNTERS = None      # when a list: BatchNorm step counters to bump with ONE fused launch
+
+
 def _track(bn, training):
+    """nn.BatchNorm2d bookkeeping (num_batches_tracked += 1 per training forward).  Inside ``Net.forward``
+    the 41 counters are collected and incremented by a single ``torch._foreach_add_`` instead of 41 launches."""
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+        if _PENDING_COUNTERS is not None:
+            _PENDING_COUNTERS.append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked += 1
 
 
 class DownsamplerBlock(nn.Module):
@@ -182,8 +190,15 @@ class Net(nn.Module):
         self.decoder = Decoder(out_channels, pretrained)
 
     def forward(self, input, flag, only_encode=False):
+        global _PENDING_COUNTERS
         if only_encode:
             return self.encoder.forward(input, predict=True)
-        encoder_output = self.encoder(input)
-        decoder_output, output_seg = self.decoder.forward(encoder_output, flag)
+        _PENDING_COUNTERS = []
+        try:
+            encoder_output = self.encoder(input)
+            decoder_output, output_seg = self.decoder.forward(encoder_output, flag)
+        finally:
+            pending, _PENDING_COUNTERS = _PENDING_COUNTERS, None
+            if pending:
+                torch._foreach_add_(pending, 1)
         return encoder_output, decoder_output, output_seg

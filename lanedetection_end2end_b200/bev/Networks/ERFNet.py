@@ -14,6 +14,5 @@ class Net(_E.Net):
     def forward(self, input, flag, only_encode=False):
         if only_encode:
             return self.encoder.forward(input, predict=True)
-        encoder_output = self.encoder(input)
-        decoder_output, _ = self.decoder.forward(encoder_output, flag)
+        encoder_output, decoder_output, _ = super().forward(input, flag)
         return encoder_output, decoder_output

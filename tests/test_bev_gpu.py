@@ -1,0 +1,56 @@
+"""Birds_Eye_View_Loss variant of the module surface (lanedetection_end2end_b200/bev): same kernels, normalised
+grid, y = 1 - y', float32 beta, 2-tuple ERFNet, 9-tuple Net.forward with M (reference BEV LSQ_layer.py:290-326)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inputs, lsq_oracle as lo, erfnet_oracle as eo
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bev_net_forward_backward_vs_oracle():
+    from lanedetection_end2end_b200.bev.Networks.LSQ_layer import Net
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    from lanedetection_end2end_b200.Loss_crit import Area_Loss
+    B, L, order = 2, 2, 2
+    args = define_args().parse_args(["--image_dir", "x", "--gt_dir", "y", "--batch_size", str(B), "--nclasses", str(L),
+                                     "--order", str(order)])
+    model = Net(args)
+    P_np = inputs.make_erfnet_params(3, L, seed=11)
+    sd = model.state_dict()
+    for k, v in P_np.items():
+        sd[k] = torch.from_numpy(v)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    for m in model.modules():
+        if hasattr(m, "dropout"):
+            m.dropout.p = 0
+    x_np = inputs.make_images(B, 256, 512, seed=3)
+    out = model(torch.from_numpy(x_np).cuda(), True)
+    assert len(out) == 9
+    beta0, beta1, beta2, beta3, masked, M, output, line, horizon = out
+    assert beta0.dtype == torch.float32 and beta0.shape == (B, order + 1, 1) and beta2 is None
+    assert M.shape == (B, 3, 3) and output.shape == (B, L, 256, 512)
+    gt = torch.tensor([[1e-3, -0.2, 0.5], [2e-3, 0.1, 0.4]], device="cuda")
+    loss = Area_Loss(order, "none")(beta0, gt) + Area_Loss(order, "none")(beta1, gt)
+    loss.backward()
+    # oracle: same network + BEV grid (normalised, const 1) in fp64
+    P = {k[4:]: torch.from_numpy(v).double().requires_grad_(True) for k, v in P_np.items()}
+    _, dec = eo.erfnet_forward(torch.from_numpy(x_np).double(), P, True)
+    grid = torch.from_numpy(np.load(os.path.join(GOLDEN, "lsq_bev_l2_d2.npz"))["grid0"])
+    np.testing.assert_array_equal(model.project_layer(model.M)[0].cpu().numpy(), grid.numpy())
+    mk = lo.activate_and_mask(dec, "square", model.zero_rows)
+    b_ref, _ = lo.wls_forward(mk, grid, order, 1.0)
+    ours = torch.stack([beta0.squeeze(-1), beta1.squeeze(-1)], 1).double().cpu()
+    err = float(((ours - b_ref.detach()).abs().amax(-1) / b_ref.detach().abs().amax(-1)).max())
+    assert err < 1e-4, err
+    ref_loss = lo.area_loss(b_ref[:, 0], gt.double().cpu(), 2) + lo.area_loss(b_ref[:, 1], gt.double().cpu(), 2)
+    ref_loss.backward()
+    g = model.net.decoder.output_conv.weight.grad.double().cpu()
+    gr = P["decoder.output_conv.weight"].grad
+    assert float((g - gr).abs().max() / gr.abs().max()) < 5e-2
