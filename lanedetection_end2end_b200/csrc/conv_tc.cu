@@ -44,7 +44,7 @@ namespace lf {
 static int g_tc_variant = 2;  // 2 = halo slab (this file), 1 = one box per tap (conv_tc_v1.cu)
 static int g_tc_debug = 0;    // timing experiments only: bit0 = skip the epilogue body, bit1 = skip the TMA loads
 
-constexpr int TC_THREADS = 192;
+
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 64;
 constexpr int TC_KCH = 32;                    // fp32 elements per 128-byte swizzle row
@@ -87,10 +87,18 @@ template <int C>
 struct TcCfg {
     static constexpr int KCHUNKS = C / TC_KCH;  // 32-channel chunks (= slabs per tile)
     static constexpr int B_BYTES = 3 * KCHUNKS * TC_B_ATOM_BYTES;
+    // Epilogue warp groups of 4 warps (one per TMEM lane quadrant).  At C=64 a tile has half the MMA work of a
+    // C=128 tile but the same 128x64 output, so one group cannot drain the accumulator as fast as the tensor
+    // pipe fills it (measured: epilogue-bound at 1.5-2.4x the MMA floor); two groups each take one 32-channel
+    // half with their own staging tile.  At C=128 the shared memory goes to slab stages instead.
+    static constexpr int EPI_GROUPS = (C == 64) ? 2 : 1;
+    static constexpr int HALVES = 2 / EPI_GROUPS;  // 32-channel halves each group walks per tile
+    static constexpr int THREADS = 64 + 128 * EPI_GROUPS;
+    static constexpr int STG_BYTES = EPI_GROUPS * TC_STG_BYTES;
 };
 
 template <int C>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
 conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     using Cfg = TcCfg<C>;
     extern __shared__ uint8_t smem_raw[];
@@ -98,7 +106,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* sB = smem;
     uint8_t* sA = smem + Cfg::B_BYTES;
     float* stg = reinterpret_cast<float*>(sA + (size_t)a.stages * a.stage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg) + TC_STG_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stg) + Cfg::STG_BYTES);
     uint64_t* full = bars;                       // [TC_MAX_STAGES]
     uint64_t* empty = bars + TC_MAX_STAGES;      // [TC_MAX_STAGES]
     uint64_t* bfull = bars + 2 * TC_MAX_STAGES;  // [1]
@@ -121,7 +129,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_init(bfull, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty[b], 4 * Cfg::EPI_GROUPS);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -203,18 +211,23 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        // ================= epilogue (warps 2..5) =================
+        // ================= epilogue (warps 2..) =================
+        constexpr int NH = Cfg::HALVES;
         const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may access
         const int m = lane_base + lane;         // phase 1: this thread's pixel row of the tile
-        const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
+        const int grp = (threadIdx.x - 64) >> 7;  // epilogue group (0 when there is only one)
+        const int et = (threadIdx.x - 64) & 127;  // 0..127 inside the group
         const int c4 = et & 7;                  // phase 2: float4 column inside a 32-channel half (fixed)
         const int r0 = et >> 3;                 // phase 2: first of this thread's 8 rows (r0, r0+16, ...)
         const int tb_shift = (a.TB == 8) ? 3 : 4;
+        const int h_first = (Cfg::EPI_GROUPS == 2) ? grp : 0;  // first (only) channel half of this group
+        float* stg_g = stg + grp * (TC_STG_BYTES / 4);
+        const int bar_id = 1 + grp;
         const bool pre_mask = a.mask_src != nullptr;
         const bool pre_add = (a.add_src != nullptr) && !pre_mask;  // both given: add_src is read in the loop
-        float4 csum[2], csq[2];                 // running column sums / sums of squares, per channel half
+        float4 csum[NH], csq[NH];               // running column sums / sums of squares, per channel half
 #pragma unroll
-        for (int h = 0; h < 2; ++h) csum[h] = csq[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int hh = 0; hh < NH; ++hh) csum[hh] = csq[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
         int it = 0;
         for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
             const int buf = it & 1;
@@ -222,7 +235,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int ta = mt % a.tiles_a;
             const int tb = (mt / a.tiles_a) % a.tiles_b;
             const int n = mt / (a.tiles_a * a.tiles_b);
-            // global offsets of this thread's 8 phase-2 rows (channel 4*c4 of half 0)
+            // global offsets of this thread's 8 phase-2 rows (channel 4*c4 of the group's first half)
             size_t roff[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -230,26 +243,26 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int ap = r >> tb_shift, bp = r & (a.TB - 1);  // slab order: cross axis fastest
                 const int pa = ta * a.TA + ap, pb = tb * a.TB + bp;
                 const int y = a.vertical ? pa : pb, x = a.vertical ? pb : pa;
-                roff[j] = ((size_t)(n * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN + 4 * c4;
+                roff[j] = ((size_t)(n * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN + 32 * h_first + 4 * c4;
             }
             // Prefetch the ReLU mask (or the gated residual gradient) of this tile while the MMAs are still
             // running: the loads' latency hides behind the wait for the accumulator.
-            float4 pre[2][8];
+            float4 pre[NH][8];
             if (pre_mask || pre_add) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (pre_mask) {
-                            pre[h][j] = __ldg(reinterpret_cast<const float4*>(a.mask_src + roff[j] + 32 * h));
+                            pre[hh][j] = __ldg(reinterpret_cast<const float4*>(a.mask_src + roff[j] + 32 * hh));
                         } else {
-                            float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + roff[j] + 32 * h));
+                            float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + roff[j] + 32 * hh));
                             if (a.add_mask) {
-                                const float4 mk = __ldg(reinterpret_cast<const float4*>(a.add_mask + roff[j] + 32 * h));
+                                const float4 mk = __ldg(reinterpret_cast<const float4*>(a.add_mask + roff[j] + 32 * hh));
                                 ad.x = mk.x > 0.f ? ad.x : 0.f; ad.y = mk.y > 0.f ? ad.y : 0.f;
                                 ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
                             }
-                            pre[h][j] = ad;
+                            pre[hh][j] = ad;
                         }
                     }
             }
@@ -262,7 +275,8 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 continue;
             }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int hh = 0; hh < NH; ++hh) {
+                const int h = h_first + hh;
                 // ---- phase 1: TMEM -> registers -> (+bias, ReLU) -> staging half-tile, one pixel row per thread
 #pragma unroll
                 for (int c0 = 0; c0 < 32; c0 += 16) {
@@ -280,25 +294,25 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (a.relu) {
                             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                         }
-                        *reinterpret_cast<float4*>(&stg[m * TC_STG_LD + c0 + 4 * q]) = o;
+                        *reinterpret_cast<float4*>(&stg_g[m * TC_STG_LD + c0 + 4 * q]) = o;
                     }
                 }
-                if (h == 1) tc_fence_before();
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // staging complete (epilogue warps only)
-                if (h == 1 && lane == 0) mbar_arrive(&tempty[buf]);  // all TMEM reads done: buffer free for the MMA warp
+                if (hh == NH - 1) tc_fence_before();
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // staging complete (this group only)
+                if (hh == NH - 1 && lane == 0) mbar_arrive(&tempty[buf]);  // this warp's TMEM reads are done
                 // ---- phase 2: row-major walk, 8 consecutive threads = one pixel's 32 channels (128 B)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int r = r0 + 16 * j;
-                    const size_t off = roff[j] + 32 * h;
-                    float4 o = *reinterpret_cast<const float4*>(&stg[r * TC_STG_LD + 4 * c4]);
+                    const size_t off = roff[j] + 32 * hh;
+                    float4 o = *reinterpret_cast<const float4*>(&stg_g[r * TC_STG_LD + 4 * c4]);
                     if (pre_mask) {
-                        const float4 mk = pre[h][j];
+                        const float4 mk = pre[hh][j];
                         o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
                         o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
                     }
                     if (pre_add) {
-                        o.x += pre[h][j].x; o.y += pre[h][j].y; o.z += pre[h][j].z; o.w += pre[h][j].w;
+                        o.x += pre[hh][j].x; o.y += pre[hh][j].y; o.z += pre[hh][j].z; o.w += pre[hh][j].w;
                     } else if (a.add_src) {
                         float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + off));
                         if (a.add_mask) {
@@ -309,32 +323,33 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
                     }
                     *reinterpret_cast<float4*>(a.out + off) = o;
-                    csum[h].x += o.x; csum[h].y += o.y; csum[h].z += o.z; csum[h].w += o.w;
-                    csq[h].x = fmaf(o.x, o.x, csq[h].x); csq[h].y = fmaf(o.y, o.y, csq[h].y);
-                    csq[h].z = fmaf(o.z, o.z, csq[h].z); csq[h].w = fmaf(o.w, o.w, csq[h].w);
+                    csum[hh].x += o.x; csum[hh].y += o.y; csum[hh].z += o.z; csum[hh].w += o.w;
+                    csq[hh].x = fmaf(o.x, o.x, csq[hh].x); csq[hh].y = fmaf(o.y, o.y, csq[hh].y);
+                    csq[hh].z = fmaf(o.z, o.z, csq[hh].z); csq[hh].w = fmaf(o.w, o.w, csq[hh].w);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // staging half-tile may be overwritten
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // staging half-tile may be overwritten
             }
         }
         if (a.colsum_partial || a.stats_partial) {
             // 16 threads share each (half, float4 column): combine them through the (now free) staging tile
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                *reinterpret_cast<float4*>(&stg[(h * 16 + r0) * TC_STG_LD + 4 * c4]) = csum[h];
-                *reinterpret_cast<float4*>(&stg[(32 + h * 16 + r0) * TC_STG_LD + 4 * c4]) = csq[h];
+            for (int hh = 0; hh < NH; ++hh) {
+                *reinterpret_cast<float4*>(&stg_g[(hh * 16 + r0) * TC_STG_LD + 4 * c4]) = csum[hh];
+                *reinterpret_cast<float4*>(&stg_g[(32 + hh * 16 + r0) * TC_STG_LD + 4 * c4]) = csq[hh];
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et < TC_BN) {
-                const int h = et >> 5, c = et & 31;
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (et < 32 * NH) {
+                const int hh = et >> 5, c = et & 31;
+                const int ch = n_half * TC_BN + 32 * (h_first + hh) + c;
                 double tot = 0.0, tsq = 0.0;
 #pragma unroll
                 for (int g = 0; g < 16; ++g) {
-                    tot += (double)stg[(h * 16 + g) * TC_STG_LD + c];
-                    tsq += (double)stg[(32 + h * 16 + g) * TC_STG_LD + c];
+                    tot += (double)stg_g[(hh * 16 + g) * TC_STG_LD + c];
+                    tsq += (double)stg_g[(32 + hh * 16 + g) * TC_STG_LD + c];
                 }
-                if (a.colsum_partial) a.colsum_partial[(size_t)cta_m * a.Ctot + n_half * TC_BN + et] = (float)tot;
+                if (a.colsum_partial) a.colsum_partial[(size_t)cta_m * a.Ctot + ch] = (float)tot;
                 if (a.stats_partial) {
-                    double* sp = a.stats_partial + (size_t)cta_m * 2 * a.Ctot + n_half * TC_BN + et;
+                    double* sp = a.stats_partial + (size_t)cta_m * 2 * a.Ctot + ch;
                     sp[0] = tot;
                     sp[a.Ctot] = tsq;
                 }
@@ -382,7 +397,7 @@ static bool tc_make_plan(int N, int H, int W, int C, const int* dy, const int* d
     p->tiles_b = ext_b / p->TB;
     p->stage_bytes = (p->TA + 2 * p->dil) * p->TB * 128;
     const int b_bytes = 3 * (C / 32) * TC_B_ATOM_BYTES;
-    const int fixed = 1024 + b_bytes + TC_STG_BYTES + 512;  // alignment slack + B + epilogue staging + barriers
+    const int fixed = 1024 + b_bytes + (C == 64 ? 2 : 1) * TC_STG_BYTES + 512;  // alignment slack + B + epilogue staging + barriers
     int stages = (TC_SMEM_LIMIT - fixed) / p->stage_bytes;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return false;
@@ -471,11 +486,11 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     if (p.C == 128) {
         e = cudaFuncSetAttribute(conv1d_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_kernel<128><<<grid, TC_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
+        conv1d_tc_kernel<128><<<grid, TcCfg<128>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
     } else {
         e = cudaFuncSetAttribute(conv1d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_kernel<64><<<grid, TC_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
+        conv1d_tc_kernel<64><<<grid, TcCfg<64>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
     }
     return check_launch();
 }

@@ -257,7 +257,7 @@ def conv3(x, w, vertical, dil, transposed, colsum=None, **epi):
         xs = x.view(N, H, W // SUPER, SUPER * C)
         sgn = -1 if transposed else 1
         taps = [((sgn * (k - 1), 0) if vertical else (0, sgn * (k - 1))) for k in range(3)]
-        epi_s = {k: (v.view(N, H, W // SUPER, SUPER * C) if (v is not None and v.dim() == 4) else v) for k, v in epi.items()}
+        epi_s = {k: (v.view(N, H, W // SUPER, SUPER * C) if (torch.is_tensor(v) and v.dim() == 4) else v) for k, v in epi.items()}
         if epi_s.get("bias") is not None:
             epi_s["bias"] = epi_s["bias"].repeat(SUPER)
         cs = torch.empty(SUPER * C, dtype=torch.float32, device=x.device) if colsum is not None else None
