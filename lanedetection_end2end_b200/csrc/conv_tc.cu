@@ -140,20 +140,23 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+        // ================= TMA producer (whole warp converged, one elected lane issues) =================
+        const bool leader = elect_one();
+        if (leader) {
             mbar_arrive_expect_tx(bfull, Cfg::B_BYTES);
             for (int kb = 0; kb < 3 * Cfg::KCHUNKS; ++kb)
                 tma_load_2d(&tmB, bfull, sB + kb * TC_B_ATOM_BYTES, kb * TC_KCH, n_half * TC_BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride) {
-                const int ta = mt % a.tiles_a;
-                const int tb = (mt / a.tiles_a) % a.tiles_b;
-                const int n = mt / (a.tiles_a * a.tiles_b);
-                const int a0 = ta * a.TA - a.dil, b0 = tb * a.TB;
-                for (int cb = 0; cb < Cfg::KCHUNKS; ++cb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride) {
+            const int ta = mt % a.tiles_a;
+            const int tb = (mt / a.tiles_a) % a.tiles_b;
+            const int n = mt / (a.tiles_a * a.tiles_b);
+            const int a0 = ta * a.TA - a.dil, b0 = tb * a.TB;
+            for (int cb = 0; cb < Cfg::KCHUNKS; ++cb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (leader) {
                     if (a.debug & 2) {
                         mbar_arrive(&full[stage]);
                     } else {
@@ -161,54 +164,49 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         // tensor map dims: (ci, cblk, cross axis, conv axis, n)
                         tma_load_5d(&tmA, &full[stage], sA + (size_t)stage * a.stage_bytes, 0, cb, b0, a0, n);
                     }
-                    if (++stage == a.stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                }
+                if (++stage == a.stages) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            mbar_wait(bfull, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
-                const int buf = it & 1;
-                const uint32_t use_parity = (it >> 1) & 1;
-                mbar_wait(&tempty[buf], use_parity ^ 1);
+        // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+        const bool leader = elect_one();
+        mbar_wait(bfull, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
+            const int buf = it & 1;
+            const uint32_t use_parity = (it >> 1) & 1;
+            mbar_wait(&tempty[buf], use_parity ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * TC_BN;
+            for (int cb = 0; cb < Cfg::KCHUNKS; ++cb) {
+                mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * TC_BN;
-                for (int cb = 0; cb < Cfg::KCHUNKS; ++cb) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t slab = smem_u32(sA + (size_t)stage * a.stage_bytes);
+                const uint32_t slab = smem_u32(sA + (size_t)stage * a.stage_bytes);
 #pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        // tap t = the slab shifted by tap_row[t] rows of 128 B (a multiple of 8 rows)
-                        const uint64_t adesc = umma_desc_sw128(slab + a.tap_row[t] * 128);
-                        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (t * Cfg::KCHUNKS + cb) * TC_B_ATOM_BYTES));
+                for (int t = 0; t < 3; ++t) {
+                    // tap t = the slab shifted by tap_row[t] rows of 128 B (a multiple of 8 rows)
+                    const uint64_t adesc = umma_desc_sw128(slab + a.tap_row[t] * 128);
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (t * Cfg::KCHUNKS + cb) * TC_B_ATOM_BYTES));
 #pragma unroll
-                        for (int k8 = 0; k8 < TC_KCH / 8; ++k8) {  // 8 tf32 = 32 bytes = 2 x 16B per MMA
-                            if (a.debug & 4)        // experiment: alternate between two accumulators (garbage results)
-                                umma_tf32(tmem_base + (k8 & 1) * TC_BN, adesc + 2 * k8, bdesc + 2 * k8, TC_IDESC, 1u);
-                            else if (a.debug & 8) { // experiment: N=128 instructions, half as many (garbage results)
-                                if (k8 & 1) umma_tf32(tmem_base, adesc + 2 * k8, bdesc + 2 * k8,
-                                                      (TC_IDESC & ~(0x3Fu << 17)) | ((128u >> 3) << 17), 1u);
-                            } else
-                                umma_tf32(d_tmem, adesc + 2 * k8, bdesc + 2 * k8, TC_IDESC, (cb | t | k8) != 0 ? 1u : 0u);
-                        }
-                    }
-                    umma_commit(&empty[stage]);  // frees the slab when these MMAs have read it
-                    if (++stage == a.stages) {
-                        stage = 0;
-                        phase ^= 1;
+                    for (int k8 = 0; k8 < TC_KCH / 8; ++k8) {  // 8 tf32 = 32 bytes = 2 x 16B per MMA
+                        // NOTE: keep this loop free of run-time switches — two extra predicated MMA variants
+                        // here (an ablation experiment) cost 50 ns per MMA = 16 us per launch.
+                        if (leader) umma_tf32(d_tmem, adesc + 2 * k8, bdesc + 2 * k8, TC_IDESC, (cb | t | k8) != 0 ? 1u : 0u);
                     }
                 }
-                umma_commit(&tfull[buf]);  // accumulator complete -> epilogue
+                if (leader) umma_commit(&empty[stage]);  // frees the slab when these MMAs have read it
+                if (++stage == a.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
+            if (leader) umma_commit(&tfull[buf]);  // accumulator complete -> epilogue
         }
     } else {
         // ================= epilogue (warps 2..) =================

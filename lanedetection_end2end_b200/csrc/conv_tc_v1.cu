@@ -109,60 +109,62 @@ conv1d_tc_v1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+        // ================= TMA producer (whole warp converged, one elected lane issues) =================
+        const bool leader = elect_one();
+        if (leader) {
             mbar_arrive_expect_tx(bfull, Cfg::B_BYTES);
             for (int kb = 0; kb < Cfg::KSTEPS; ++kb)
                 tma_load_2d(&tmB, bfull, sB + kb * TC_B_ATOM_BYTES_V1, kb * TC_KCH_V1, n_half * TC_BN_V1);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride) {
-                const int tx = mt % tiles_x;
-                const int ty = (mt / tiles_x) % tiles_y;
-                const int n = mt / (tiles_x * tiles_y);
-                for (int t = 0; t < 3; ++t) {
-                    const int x0 = tx * a.bx + a.dx[t], y0 = ty * a.by + a.dy[t];
-                    for (int cb = 0; cb < Cfg::KCHUNKS; ++cb) {
-                        mbar_wait(&empty[stage], phase ^ 1);
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride) {
+            const int tx = mt % tiles_x;
+            const int ty = (mt / tiles_x) % tiles_y;
+            const int n = mt / (tiles_x * tiles_y);
+            for (int t = 0; t < 3; ++t) {
+                const int x0 = tx * a.bx + a.dx[t], y0 = ty * a.by + a.dy[t];
+                for (int cb = 0; cb < Cfg::KCHUNKS; ++cb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (leader) {
                         mbar_arrive_expect_tx(&full[stage], TC_A_STAGE_BYTES_V1);
                         tma_load_5d(&tmA, &full[stage], sA + stage * TC_A_STAGE_BYTES_V1, 0, cb, x0, y0, n);
-                        if (++stage == Cfg::STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
                     }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            mbar_wait(bfull, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
-                const int buf = it & 1;
-                const uint32_t use_parity = (it >> 1) & 1;
-                mbar_wait(&tempty[buf], use_parity ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * TC_BN_V1;
-                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint64_t adesc = umma_desc_sw128_v1(smem_u32(sA + stage * TC_A_STAGE_BYTES_V1));
-                    const uint64_t bdesc = umma_desc_sw128_v1(smem_u32(sB + ks * TC_B_ATOM_BYTES_V1));
-#pragma unroll
-                    for (int k8 = 0; k8 < TC_KCH_V1 / 8; ++k8)  // 8 tf32 = 32 bytes = 2 x 16B per MMA
-                        umma_tf32(d_tmem, adesc + 2 * k8, bdesc + 2 * k8, TC_IDESC_V1, (ks | k8) != 0 ? 1u : 0u);
-                    umma_commit(&empty[stage]);  // frees the A stage when these MMAs have read it
                     if (++stage == Cfg::STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tfull[buf]);  // accumulator complete -> epilogue
             }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+        const bool leader = elect_one();
+        mbar_wait(bfull, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
+            const int buf = it & 1;
+            const uint32_t use_parity = (it >> 1) & 1;
+            mbar_wait(&tempty[buf], use_parity ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * TC_BN_V1;
+            for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128_v1(smem_u32(sA + stage * TC_A_STAGE_BYTES_V1));
+                const uint64_t bdesc = umma_desc_sw128_v1(smem_u32(sB + ks * TC_B_ATOM_BYTES_V1));
+#pragma unroll
+                for (int k8 = 0; k8 < TC_KCH_V1 / 8; ++k8)  // 8 tf32 = 32 bytes = 2 x 16B per MMA
+                    if (leader) umma_tf32(d_tmem, adesc + 2 * k8, bdesc + 2 * k8, TC_IDESC_V1, (ks | k8) != 0 ? 1u : 0u);
+                if (leader) umma_commit(&empty[stage]);  // frees the A stage when these MMAs have read it
+                if (++stage == Cfg::STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (leader) umma_commit(&tfull[buf]);  // accumulator complete -> epilogue
         }
     } else {
         // ================= epilogue (warps 2..5) =================

@@ -34,6 +34,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > TC_SPIN_LIMIT) __trap();  // never hang the GPU on a protocol bug
     }
 }
+// One lane of a CONVERGED warp (elect.sync).  The tcgen05 / TMA issuing warps run their loops with all 32 lanes so
+// that descriptors, coordinates and barrier addresses are warp-uniform values (uniform registers); only the issuing
+// instruction itself is predicated on the elected lane.  Running the whole loop under `if (lane == 0)` instead makes
+// every UTCHMMA / UTMALDG operand a per-thread value that the compiler moves into uniform registers with an
+// ELECT + 5x R2UR + branch "waterfall" per instruction (~17 extra instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -95,65 +95,70 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int p = p_begin; p < p_end; ++p) {
-                const int tx = p % tiles_x;
-                const int ty = (p / tiles_x) % tiles_y;
-                const int n = p / (tiles_x * tiles_y);
-                const int x0 = tx * a.bx, y0 = ty * a.by;
-                mbar_wait(&empty[stage], phase ^ 1);
+        // TMA producer: whole warp converged (uniform coordinates / addresses), one elected lane issues
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int p = p_begin; p < p_end; ++p) {
+            const int tx = p % tiles_x;
+            const int ty = (p / tiles_x) % tiles_y;
+            const int n = p / (tiles_x * tiles_y);
+            const int x0 = tx * a.bx, y0 = ty * a.by;
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+            if (leader) {
                 mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
                 for (int cb = 0; cb < Cfg::CB; ++cb) tma_load_5d(&tmDY, &full[stage], st + cb * Cfg::BOX_BYTES, 0, cb, x0, y0, n);
                 for (int t = 0; t < 3; ++t)
                     for (int cb = 0; cb < Cfg::CB; ++cb)
                         tma_load_5d(&tmX, &full[stage], st + ((1 + t) * Cfg::CB + cb) * Cfg::BOX_BYTES, 0, cb, x0 + a.dx[t],
                                     y0 + a.dy[t], n);
-                if (++stage == Cfg::STAGES) {
-                    stage = 0;
-                    phase ^= 1;
-                }
+            }
+            if (++stage == Cfg::STAGES) {
+                stage = 0;
+                phase ^= 1;
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            bool first = true;
-            for (int p = p_begin; p < p_end; ++p) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after();
-                const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        // MMA issuer: whole warp converged so the descriptors stay in uniform registers (see elect_one())
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        bool first = true;
+        for (int p = p_begin; p < p_end; ++p) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
 #pragma unroll
-                for (int k8 = 0; k8 < Cfg::KP / 8; ++k8) {
-                    const uint32_t koff = k8 * 1024;  // 8 pixel rows
-                    const uint64_t bdesc = umma_desc_mn_sw128(st + koff, Cfg::BOX_BYTES);
-                    const uint32_t acc = (first && k8 == 0) ? 0u : 1u;
-                    if (C == 128) {
+            for (int k8 = 0; k8 < Cfg::KP / 8; ++k8) {
+                const uint32_t koff = k8 * 1024;  // 8 pixel rows
+                const uint64_t bdesc = umma_desc_mn_sw128(st + koff, Cfg::BOX_BYTES);
+                const uint32_t acc = (first && k8 == 0) ? 0u : 1u;
+                if (C == 128) {
 #pragma unroll
-                        for (int t = 0; t < 3; ++t)
-                            umma_tf32(tmem_base + t * C, umma_desc_mn_sw128(st + (1 + t) * Cfg::CB * Cfg::BOX_BYTES + koff, Cfg::BOX_BYTES),
-                                      bdesc, Cfg::IDESC, acc);
-                    } else {
-                        // rows 0-63 = tap 0, rows 64-127 = tap 1 (adjacent boxes)
-                        umma_tf32(tmem_base, umma_desc_mn_sw128(st + 1 * Cfg::CB * Cfg::BOX_BYTES + koff, Cfg::BOX_BYTES), bdesc,
-                                  Cfg::IDESC, acc);
-                        // rows 0-63 = tap 2, rows 64-127 = whatever follows (discarded)
-                        umma_tf32(tmem_base + C, umma_desc_mn_sw128(st + 3 * Cfg::CB * Cfg::BOX_BYTES + koff, Cfg::BOX_BYTES), bdesc,
-                                  Cfg::IDESC, acc);
+                    for (int t = 0; t < 3; ++t) {
+                        const uint64_t adesc = umma_desc_mn_sw128(st + (1 + t) * Cfg::CB * Cfg::BOX_BYTES + koff, Cfg::BOX_BYTES);
+                        if (leader) umma_tf32(tmem_base + t * C, adesc, bdesc, Cfg::IDESC, acc);
+                    }
+                } else {
+                    // rows 0-63 = tap 0, rows 64-127 = tap 1 (adjacent boxes)
+                    const uint64_t ad01 = umma_desc_mn_sw128(st + 1 * Cfg::CB * Cfg::BOX_BYTES + koff, Cfg::BOX_BYTES);
+                    // rows 0-63 = tap 2, rows 64-127 = whatever follows (discarded)
+                    const uint64_t ad2 = umma_desc_mn_sw128(st + 3 * Cfg::CB * Cfg::BOX_BYTES + koff, Cfg::BOX_BYTES);
+                    if (leader) {
+                        umma_tf32(tmem_base, ad01, bdesc, Cfg::IDESC, acc);
+                        umma_tf32(tmem_base + C, ad2, bdesc, Cfg::IDESC, acc);
                     }
                 }
-                first = false;
-                umma_commit(&empty[stage]);
-                if (++stage == Cfg::STAGES) {
-                    stage = 0;
-                    phase ^= 1;
-                }
             }
-            umma_commit(done);
+            first = false;
+            if (leader) umma_commit(&empty[stage]);
+            if (++stage == Cfg::STAGES) {
+                stage = 0;
+                phase ^= 1;
+            }
         }
+        if (leader) umma_commit(done);
     } else {
         // epilogue: TMEM lane = GEMM row
         const int lane_base = (warp & 3) * 32;

@@ -63,6 +63,31 @@ class GraphedTrainStep:
         self.xgt.copy_(xgt, non_blocking=True)
         self.valid.copy_(valid, non_blocking=True)
 
+    # -- double-buffered input pipeline: the H2D copy of batch i+1 runs on a copy stream while step i computes
+    def prefetch(self, x, xgt, valid):
+        """Start copying the NEXT batch (pinned host tensors) into the staging buffers on the copy stream."""
+        if not hasattr(self, "_copy_stream"):
+            dev = self.x.device
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [torch.empty_like(self.x), torch.empty_like(self.xgt), torch.empty_like(self.valid)]
+            self._ready = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(dev))
+        self._copy_stream.wait_event(self._consumed)     # staging buffers were drained by swap_in()
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._stage, (x, xgt, valid)):
+                dst.copy_(src, non_blocking=True)
+            self._ready.record(self._copy_stream)
+
+    def swap_in(self):
+        """Move the prefetched batch into the graph's static inputs (device-to-device, on the compute stream)."""
+        cur = torch.cuda.current_stream(self.x.device)
+        cur.wait_event(self._ready)
+        self.x.copy_(self._stage[0], non_blocking=True)
+        self.xgt.copy_(self._stage[1], non_blocking=True)
+        self.valid.copy_(self._stage[2], non_blocking=True)
+        self._consumed.record(cur)
+
     def __call__(self):
         self.graph.replay()
         return self.loss

@@ -17,8 +17,14 @@ __device__ __forceinline__ void umma_f16(uint32_t d, uint64_t a, uint64_t b, uin
                  : "memory");
 }
 
-// kind: 0 = tf32, 1 = bf16
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int kind, int N, int nacc, int reps, long long* out) {
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+                 "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+
+// kind: 0 = tf32, 1 = bf16, 2 = tf32 with A in tensor memory (TS); M: 128 or 64
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int kind, int M, int N, int nacc, int reps, long long* out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
@@ -33,9 +39,11 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int kind, int N, int n
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = tmem_slot;
-    if (threadIdx.x == 0) {
-        const uint32_t fmt = kind == 0 ? 2u : 1u;  // TF32 : BF16
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    if (threadIdx.x < 32) {  // converged warp, elected lane issues (operands stay in uniform registers)
+        const bool leader = elect_one();
+        const uint32_t fmt = kind == 1 ? 1u : 2u;  // BF16 : TF32
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | (((uint32_t)M >> 4) << 24);
+        const uint32_t a_tm = tm + 256;            // TS mode: A lives in columns 256.. (accumulators stay below 256)
         const uint64_t a = desc_sw128(smem_u32(smem)), b = desc_sw128(smem_u32(smem + 16 * 1024));
         // fully unrolled groups of 8 (no per-MMA integer work): accumulator = (j % nacc) * N precomputed
         uint32_t dsel[8];
@@ -44,16 +52,19 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int kind, int N, int n
         for (int r = 0; r < reps; r += 8) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
+                if (!leader) continue;
                 if (kind == 0)
                     umma_tf32(dsel[j], a + 2 * (j & 3), b + 2 * (j & 3), idesc, 1u);
+                else if (kind == 2)
+                    umma_tf32_ts(dsel[j], a_tm + 8 * (j & 3), b + 2 * (j & 3), idesc, 1u);
                 else
                     umma_f16(dsel[j], a + 2 * (j & 3), b + 2 * (j & 3), idesc, 1u);
             }
         }
-        umma_commit(&bar);
+        if (leader) umma_commit(&bar);
         mbar_wait(&bar, 0);
         const long long t1 = clock64();
-        if (blockIdx.x == 0) out[0] = t1 - t0;
+        if (leader && blockIdx.x == 0) out[0] = t1 - t0;
     }
     tc_fence_before();
     __syncthreads();
@@ -72,11 +83,13 @@ int main() {
     cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
     printf("device clock attr %d kHz\n", clk_khz);
     for (int grid : {1, 148}) {
-        for (int kind = 0; kind < 2; ++kind)
+        for (int kind = 0; kind < 3; ++kind)
+          for (int M : {128, 64})
             for (int N : {64, 128, 256})
                 for (int nacc : {1, 2, 4}) {
-                    if (nacc * N > 512) continue;
-                    mma_rate_kernel<<<grid, 128, 64 * 1024>>>(kind, N, nacc, reps, d_out);
+                    if (nacc * N > (kind == 2 ? 256 : 512)) continue;
+                    if (M == 64 && nacc != 2) continue;
+                    mma_rate_kernel<<<grid, 128, 64 * 1024>>>(kind, M, N, nacc, reps, d_out);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) {
                         printf("error %s\n", cudaGetErrorString(e));
@@ -85,10 +98,10 @@ int main() {
                     long long cyc;
                     cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
                     const double per = (double)cyc / reps;
-                    const int K = kind == 0 ? 8 : 16;
-                    printf("{\"grid\": %d, \"kind\": \"%s\", \"M\": 128, \"N\": %d, \"K\": %d, \"accumulators\": %d, \"cycles_per_mma\": %.1f, "
+                    const int K = kind == 1 ? 16 : 8;
+                    printf("{\"grid\": %d, \"kind\": \"%s\", \"M\": %d, \"N\": %d, \"K\": %d, \"accumulators\": %d, \"cycles_per_mma\": %.1f, "
                            "\"mac_per_cycle_per_sm\": %.0f}\n",
-                           grid, kind == 0 ? "tf32" : "bf16", N, K, nacc, per, 128.0 * N * K / per);
+                           grid, kind == 0 ? "tf32" : kind == 1 ? "bf16" : "tf32_ts", M, N, K, nacc, per, (double)M * N * K / per);
                 }
     }
     return 0;
