@@ -255,6 +255,18 @@ int lf_outconv_bwd_weight(const float* x, const float* d_out, int N, int H, int 
 
 /* NCHW fp32 image [N,C,H,W] -> NHWC padded to Cpad channels (zeros), the stem's input layout */
 int lf_nchw_to_nhwc_pad(const float* in, int N, int C, int H, int W, int Cpad, float* out, lf_stream_t stream);
+/* Batched weight packing (host side: ops_net.WeightPackCache).  The reference keeps Conv2d / ConvTranspose2d
+ * weights as [Co,Ci,kh,kw] (Networks/ERFNet.py:18-55 builds them with nn.Conv2d); every kernel above wants a
+ * GEMM layout.  Each job gathers dst[k] = idx[k] >= 0 ? src[idx[k]] : 0 for k < n; one launch runs all jobs.
+ * jobs_dev: DEVICE array of njobs records. */
+typedef struct LfPackJob {
+    const float* src;   /* parameter in the reference layout (device) */
+    float* dst;         /* packed operand (device) */
+    const int* idx;     /* n gather indices into src, -1 = zero (device) */
+    long long n;
+} LfPackJob;
+int lf_pack_gather(const LfPackJob* jobs_dev, int njobs, int blocks_per_job, lf_stream_t stream);
+
 /* NHWC [N,H,W,C] <-> NCHW [N,C,H,W] (module-boundary layout changes) */
 int lf_nhwc_to_nchw(const float* in, int N, int H, int W, int C, float* out, lf_stream_t stream);
 int lf_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out, lf_stream_t stream);

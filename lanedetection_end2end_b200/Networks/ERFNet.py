@@ -194,6 +194,13 @@ class Net(nn.Module):
         if only_encode:
             return self.encoder.forward(input, predict=True)
         _PENDING_COUNTERS = []
+        if input.is_cuda:
+            # one launch re-packs every layer's GEMM-layout weight operand from the current parameters
+            packs = self.__dict__.get("_weight_packs")
+            if packs is None:
+                packs = self.__dict__["_weight_packs"] = _ops.WeightPackCache(self)
+            packs.refresh()
+            _ops.ACTIVE_PACKS = packs
         try:
             encoder_output = self.encoder(input)
             decoder_output, output_seg = self.decoder.forward(encoder_output, flag)

@@ -101,6 +101,7 @@ _NET_PROTOS = {
     "lf_nchw_to_nhwc_pad": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "lf_nhwc_to_nchw": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "lf_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "lf_pack_gather": (_i, [_p, _i, _i, _p]),
 }
 PROTOTYPES.update(_NET_PROTOS)
 

@@ -211,6 +211,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else {
         // ================= epilogue (warps 2..) =================
         constexpr int NH = Cfg::HALVES;
+        constexpr bool PRE_BOTH = (NH == 1);
         const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may access
         const int m = lane_base + lane;         // phase 1: this thread's pixel row of the tile
         const int grp = (threadIdx.x - 64) >> 7;  // epilogue group (0 when there is only one)
@@ -246,6 +247,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // Prefetch the ReLU mask (or the gated residual gradient) of this tile while the MMAs are still
             // running: the loads' latency hides behind the wait for the accumulator.
             float4 pre[NH][8];
+            float4 pre2[PRE_BOTH ? 8 : 1];
             if (pre_mask || pre_add) {
 #pragma unroll
                 for (int hh = 0; hh < NH; ++hh)
@@ -263,6 +265,20 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             pre[hh][j] = ad;
                         }
                     }
+                if (PRE_BOTH && pre_mask && a.add_src) {
+                    // mask AND gated residual (the block's first dgrad): with one half per thread there are
+                    // registers to prefetch the second operand as well
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + roff[j]));
+                        if (a.add_mask) {
+                            const float4 mk = __ldg(reinterpret_cast<const float4*>(a.add_mask + roff[j]));
+                            ad.x = mk.x > 0.f ? ad.x : 0.f; ad.y = mk.y > 0.f ? ad.y : 0.f;
+                            ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
+                        }
+                        pre2[j] = ad;
+                    }
+                }
             }
             mbar_wait(&tfull[buf], use_parity);
             tc_fence_after();
@@ -311,6 +327,8 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     if (pre_add) {
                         o.x += pre[hh][j].x; o.y += pre[hh][j].y; o.z += pre[hh][j].z; o.w += pre[hh][j].w;
+                    } else if (PRE_BOTH && a.add_src) {
+                        o.x += pre2[j].x; o.y += pre2[j].y; o.z += pre2[j].z; o.w += pre2[j].w;
                     } else if (a.add_src) {
                         float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + off));
                         if (a.add_mask) {

@@ -570,6 +570,35 @@ extern "C" int lf_outconv_bwd_weight(const float* x, const float* d_out, int N, 
     return check_launch();
 }
 
+// ------------------------------------------------------------------------------------------
+// Batched weight packing: every layer's GEMM-layout weight operand (forward, input-gradient, super-pixel ...)
+// is a gather of the reference-layout parameter (index -1 = structural zero).  One launch per training step
+// serves all ~130 operands (blockIdx.y = job) instead of ~250 small permute / copy / fill launches.
+// ------------------------------------------------------------------------------------------
+struct PackJob {
+    const float* src;
+    float* dst;
+    const int* idx;
+    long long n;
+};
+static_assert(sizeof(PackJob) == 32, "LfPackJob layout");
+
+__global__ void __launch_bounds__(256) pack_gather_kernel(const PackJob* __restrict__ jobs) {
+    const PackJob j = jobs[blockIdx.y];
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < j.n; k += (long long)gridDim.x * blockDim.x) {
+        const int i = __ldg(j.idx + k);
+        j.dst[k] = i >= 0 ? __ldg(j.src + i) : 0.f;
+    }
+}
+
+extern "C" int lf_pack_gather(const LfPackJob* jobs_dev, int njobs, int blocks_per_job, lf_stream_t stream_) {
+    STREAM;
+    LF_REQUIRE(jobs_dev && njobs > 0 && njobs <= 65535 && blocks_per_job > 0);
+    dim3 grid(blocks_per_job, njobs);
+    pack_gather_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const PackJob*>(jobs_dev));
+    return check_launch();
+}
+
 extern "C" int lf_nchw_to_nhwc_pad(const float* in, int N, int C, int H, int W, int Cpad, float* out, lf_stream_t stream_) {
     STREAM;
     LF_REQUIRE(in && out && N > 0 && C > 0 && Cpad >= C);

@@ -87,6 +87,94 @@ def pack_convT_dgrad(w):
 
 
 # --------------------------------------------------------------------------------------
+# one-launch weight packing
+# --------------------------------------------------------------------------------------
+def pack_gather_table(fn, shape):
+    """int32 gather indices t with fn(w).flatten()[k] == (w.flatten()[t[k]] if t[k] >= 0 else 0), shaped like
+    fn(w): obtained by running the packer on 1-based element numbers (0 = structural zero)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    numbered = torch.arange(1, n + 1, dtype=torch.float64).view(tuple(shape))
+    return (fn(numbered).to(torch.int64) - 1).to(torch.int32).contiguous()
+
+
+class WeightPackCache:
+    """All GEMM-layout weight operands of a model, refreshed by ONE kernel per step (lf_pack_gather).
+
+    Every packer above is pure data movement, so its gather table is obtained by running the packer on an
+    index tensor once.  ``refresh()`` (called at the top of ERFNet.forward) re-packs every registered
+    operand from the current parameter values; ``get()`` hands the packed tensor to conv3()/wgrad3()/... if it
+    is current (same parameter object still at that address, same in-place version as at the last refresh),
+    else returns None and the caller packs directly (first use, eval of a foreign tensor, ...).
+    Operands are registered lazily on their first miss and served from the next refresh on."""
+
+    BLOCKS_PER_JOB = 12
+
+    def __init__(self, module):
+        self.module = module
+        self.by_ptr = {}
+        self.entries = {}        # (data_ptr, kind) -> [param, idx(int32 dev), out(dev), version_at_refresh]
+        self.jobs = None
+        self.dirty = False
+
+    def _scan(self):
+        self.by_ptr = {p.data_ptr(): p for p in self.module.parameters() if p.is_cuda}
+
+    def get(self, w, kind, fn):
+        if not w.is_cuda:
+            return None
+        p = self.by_ptr.get(w.data_ptr())
+        if p is None or p.shape != w.shape:
+            return None
+        key = (w.data_ptr(), kind)
+        e = self.entries.get(key)
+        if e is None:
+            if torch.cuda.is_current_stream_capturing():
+                return None
+            idx = pack_gather_table(fn, p.shape)
+            self.entries[key] = [p, idx.to(w.device), torch.empty(idx.shape, dtype=torch.float32, device=w.device), -1]
+            self.dirty = True
+            return None
+        if e[3] != p._version or e[0] is not p:
+            return None
+        return e[2]
+
+    def refresh(self):
+        self._scan()
+        dead = [k for k, e in self.entries.items() if self.by_ptr.get(k[0]) is not e[0]]
+        for k in dead:
+            del self.entries[k]
+            self.dirty = True
+        if not self.entries:
+            return
+        if self.dirty:
+            if torch.cuda.is_current_stream_capturing():
+                return                      # keep serving the operands that are already in the table
+            rows = [[e[0].data_ptr(), e[2].data_ptr(), e[1].data_ptr(), e[1].numel()] for e in self.entries.values()]
+            dev = next(iter(self.entries.values()))[2].device
+            self.jobs = torch.tensor(rows, dtype=torch.int64).to(dev)
+            self.job_entries = list(self.entries.values())
+            self.dirty = False
+        _capi.call("lf_pack_gather", ptr(self.jobs), len(self.job_entries), self.BLOCKS_PER_JOB, _stream())
+        for e in self.job_entries:
+            e[3] = e[0]._version
+
+
+ACTIVE_PACKS = None
+
+
+def packed(w, kind, fn):
+    """The packed operand ``fn(w)``: from the active WeightPackCache when current, else computed now."""
+    c = ACTIVE_PACKS
+    if c is not None:
+        t = c.get(w, kind, fn)
+        if t is not None:
+            return t
+    return fn(w)
+
+
+# --------------------------------------------------------------------------------------
 # launch helpers
 # --------------------------------------------------------------------------------------
 
@@ -261,7 +349,7 @@ def conv3(x, w, vertical, dil, transposed, colsum=None, **epi):
         if epi_s.get("bias") is not None:
             epi_s["bias"] = epi_s["bias"].repeat(SUPER)
         cs = torch.empty(SUPER * C, dtype=torch.float32, device=x.device) if colsum is not None else None
-        run_conv_tc(taps, xs, pack_tc_super(w, vertical, transposed), out.view(N, H, W // SUPER, SUPER * C), colsum=cs,
+        run_conv_tc(taps, xs, packed(w, "tc_super_%d%d" % (vertical, transposed), lambda t: pack_tc_super(t, vertical, transposed)), out.view(N, H, W // SUPER, SUPER * C), colsum=cs,
                     **epi_s)
         if colsum is not None:
             colsum.copy_(cs.view(SUPER, C).sum(0))
@@ -269,17 +357,17 @@ def conv3(x, w, vertical, dil, transposed, colsum=None, **epi):
     if CONV_MODE == "tf32" and C in (64, 128) and tc_supported(x):
         sgn = -1 if transposed else 1
         taps = [((sgn * (k - 1) * dil, 0) if vertical else (0, sgn * (k - 1) * dil)) for k in range(3)]
-        wp = pack_tc_dgrad(w) if transposed else pack_tc_fwd(w)
+        wp = packed(w, "tc_dgrad", pack_tc_dgrad) if transposed else packed(w, "tc_fwd", pack_tc_fwd)
         return run_conv_tc(taps, x, wp, out, colsum=colsum, **epi)
     kh, kw = (3, 1) if vertical else (1, 3)
     ph, pw = (dil, 0) if vertical else (0, dil)
     dh, dw = (dil, 1) if vertical else (1, dil)
     if transposed:
         phases, _ = plans.conv_dgrad_plan_s1(H, W, kh, kw, ph, pw, dh, dw)
-        run_conv(phases, x, pack_conv_dgrad(w), C, out, C, **epi)
+        run_conv(phases, x, packed(w, "conv_dgrad", pack_conv_dgrad), C, out, C, **epi)
     else:
         phases, _ = plans.conv_fwd_plan(H, W, kh, kw, 1, ph, pw, dh, dw)
-        run_conv(phases, x, pack_conv_fwd(w), C, out, C, **epi)
+        run_conv(phases, x, packed(w, "conv_fwd", pack_conv_fwd), C, out, C, **epi)
     if colsum is not None:
         run_colsum(out, C, 0, colsum)
     return out
@@ -429,7 +517,7 @@ def conv3_bn_stats(x, w, vertical, dil, bias, gamma, beta, running_mean, running
         rows = tc_rows(x)
         part = torch.empty(rows * 2 * C, dtype=torch.float64, device=x.device)
         taps = [(((k - 1) * dil, 0) if vertical else (0, (k - 1) * dil)) for k in range(3)]
-        out = run_conv_tc(taps, x, pack_tc_fwd(w), torch.empty_like(x), bias=bias, stats_partial=part)
+        out = run_conv_tc(taps, x, packed(w, "tc_fwd", pack_tc_fwd), torch.empty_like(x), bias=bias, stats_partial=part)
         return out, bn_finalize(part, rows, N * H * W, C, gamma, beta, running_mean, running_var)
     out = conv3(x, w, vertical, dil, False, bias=bias)
     return out, bn_forward_stats(out, gamma, beta, running_mean, running_var, training)
@@ -485,7 +573,7 @@ class DownFunction(torch.autograd.Function):
         cc = w.shape[0]                      # conv output channels = noutput - ninput
         cout = cc + cin
         cin_gemm = plans.pad_to(cin, 4)
-        wmat = pack_conv_fwd(w, cin_gemm)
+        wmat = packed(w, "conv_fwd_%d" % cin_gemm, lambda t: pack_conv_fwd(t, cin_gemm))
         phases, (Ho, Wo) = plans.conv_fwd_plan(H, W, 3, 3, 2, 1, 1, 1, 1)
         cat = _empty((N, Ho, Wo, cout), x)
         run_conv(phases, x, wmat, cin_gemm, cat, cc, 0, bias=b)
@@ -519,7 +607,7 @@ class DownFunction(torch.autograd.Function):
         dx = None
         if need_dx:
             dx = _empty((N, H, W, cx), x)
-            wd = pack_conv_dgrad(w)                      # [9, cc, cinPad]
+            wd = packed(w, "conv_dgrad", pack_conv_dgrad)   # [9, cc, cinPad]
             phases, _ = plans.transposed_gather_plan(dcat.shape[1], dcat.shape[2], H, W, 3, 1)
             run_conv(phases, dcat, wd, cc, dx, cin, 0)
             _capi.call("lf_maxpool2_bwd", ptr(x), N, H, W, cin, cx, ptr(dcat), cout, cc, ptr(dx), cx, 1, _stream())
@@ -592,7 +680,7 @@ class UpFunction(torch.autograd.Function):
         N, H, W, ci = x.shape
         co = w.shape[1]
         phases, (Ho, Wo) = plans.transposed_gather_plan(H, W, 2 * H, 2 * W, 3, 1)
-        u = run_conv(phases, x, pack_convT_fwd(w), ci, _empty((N, Ho, Wo, co), x), co, bias=b)
+        u = run_conv(phases, x, packed(w, "convT_fwd", pack_convT_fwd), ci, _empty((N, Ho, Wo, co), x), co, bias=b)
         s = bn_forward_stats(u, gamma, beta, rm, rv, training)
         y = bn_apply(u, s, relu=True)
         ctx.save_for_backward(x, w, u, y, gamma, s.mean, s.invstd)
@@ -613,7 +701,7 @@ class UpFunction(torch.autograd.Function):
         run_wgrad(plans.convT_wgrad_plan(H, W, 3, 1), x, ci, du, co, 0, N, dw, (1, co * 9, 9))
         run_colsum(du, co, 0, db)
         pd, _ = plans.convT_dgrad_plan(2 * H, 2 * W, H, W, 3, 1)
-        dx = run_conv(pd, du, pack_convT_dgrad(w), co, torch.empty_like(x), ci)
+        dx = run_conv(pd, du, packed(w, "convT_dgrad", pack_convT_dgrad), co, torch.empty_like(x), ci)
         return dx, dw, db, dgamma, dbeta, None, None, None
 
 

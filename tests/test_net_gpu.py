@@ -356,3 +356,75 @@ def test_full_path_tf32_mode_accuracy(name):
     # decoder outputs of this random-weight, batch-2 network move by up to 17 % of the max (ReLU/BN chaos),
     # which the weighted fit averages out
     assert rec["beta_normwise_err_tf32"] < 2e-2 and rec["loss_rel_err_tf32"] < 2e-2, rec
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_weight_pack_cache_serves_current_weights(mode):
+    """WeightPackCache: from the second Net.forward on every GEMM-layout weight operand comes from ONE
+    lf_pack_gather launch.  Step 2 (served from the cache) must reproduce step 1 (packed directly) bit for bit,
+    an in-place weight update must be picked up by the next refresh, and a direct block call after an update
+    (no refresh in between) must not see stale operands."""
+    from lanedetection_end2end_b200 import ops_net as o, _capi
+    prev = o.CONV_MODE
+    o.set_conv_mode(mode)
+    try:
+        L, B = 2, 2
+        model, args = _build_net(L, 2, 0.3, B)
+        torch.manual_seed(3)
+        model = model.cuda().train()
+        for m in model.modules():
+            if hasattr(m, "dropout"):
+                m.dropout.p = 0
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.momentum = 0.0               # identical BN state in every step
+        x = torch.from_numpy(inputs.make_images(B, 256, 512, seed=11)).cuda()
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            out = model(x, torch.zeros(B, 4), True)
+            betas = [b for b in out[:4] if b is not None]
+            loss = sum((b ** 2).sum() for b in betas)
+            loss.backward()
+            torch.cuda.synchronize()
+            return torch.cat([b.flatten() for b in betas]).clone(), {n: p.grad.clone() for n, p in model.named_parameters()
+                                                                    if p.grad is not None}
+
+        b1, g1 = step()                         # every operand missed -> packed directly, registered
+        packs = model.net.__dict__["_weight_packs"]
+        assert len(packs.entries) > 100 and packs.dirty
+        _capi.TRACE = []
+        b2, g2 = step()                         # refresh: one launch, then every lookup hits
+        names = [t[0] for t in _capi.TRACE]
+        _capi.TRACE = None
+        assert names.count("lf_pack_gather") == 1
+        assert all(e[3] == e[0]._version for e in packs.entries.values())
+        assert torch.equal(b1, b2)
+        for n in g1:
+            assert torch.equal(g1[n], g2[n]), n
+        # in-place update of every weight: the next step must use the new values
+        with torch.no_grad():
+            for p in model.parameters():
+                p.mul_(1.01)
+        w = model.net.encoder.layers[1].conv3x1_1.weight
+        e = packs.entries[(w.data_ptr(), "tc_fwd" if mode == "tf32" else "conv_fwd")]
+        assert e[3] != w._version               # stale until the next refresh ...
+        assert packs.get(w, "tc_fwd" if mode == "tf32" else "conv_fwd", o.pack_tc_fwd) is None   # ... and not served
+        b3, g3 = step()
+        ref_pack = o.pack_tc_fwd(w) if mode == "tf32" else o.pack_conv_fwd(w)
+        assert torch.equal(e[2], ref_pack)
+        assert not torch.equal(b3, b2)
+        # fresh model with the same updated weights, direct packing (first step) -> same numbers
+        model2, _ = _build_net(L, 2, 0.3, B)
+        model2.load_state_dict(model.state_dict())
+        model2 = model2.cuda().train()
+        for m in model2.modules():
+            if hasattr(m, "dropout"):
+                m.dropout.p = 0
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.momentum = 0.0
+        out = model2(x, torch.zeros(B, 4), True)
+        b4 = torch.cat([b.flatten() for b in out[:4] if b is not None])
+        assert torch.equal(b3, b4.detach())
+    finally:
+        o.set_conv_mode(prev)
+        o.ACTIVE_PACKS = None

@@ -197,3 +197,29 @@ def test_super_pixel_packing_of_16_channel_convs(vertical, transposed):
         (gws,) = torch.autograd.grad(ysup, wsup, nhwc(gy).reshape(N, H, W // 4, 64).permute(0, 3, 1, 2))
         got = ops.unpack_wgrad_super(gws.reshape(64, 64, 3), vertical).reshape(C, C, kh, kw)
         torch.testing.assert_close(got, gw)
+
+
+def test_weight_pack_gather_tables_reproduce_every_packer():
+    """ops_net.WeightPackCache packs all operands with one gather kernel; its index tables are derived by running
+    each packer on element numbers.  Check table-gather == packer on random weights for every packer / layer shape."""
+    from lanedetection_end2end_b200 import ops_net as o
+    g = torch.Generator().manual_seed(5)
+    cases = [
+        (o.pack_tc_fwd, (64, 64, 3, 1)), (o.pack_tc_fwd, (128, 128, 1, 3)), (o.pack_tc_dgrad, (64, 64, 1, 3)),
+        (o.pack_tc_dgrad, (128, 128, 3, 1)),
+        (o.pack_conv_fwd, (16, 16, 3, 1)), (o.pack_conv_dgrad, (16, 16, 1, 3)), (o.pack_conv_fwd, (48, 16, 3, 3)),
+        (lambda t: o.pack_conv_fwd(t, 4), (13, 3, 3, 3)), (o.pack_conv_dgrad, (64, 64, 3, 3)),
+        (o.pack_convT_fwd, (128, 64, 3, 3)), (o.pack_convT_dgrad, (64, 16, 3, 3)),
+    ]
+    for vertical in (True, False):
+        for transposed in (True, False):
+            cases.append((lambda t, v=vertical, tr=transposed: o.pack_tc_super(t, v, tr),
+                          (16, 16, 3, 1) if vertical else (16, 16, 1, 3)))
+    for fn, shape in cases:
+        w = torch.randn(*shape, generator=g)
+        idx = o.pack_gather_table(fn, shape)
+        ref = fn(w)
+        assert idx.shape == ref.shape
+        src = torch.cat([w.reshape(-1), w.new_zeros(1)])
+        got = src[idx.to(torch.int64).clamp(min=-1)]          # -1 wraps to the appended zero
+        assert torch.equal(got, ref), (fn, shape)
