@@ -255,6 +255,34 @@ int lf_outconv_bwd_weight(const float* x, const float* d_out, int N, int H, int 
 
 /* NCHW fp32 image [N,C,H,W] -> NHWC padded to Cpad channels (zeros), the stem's input layout */
 int lf_nchw_to_nhwc_pad(const float* in, int N, int C, int H, int W, int Cpad, float* out, lf_stream_t stream);
+/* tcgen05 gather-GEMM convolution for the resolution-changing layers (csrc/conv_tcg.cu): the 3x3 stride-2
+ * Conv2d of DownsamplerBlock (BP/Networks/ERFNet.py:15,19-22), the 3x3 stride-2 ConvTranspose2d of UpsamplerBlock
+ * (:66-73) and their input gradients, TF32 multiply / fp32 accumulate:
+ *   out[n*osn + (oy*oy_mul + oy0)*osy + ox*osx + c] =
+ *       bias[c] + sum_{t<ntaps} sum_{k<Kc} A_{map[t]}(n, oy+dy[t], ox+dx[t], k) * wg[c*ntaps*Kc + t*Kc + k]
+ * for (n, oy, ox) in [N]x[Hs]x[Ws], c < Ng; A_i(n,y,x,k) = a[i].ptr[n*sn + y*sy + x*sx + k], zero outside
+ * [0,H)x[0,W).  Kc: multiple of 32 (<= 256); Ng: multiple of 16 (<= 128); all strides multiples of 4 elements.
+ * ops_net.py (tcg_* packers) maps the four layer forms onto this through pair-pixel / row-parity views. */
+#define LF_TCG_MAX_TAPS 6
+typedef struct LfTcgView {
+    const float* ptr;
+    int H, W;
+    long long sn, sy, sx;   /* element strides of image, row, pixel */
+} LfTcgView;
+typedef struct LfConvTcgArgs {
+    LfTcgView a[2];
+    const float* wg;        /* [Ng][ntaps*Kc] */
+    const float* bias;      /* [Ng] or NULL */
+    float* out;
+    long long osn, osy, osx;
+    int oy_mul, oy0;
+    int N, Hs, Ws;
+    int Kc, Ng, ntaps;
+    int map[LF_TCG_MAX_TAPS], dy[LF_TCG_MAX_TAPS], dx[LF_TCG_MAX_TAPS];
+} LfConvTcgArgs;
+int lf_conv_tcg_supported(int N, int Hs, int Ws, int Kc, int Ng);
+int lf_conv_tcg(const LfConvTcgArgs* args, lf_stream_t stream);
+
 /* Batched weight packing (host side: ops_net.WeightPackCache).  The reference keeps Conv2d / ConvTranspose2d
  * weights as [Co,Ci,kh,kw] (Networks/ERFNet.py:18-55 builds them with nn.Conv2d); every kernel above wants a
  * GEMM layout.  Each job gathers dst[k] = idx[k] >= 0 ? src[idx[k]] : 0 for k < n; one launch runs all jobs.

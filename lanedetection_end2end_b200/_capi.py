@@ -69,7 +69,23 @@ class LfWgradArgs(ctypes.Structure):
                 ("CpPad", _i), ("CqPad", _i), ("nsplit", _i)]
 
 
+TCG_MAX_TAPS = 6
+_ll = ctypes.c_longlong
+
+
+class LfTcgView(ctypes.Structure):
+    _fields_ = [("ptr", _p), ("H", _i), ("W", _i), ("sn", _ll), ("sy", _ll), ("sx", _ll)]
+
+
+class LfConvTcgArgs(ctypes.Structure):
+    _fields_ = [("a", LfTcgView * 2), ("wg", _p), ("bias", _p), ("out", _p), ("osn", _ll), ("osy", _ll), ("osx", _ll),
+                ("oy_mul", _i), ("oy0", _i), ("N", _i), ("Hs", _i), ("Ws", _i), ("Kc", _i), ("Ng", _i), ("ntaps", _i),
+                ("map", _i * TCG_MAX_TAPS), ("dy", _i * TCG_MAX_TAPS), ("dx", _i * TCG_MAX_TAPS)]
+
+
 _NET_PROTOS = {
+    "lf_conv_tcg_supported": (_i, [_i, _i, _i, _i, _i]),
+    "lf_conv_tcg": (_i, [ctypes.POINTER(LfConvTcgArgs), _p]),
     "lf_conv_f32": (_i, [ctypes.POINTER(LfConvArgs), _p]),
     "lf_wgrad_f32": (_i, [ctypes.POINTER(LfWgradArgs), _p]),
     "lf_conv1d_tc": (_i, [ctypes.POINTER(LfConvTcArgs), _p]),

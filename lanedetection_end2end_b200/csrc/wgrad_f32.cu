@@ -179,6 +179,229 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const WgradArgs a
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Small-channel weight gradient (stem 3->13, 16->48 downsampler, 64->16 upsampler): all taps in one CTA.
+// Per pixel m the gradient is an outer product U^T V with
+//   taps on P (Conv2d):          U = concat_t P[m*s + tap_t] (ntaps*Cp values),  V = Q[m] (Cq values)
+//   taps on Q (ConvTranspose2d): U = P[m] (Cp values),  V = concat_t Q[m*s + tap_t] (ntaps*Cq values).
+// A thread owns a 4 (U) x 16 (V) register tile: 5 shared-memory loads per 64 FMAs, no zero padding of the
+// channel dimensions to 64, and Q / P are staged once for all taps.  (LU/4)*(LV/16) threads cover one
+// pixel; the CTA runs G such pixel groups side by side and sums them in fixed order at the end.
+// The generic tile kernel above spent 316-443 us per launch on these layers; this one is FMA/HBM-bound.
+// ------------------------------------------------------------------------------------------
+struct WsPlan {
+    int LU, LV, TPG, G, PXG, PXS, threads, taps_on_p, smem_bytes, nslot;
+};
+constexpr int WS_MAXSLOT = 8;
+
+static bool ws_make_plan(const WgradArgs& a, WsPlan* p) {
+    bool p_same = true, q_same = true;
+    for (int t = 1; t < a.ntaps; ++t) {
+        p_same = p_same && a.pdy[t] == a.pdy[0] && a.pdx[t] == a.pdx[0];
+        q_same = q_same && a.qdy[t] == a.qdy[0] && a.qdx[t] == a.qdx[0];
+    }
+    if (a.ntaps > 1 && p_same == q_same) return false;  // exactly one side may be gathered per tap
+    if (a.Cp > 16 && a.Cq > 16) return false;            // the 64x64 tile kernel serves the wide layers
+    p->taps_on_p = (a.ntaps == 1) || !p_same;
+    if (!p->taps_on_p && (a.qsum_partial || a.Cq % 16 != 0)) return false;
+    p->LU = p->taps_on_p ? a.ntaps * a.Cp : a.Cp;
+    p->LV = p->taps_on_p ? a.Cq : a.ntaps * a.Cq;
+    if (p->LU % 4 != 0 || p->LV % 16 != 0) return false;
+    p->TPG = (p->LU / 4) * (p->LV / 16);
+    if (p->TPG > 256 || p->TPG < 1) return false;
+    p->G = 256 / p->TPG;
+    p->threads = ((p->G * p->TPG + 31) / 32) * 32;
+    p->PXG = p->G >= 8 ? 4 : 16;
+    p->PXS = p->PXG * p->G;
+    const int tile_floats = 2 * p->PXS * (p->LU + p->LV);
+    if (p->G > 1 && p->LU * p->LV + p->LV > tile_floats) return false;  // group reduction reuses the tiles
+    p->smem_bytes = tile_floats * 4;
+    if (p->smem_bytes > 96 * 1024) return false;
+    const int total4 = p->PXS * (p->LU + p->LV) / 4;
+    p->nslot = (total4 + p->threads - 1) / p->threads;
+    return p->nslot <= WS_MAXSLOT;
+}
+
+__global__ void __launch_bounds__(256) wgrad_small_kernel(const WgradArgs a, const WsPlan pl) {
+    extern __shared__ __align__(16) float ws_smem[];
+    const int LU = pl.LU, LV = pl.LV, PXS = pl.PXS, G = pl.G;
+    float* sU = ws_smem;                  // [2][PXS][LU]
+    float* sV = ws_smem + 2 * PXS * LU;   // [2][PXS][LV]
+    const int tid = threadIdx.x;
+    const int split = blockIdx.x;
+    const int M = a.N * a.Hs * a.Ws;
+    int per = (M + a.nsplit - 1) / a.nsplit;
+    per = ((per + PXS - 1) / PXS) * PXS;
+    const int m_begin = min(M, split * per);
+    const int m_end = min(M, m_begin + per);
+    const int HW = a.Hs * a.Ws;
+
+    // ---- load slots: which float4 of the (pixel, U|V) tile this thread fetches; fixed for the whole kernel
+    const int nU4 = LU / 4, per_px4 = (LU + LV) / 4, total4 = PXS * per_px4;
+    int s_lp[WS_MAXSLOT], s_soff[WS_MAXSLOT], s_goff[WS_MAXSLOT], s_dy[WS_MAXSLOT], s_dx[WS_MAXSLOT];
+    unsigned s_valid = 0, s_isu = 0;
+#pragma unroll
+    for (int q = 0; q < WS_MAXSLOT; ++q) {
+        s_lp[q] = s_soff[q] = s_goff[q] = s_dy[q] = s_dx[q] = 0;
+        const int f = tid + q * pl.threads;
+        if (q < pl.nslot && f < total4) {
+            s_valid |= 1u << q;
+            const int lp = f / per_px4, e = f - lp * per_px4;
+            s_lp[q] = lp;
+            if (e < nU4) {
+                s_isu |= 1u << q;
+                const int u = 4 * e;
+                const int t = pl.taps_on_p ? u / a.Cp : 0;
+                s_goff[q] = a.p_coff + (pl.taps_on_p ? u - t * a.Cp : u);
+                s_dy[q] = a.pdy[t];
+                s_dx[q] = a.pdx[t];
+                s_soff[q] = lp * LU + u;
+            } else {
+                const int v = 4 * (e - nU4);
+                const int t = pl.taps_on_p ? 0 : v / a.Cq;
+                s_goff[q] = a.q_coff + (pl.taps_on_p ? v : v - t * a.Cq);
+                s_dy[q] = a.qdy[t];
+                s_dx[q] = a.qdx[t];
+                s_soff[q] = lp * LV + v;
+            }
+        }
+    }
+    float4 rr[WS_MAXSLOT];
+    auto load = [&](int m0) {
+#pragma unroll
+        for (int q = 0; q < WS_MAXSLOT; ++q) {
+            rr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!((s_valid >> q) & 1u)) continue;
+            const int m = m0 + s_lp[q];
+            if (m >= m_end) continue;
+            const int n = m / HW;
+            const int rem = m - n * HW;
+            const int j = rem / a.Ws, i = rem - j * a.Ws;
+            if ((s_isu >> q) & 1u) {
+                const int y = j * a.psy + s_dy[q], x = i * a.psx + s_dx[q];
+                if (y >= 0 && y < a.Hp && x >= 0 && x < a.Wp)
+                    rr[q] = __ldg(reinterpret_cast<const float4*>(a.P + ((size_t)(n * a.Hp + y) * a.Wp + x) * a.p_cstride + s_goff[q]));
+            } else {
+                const int y = j * a.qsy + s_dy[q], x = i * a.qsx + s_dx[q];
+                if (y >= 0 && y < a.Hq && x >= 0 && x < a.Wq)
+                    rr[q] = __ldg(reinterpret_cast<const float4*>(a.Q + ((size_t)(n * a.Hq + y) * a.Wq + x) * a.q_cstride + s_goff[q]));
+            }
+        }
+    };
+    auto store = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < WS_MAXSLOT; ++q) {
+            if (!((s_valid >> q) & 1u)) continue;
+            float* base = ((s_isu >> q) & 1u) ? sU + buf * PXS * LU : sV + buf * PXS * LV;
+            *reinterpret_cast<float4*>(base + s_soff[q]) = rr[q];
+        }
+    };
+
+    // ---- compute role
+    const bool active = tid < G * pl.TPG;
+    const int g = tid / pl.TPG, r = tid - g * pl.TPG;
+    const int nvg = LV / 16;
+    const int ug = r / nvg, vg = r - ug * nvg;
+    const bool do_qsum = active && a.qsum_partial != nullptr && ug == 0;
+    float acc[4][16];
+    float qs[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        qs[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][c] = 0.f;
+    }
+
+    if (m_begin < m_end) {
+        load(m_begin);
+        store(0);
+    }
+    __syncthreads();
+    int it = 0;
+    for (int m0 = m_begin; m0 < m_end; m0 += PXS, ++it) {
+        const int buf = it & 1;
+        const bool more = (m0 + PXS) < m_end;
+        if (more) load(m0 + PXS);
+        if (active) {
+            const float* bu = sU + buf * PXS * LU + 4 * ug;
+            const float* bv = sV + buf * PXS * LV + 16 * vg;
+#pragma unroll 4
+            for (int pp = 0; pp < pl.PXG; ++pp) {
+                const int p = pp * G + g;  // groups interleave the pixels of a step
+                const float4 u4 = *reinterpret_cast<const float4*>(bu + p * LU);
+                const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+                float vv[16];
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(bv + p * LV + 4 * c4);
+                    vv[4 * c4] = v4.x; vv[4 * c4 + 1] = v4.y; vv[4 * c4 + 2] = v4.z; vv[4 * c4 + 3] = v4.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) acc[i][c] = fmaf(uu[i], vv[c], acc[i][c]);
+                if (do_qsum) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) qs[c] += vv[c];
+                }
+            }
+        }
+        if (more) store(buf ^ 1);
+        __syncthreads();
+    }
+
+    // ---- write [t][cp][cq] partials (fixed-order sum over the G pixel groups through shared memory)
+    float* dst = a.partial + (size_t)split * a.ntaps * a.CpPad * a.CqPad;
+    auto out_index = [&](int u, int v) -> size_t {
+        int t, cp, cq;
+        if (pl.taps_on_p) {
+            t = u / a.Cp; cp = u - t * a.Cp; cq = v;
+        } else {
+            t = v / a.Cq; cq = v - t * a.Cq; cp = u;
+        }
+        return ((size_t)t * a.CpPad + cp) * a.CqPad + cq;
+    };
+    if (G == 1) {
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4)
+                    *reinterpret_cast<float4*>(dst + out_index(4 * ug + i, 16 * vg + 4 * c4)) =
+                        make_float4(acc[i][4 * c4], acc[i][4 * c4 + 1], acc[i][4 * c4 + 2], acc[i][4 * c4 + 3]);
+            if (do_qsum) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) a.qsum_partial[(size_t)split * a.CqPad + 16 * vg + c] = qs[c];
+            }
+        }
+        return;
+    }
+    float* red = ws_smem;         // [LU][LV] then [LV] for the bias sums
+    float* redq = ws_smem + LU * LV;
+    for (int gg = 0; gg < G; ++gg) {
+        if (active && g == gg) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float* e = red + (4 * ug + i) * LV + 16 * vg + c;
+                    *e = (gg == 0) ? acc[i][c] : *e + acc[i][c];
+                }
+            if (do_qsum) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float* e = redq + 16 * vg + c;
+                    *e = (gg == 0) ? qs[c] : *e + qs[c];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < LU * LV; e += blockDim.x) dst[out_index(e / LV, e % LV)] = red[e];
+    if (a.qsum_partial != nullptr)
+        for (int e = tid; e < LV; e += blockDim.x) a.qsum_partial[(size_t)split * a.CqPad + e] = redq[e];
+}
+
 // dst[t*st + cp*sp + cq*sq] = sum_k partial[k][t][cp][cq], fixed order.  One thread = 4 consecutive cq
 // (float4 loads) x one of 8 split lanes (k = lane, lane+8, ...); the 8 lanes are combined through
 // shared memory in lane order -> deterministic, 8x shorter dependent chains than one thread per output.
@@ -279,6 +502,13 @@ extern "C" int lf_wgrad_f32(const LfWgradArgs* args, lf_stream_t stream_) {
     LF_REQUIRE(a.p_coff % 4 == 0 && a.q_coff % 4 == 0);
     LF_REQUIRE(a.CpPad % WG_TILE == 0 && a.CqPad % WG_TILE == 0 && a.CpPad >= a.Cp && a.CqPad >= a.Cq);
     LF_REQUIRE((long long)a.N * a.Hs * a.Ws + 4096 < (1ll << 31));
+    WsPlan wsp;
+    if (ws_make_plan(a, &wsp)) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
+        wgrad_small_kernel<<<a.nsplit, wsp.threads, wsp.smem_bytes, stream>>>(a, wsp);
+        return check_launch();
+    }
     const bool smallP = a.Cp <= 16, smallQ = a.Cq <= 16;
     const int TP = smallP ? 16 : 64, TQ = smallQ ? 16 : 64;
     // small tiles only cover the first 16 channels of the 64-padded buffers: one tile in that dimension

@@ -87,6 +87,110 @@ def pack_convT_dgrad(w):
 
 
 # --------------------------------------------------------------------------------------
+# Resolution-changing layers on the tensor cores (csrc/conv_tcg.cu, tf32 mode).
+# Two horizontally adjacent pixels of an NHWC tensor form a "pair pixel" with 2C channels (a free view);
+# even / odd rows are two strided views.  In these coordinates
+#   * a 3x3 stride-2 convolution (Down forward; input gradient of the stride-2 transposed conv) is a 6-tap
+#     unit-stride gather: kernel row ky reads the odd-row view at i-1 (ky=0), the even-row view at i (ky=1),
+#     the odd-row view at i (ky=2); kernel column kx=0 is the second half of pair j-1, kx=1 / kx=2 the two
+#     halves of pair j;
+#   * a 3x3 stride-2 transposed convolution (Up forward; input gradient of the stride-2 conv) produces, per
+#     output-row parity a, the pair pixel (2j, 2j+1) of row 2i+a from inputs (i[+1], j[+1]).
+# --------------------------------------------------------------------------------------
+TCG_S2CONV_TAPS = [(1, -1, -1), (1, -1, 0), (0, 0, -1), (0, 0, 0), (1, 0, -1), (1, 0, 0)]   # (row view, dy, dx), t = 2*ky + dxi
+
+
+def pack_tcg_s2conv(w):
+    """[O, C, 3, 3] (Conv2d weight, or ConvTranspose2d weight read as [out=Cin_T][in=Cout_T]) ->
+    Wg [pad16(O)][6 * 2C], column = t*2C + b*C + c with t = 2*ky + dxi (TCG_S2CONV_TAPS)."""
+    O, C = w.shape[0], w.shape[1]
+    Og = plans.pad_to(O, 16)
+    g = w.new_zeros(Og, 3, 2, 2, C)                 # [o][ky][dxi][b][c]
+    g[:O, :, 0, 1] = w[:, :, :, 0].permute(0, 2, 1)  # pair j-1, second half  <- kx = 0
+    g[:O, :, 1, 0] = w[:, :, :, 1].permute(0, 2, 1)  # pair j,   first half   <- kx = 1
+    g[:O, :, 1, 1] = w[:, :, :, 2].permute(0, 2, 1)  # pair j,   second half  <- kx = 2
+    return g.reshape(Og, 6 * 2 * C)
+
+
+def tcg_s2convT_taps(a):
+    """(dy, dx, ky) of the taps feeding output rows of parity a."""
+    rows = [(0, 1)] if a == 0 else [(0, 2), (1, 0)]
+    return [(dy, dx, ky) for dy, ky in rows for dx in (0, 1)]
+
+
+def pack_tcg_s2convT(w, a, kc):
+    """[I, O, 3, 3] (ConvTranspose2d weight, or Conv2d weight read as [in=Cout][out=Cin]) -> Wg [2*O][ntaps*kc]
+    for output-row parity a: row = b*O + o, column = t*kc + i (zero for i >= I)."""
+    I, O = w.shape[0], w.shape[1]
+    taps = tcg_s2convT_taps(a)
+    g = w.new_zeros(2, O, len(taps), kc)            # [b][o][t][i]
+    for t, (dy, dx, ky) in enumerate(taps):
+        if dx == 0:
+            g[0, :, t, :I] = w[:, :, ky, 1].t()     # column 2j   <- kx = 1 from input column j
+            g[1, :, t, :I] = w[:, :, ky, 2].t()     # column 2j+1 <- kx = 2 from input column j
+        else:
+            g[1, :, t, :I] = w[:, :, ky, 0].t()     # column 2j+1 <- kx = 0 from input column j+1
+    return g.reshape(2 * O, len(taps) * kc)
+
+
+def _tcg_view(t, H, W, sn, sy, sx, offset=0):
+    v = _capi.LfTcgView()
+    v.ptr, v.H, v.W, v.sn, v.sy, v.sx = t.data_ptr() + 4 * offset, H, W, sn, sy, sx
+    return v
+
+
+def tcg_s2conv_ok(x, C, O):
+    """stride-2 conv of x[..., :C] (dense [N,H,W,C]) to O channels on lf_conv_tcg?"""
+    N, H, W, cx = x.shape
+    return (CONV_MODE == "tf32" and cx == C and (2 * C) % 32 == 0 and H % 2 == 0 and W % 2 == 0 and x.is_contiguous()
+            and int(_lib().lf_conv_tcg_supported(N, H // 2, W // 2, 2 * C, plans.pad_to(O, 16))) > 0)
+
+
+def run_tcg_s2conv(x, wg, O, out, bias=None):
+    """out[n,i,j,:O] = bias + conv3x3/s2/p1(x) with wg = pack_tcg_s2conv(w); x dense [N,H,W,C]; out [N,H/2,W/2,Co_total]
+    (the first pad16(O) channels are written: the caller overwrites / ignores any padding columns)."""
+    N, H, W, C = x.shape
+    _, Ho, Wo, cot = out.shape
+    a = _capi.LfConvTcgArgs()
+    a.a[0] = _tcg_view(x, H // 2, W // 2, H * W * C, 2 * W * C, 2 * C)             # even rows, pair pixels
+    a.a[1] = _tcg_view(x, H // 2, W // 2, H * W * C, 2 * W * C, 2 * C, W * C)      # odd rows
+    a.wg, a.bias, a.out = wg.data_ptr(), (bias.data_ptr() if bias is not None else None), out.data_ptr()
+    a.osn, a.osy, a.osx, a.oy_mul, a.oy0 = Ho * Wo * cot, Wo * cot, cot, 1, 0
+    a.N, a.Hs, a.Ws, a.Kc, a.Ng, a.ntaps = N, Ho, Wo, 2 * C, wg.shape[0], 6
+    for t, (m, dy, dx) in enumerate(TCG_S2CONV_TAPS):
+        a.map[t], a.dy[t], a.dx[t] = m, dy, dx
+    _capi.call("lf_conv_tcg", ctypes.byref(a), _stream(), flops=2 * N * Ho * Wo * 9 * C * O, nbytes=4 * N * (H * W * C + Ho * Wo * O))
+    return out
+
+
+def tcg_s2convT_ok(x, I, O):
+    """stride-2 transposed conv of x[..., :I] ([N,H,W,cx], cx >= pad32(I)) to O channels on lf_conv_tcg?"""
+    N, H, W, cx = x.shape
+    kc = plans.pad_to(I, 32)
+    return (CONV_MODE == "tf32" and cx >= kc and cx % 4 == 0 and (2 * O) % 16 == 0 and 2 * O <= 128 and x.is_contiguous()
+            and int(_lib().lf_conv_tcg_supported(N, H, W, kc, 2 * O)) > 0)
+
+
+def run_tcg_s2convT(x, I, wgs, O, out, bias2=None):
+    """out [N,2H,2W,O] = bias + convT3x3/s2/p1/op1(x[..., :I]); wgs = (pack_tcg_s2convT(w,0,kc), pack_tcg_s2convT(w,1,kc));
+    bias2 = bias tiled twice (pair pixel)."""
+    N, H, W, cx = x.shape
+    kc = plans.pad_to(I, 32)
+    for par in (0, 1):
+        taps = tcg_s2convT_taps(par)
+        a = _capi.LfConvTcgArgs()
+        a.a[0] = _tcg_view(x, H, W, H * W * cx, W * cx, cx)
+        a.wg, a.bias, a.out = wgs[par].data_ptr(), (bias2.data_ptr() if bias2 is not None else None), out.data_ptr()
+        a.osn, a.osy, a.osx, a.oy_mul, a.oy0 = 4 * H * W * O, 2 * W * O, 2 * O, 2, par
+        a.N, a.Hs, a.Ws, a.Kc, a.Ng, a.ntaps = N, H, W, kc, 2 * O, len(taps)
+        for t, (dy, dx, _ky) in enumerate(taps):
+            a.map[t], a.dy[t], a.dx[t] = 0, dy, dx
+        _capi.call("lf_conv_tcg", ctypes.byref(a), _stream(), flops=2 * N * H * W * len(taps) * I * 2 * O,
+                   nbytes=4 * N * H * W * (I + 2 * O))
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # one-launch weight packing
 # --------------------------------------------------------------------------------------
 def pack_gather_table(fn, shape):
@@ -573,10 +677,13 @@ class DownFunction(torch.autograd.Function):
         cc = w.shape[0]                      # conv output channels = noutput - ninput
         cout = cc + cin
         cin_gemm = plans.pad_to(cin, 4)
-        wmat = packed(w, "conv_fwd_%d" % cin_gemm, lambda t: pack_conv_fwd(t, cin_gemm))
         phases, (Ho, Wo) = plans.conv_fwd_plan(H, W, 3, 3, 2, 1, 1, 1, 1)
         cat = _empty((N, Ho, Wo, cout), x)
-        run_conv(phases, x, wmat, cin_gemm, cat, cc, 0, bias=b)
+        if cc % 16 == 0 and tcg_s2conv_ok(x, cin, cc):
+            run_tcg_s2conv(x, packed(w, "tcg_s2conv", pack_tcg_s2conv), cc, cat, bias=b)
+        else:
+            wmat = packed(w, "conv_fwd_%d" % cin_gemm, lambda t: pack_conv_fwd(t, cin_gemm))
+            run_conv(phases, x, wmat, cin_gemm, cat, cc, 0, bias=b)
         _capi.call("lf_maxpool2_fwd", ptr(x), N, H, W, cin, cx, ptr(cat), cout, cc, _stream())
         s = bn_forward_stats(cat, gamma, beta, rm, rv, training)
         y = bn_apply(cat, s, relu=True)
@@ -607,9 +714,15 @@ class DownFunction(torch.autograd.Function):
         dx = None
         if need_dx:
             dx = _empty((N, H, W, cx), x)
-            wd = packed(w, "conv_dgrad", pack_conv_dgrad)   # [9, cc, cinPad]
-            phases, _ = plans.transposed_gather_plan(dcat.shape[1], dcat.shape[2], H, W, 3, 1)
-            run_conv(phases, dcat, wd, cc, dx, cin, 0)
+            if cx == cin and tcg_s2convT_ok(dcat, cc, cin):
+                kc = plans.pad_to(cc, 32)
+                wgs = tuple(packed(w, "tcg_s2convT%d_%d" % (par, kc), lambda t, par=par: pack_tcg_s2convT(t, par, kc))
+                            for par in (0, 1))
+                run_tcg_s2convT(dcat, cc, wgs, cin, dx)
+            else:
+                wd = packed(w, "conv_dgrad", pack_conv_dgrad)   # [9, cc, cinPad]
+                phases, _ = plans.transposed_gather_plan(dcat.shape[1], dcat.shape[2], H, W, 3, 1)
+                run_conv(phases, dcat, wd, cc, dx, cin, 0)
             _capi.call("lf_maxpool2_bwd", ptr(x), N, H, W, cin, cx, ptr(dcat), cout, cc, ptr(dx), cx, 1, _stream())
         return dx, None, dw, db, dgamma, dbeta, None, None, None, None
 
@@ -680,7 +793,12 @@ class UpFunction(torch.autograd.Function):
         N, H, W, ci = x.shape
         co = w.shape[1]
         phases, (Ho, Wo) = plans.transposed_gather_plan(H, W, 2 * H, 2 * W, 3, 1)
-        u = run_conv(phases, x, packed(w, "convT_fwd", pack_convT_fwd), ci, _empty((N, Ho, Wo, co), x), co, bias=b)
+        if tcg_s2convT_ok(x, ci, co):
+            wgs = tuple(packed(w, "tcg_s2convT%d_%d" % (par, ci), lambda t, par=par: pack_tcg_s2convT(t, par, ci))
+                        for par in (0, 1))
+            u = run_tcg_s2convT(x, ci, wgs, co, _empty((N, Ho, Wo, co), x), bias2=packed(b, "tile2", lambda t: t.repeat(2)))
+        else:
+            u = run_conv(phases, x, packed(w, "convT_fwd", pack_convT_fwd), ci, _empty((N, Ho, Wo, co), x), co, bias=b)
         s = bn_forward_stats(u, gamma, beta, rm, rv, training)
         y = bn_apply(u, s, relu=True)
         ctx.save_for_backward(x, w, u, y, gamma, s.mean, s.invstd)
@@ -700,8 +818,11 @@ class UpFunction(torch.autograd.Function):
         dw, db = torch.empty_like(w), _empty((co,), x)
         run_wgrad(plans.convT_wgrad_plan(H, W, 3, 1), x, ci, du, co, 0, N, dw, (1, co * 9, 9))
         run_colsum(du, co, 0, db)
-        pd, _ = plans.convT_dgrad_plan(2 * H, 2 * W, H, W, 3, 1)
-        dx = run_conv(pd, du, packed(w, "convT_dgrad", pack_convT_dgrad), co, torch.empty_like(x), ci)
+        if ci % 16 == 0 and tcg_s2conv_ok(du, co, ci):
+            dx = run_tcg_s2conv(du, packed(w, "tcg_s2conv", pack_tcg_s2conv), ci, torch.empty_like(x))
+        else:
+            pd, _ = plans.convT_dgrad_plan(2 * H, 2 * W, H, W, 3, 1)
+            dx = run_conv(pd, du, packed(w, "convT_dgrad", pack_convT_dgrad), co, torch.empty_like(x), ci)
         return dx, dw, db, dgamma, dbeta, None, None, None
 
 

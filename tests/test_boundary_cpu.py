@@ -37,7 +37,8 @@ def test_ctypes_struct_layout_matches_header():
     from lanedetection_end2end_b200 import _capi
     hdr = open(os.path.join(ROOT, "include", "lanefit_b200.h")).read()
     for cname, cls in (("LfConvArgs", _capi.LfConvArgs), ("LfWgradArgs", _capi.LfWgradArgs),
-                       ("LfConvTcArgs", _capi.LfConvTcArgs)):
+                       ("LfConvTcArgs", _capi.LfConvTcArgs), ("LfTcgView", _capi.LfTcgView),
+                       ("LfConvTcgArgs", _capi.LfConvTcgArgs)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
@@ -45,7 +46,7 @@ def test_ctypes_struct_layout_matches_header():
             decl = decl.strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(float|int|double)\s*\*?", "", decl)
+            decl = re.sub(r"^(const\s+)?(float|int|double|long long|LfTcgView)\s*\*?", "", decl)
             for part in decl.split(","):
                 names.append(re.sub(r"\[.*\]", "", part.replace("*", "")).strip())
         mine = [f[0] for f in cls._fields_]

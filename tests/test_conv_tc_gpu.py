@@ -197,3 +197,67 @@ def test_c16_layers_on_tensor_cores_via_super_pixels(vertical):
     for i, (a, r) in enumerate(zip(res["tf32"], res["fp32"])):
         tol = 2e-6 if i < 2 else 1e-4
         assert float((a - r).abs().max()) <= tol * float(r.abs().max()), i
+
+
+# ------------------------------------------------------------------------------------------------
+# lf_conv_tcg: the resolution-changing layers (Down / Up blocks) on the tensor cores
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,O,tot,H,W,N", [(16, 48, 64, 128, 256, 2), (64, 64, 128, 64, 128, 3), (16, 48, 64, 32, 64, 1)])
+def test_tcg_stride2_conv_and_its_input_gradient(C, O, tot, H, W, N):
+    """DownsamplerBlock conv (3x3, stride 2) into the concat buffer and its input gradient (TF32-exact operands ->
+    fp32-level agreement with torch fp64)."""
+    o = ops()
+    o.set_conv_mode("tf32")
+    try:
+        g = torch.Generator().manual_seed(C + O)
+        x = tf32_exact(torch.randn(N, H, W, C, generator=g).cuda())
+        w = tf32_exact((torch.randn(O, C, 3, 3, generator=g) / (9 * C) ** 0.5).cuda())
+        b = torch.randn(O, generator=g).cuda()
+        assert o.tcg_s2conv_ok(x, C, O)
+        cat = torch.full((N, H // 2, W // 2, tot), 7.0, device="cuda")
+        o.run_tcg_s2conv(x, o.pack_tcg_s2conv(w), O, cat, bias=b)
+        ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=2, padding=1).permute(0, 2, 3, 1)
+        err = float((cat[..., :O].double() - ref).abs().max() / ref.abs().max())
+        assert err < 3e-6, err
+        assert bool((cat[..., O:] == 7.0).all())
+        dcat = tf32_exact(torch.randn(N, H // 2, W // 2, tot, generator=g).cuda())
+        assert o.tcg_s2convT_ok(dcat, O, C)
+        kc = ((O + 31) // 32) * 32
+        dx = torch.full((N, H, W, C), 3.0, device="cuda")
+        o.run_tcg_s2convT(dcat, O, (o.pack_tcg_s2convT(w, 0, kc), o.pack_tcg_s2convT(w, 1, kc)), C, dx)
+        ref = F.conv_transpose2d(dcat[..., :O].permute(0, 3, 1, 2).double(), w.double(), stride=2, padding=1,
+                                 output_padding=1).permute(0, 2, 3, 1)
+        err = float((dx.double() - ref).abs().max() / ref.abs().max())
+        assert err < 3e-6, err
+    finally:
+        o.set_conv_mode("fp32")
+
+
+@pytest.mark.parametrize("I,O,H,W,N", [(128, 64, 32, 64, 2), (64, 16, 64, 128, 3), (64, 16, 16, 32, 1)])
+def test_tcg_stride2_transposed_conv_and_its_input_gradient(I, O, H, W, N):
+    """UpsamplerBlock ConvTranspose2d (3x3, stride 2, padding 1, output_padding 1) and its input gradient."""
+    o = ops()
+    o.set_conv_mode("tf32")
+    try:
+        g = torch.Generator().manual_seed(I + O)
+        x = tf32_exact(torch.randn(N, H, W, I, generator=g).cuda())
+        w = tf32_exact((torch.randn(I, O, 3, 3, generator=g) / (9 * I) ** 0.5).cuda())
+        b = torch.randn(O, generator=g).cuda()
+        assert o.tcg_s2convT_ok(x, I, O)
+        u = torch.zeros(N, 2 * H, 2 * W, O, device="cuda")
+        o.run_tcg_s2convT(x, I, (o.pack_tcg_s2convT(w, 0, I), o.pack_tcg_s2convT(w, 1, I)), O, u, bias2=b.repeat(2))
+        ref = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=2, padding=1,
+                                 output_padding=1).permute(0, 2, 3, 1)
+        err = float((u.double() - ref).abs().max() / ref.abs().max())
+        assert err < 3e-6, err
+        du = tf32_exact(torch.randn(N, 2 * H, 2 * W, O, generator=g).cuda())
+        assert o.tcg_s2conv_ok(du, O, I)
+        dx = torch.zeros(N, H, W, I, device="cuda")
+        o.run_tcg_s2conv(du, o.pack_tcg_s2conv(w), I, dx)
+        xin = x.permute(0, 3, 1, 2).double().requires_grad_(True)
+        F.conv_transpose2d(xin, w.double(), stride=2, padding=1, output_padding=1).backward(du.permute(0, 3, 1, 2).double())
+        ref = xin.grad.permute(0, 2, 3, 1)
+        err = float((dx.double() - ref).abs().max() / ref.abs().max())
+        assert err < 3e-6, err
+    finally:
+        o.set_conv_mode("fp32")

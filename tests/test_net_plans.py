@@ -223,3 +223,96 @@ def test_weight_pack_gather_tables_reproduce_every_packer():
         src = torch.cat([w.reshape(-1), w.new_zeros(1)])
         got = src[idx.to(torch.int64).clamp(min=-1)]          # -1 wraps to the appended zero
         assert torch.equal(got, ref), (fn, shape)
+
+
+def _emulate_conv_tcg(a, tensors):
+    """CPU restatement of the lf_conv_tcg contract (include/lanefit_b200.h) on the exact views / strides the host
+    code put into LfConvTcgArgs; `tensors` = the CPU tensors the pointers refer to."""
+    def locate(ptr):
+        for t in tensors:
+            if t.data_ptr() <= ptr < t.data_ptr() + t.numel() * 4:
+                return t, (ptr - t.data_ptr()) // 4
+        raise AssertionError("pointer outside the known tensors")
+
+    K = a.ntaps * a.Kc
+    wt, woff = locate(a.wg)
+    Wg = wt.reshape(-1)[woff:woff + a.Ng * K].view(a.Ng, K).double()
+    acc = torch.zeros(a.N, a.Hs, a.Ws, a.Ng, dtype=torch.float64)
+    for t in range(a.ntaps):
+        v = a.a[a.map[t]]
+        base, off = locate(v.ptr)
+        # as_strided must stay inside the storage: gather explicitly with bounds checks (zero outside [0,H)x[0,W))
+        flat = base.reshape(-1).double()
+        ys = torch.arange(a.Hs) + a.dy[t]
+        xs = torch.arange(a.Ws) + a.dx[t]
+        ok = ((ys >= 0) & (ys < v.H)).view(1, -1, 1, 1) & ((xs >= 0) & (xs < v.W)).view(1, 1, -1, 1)
+        idx = (off + torch.arange(a.N).view(-1, 1, 1, 1) * v.sn + ys.clamp(0, v.H - 1).view(1, -1, 1, 1) * v.sy
+               + xs.clamp(0, v.W - 1).view(1, 1, -1, 1) * v.sx + torch.arange(a.Kc).view(1, 1, 1, -1))
+        A = flat[idx] * ok
+        acc += torch.einsum("nyxk,ck->nyxc", A, Wg[:, t * a.Kc:(t + 1) * a.Kc])
+    if a.bias:
+        bt, boff = locate(a.bias)
+        acc += bt.reshape(-1)[boff:boff + a.Ng].double()
+    ot, ooff = locate(a.out)
+    oflat = ot.reshape(-1)
+    oidx = (ooff + torch.arange(a.N).view(-1, 1, 1, 1) * a.osn + (torch.arange(a.Hs) * a.oy_mul + a.oy0).view(1, -1, 1, 1) * a.osy
+            + torch.arange(a.Ws).view(1, 1, -1, 1) * a.osx + torch.arange(a.Ng).view(1, 1, 1, -1))
+    oflat[oidx.reshape(-1)] = acc.reshape(-1).float()
+
+
+def test_tcg_pair_pixel_forms_match_torch_convs(monkeypatch):
+    """The four layer forms served by lf_conv_tcg (Down forward / input gradient, Up forward / input gradient) are
+    re-expressed as unit-stride gathers over pair-pixel / row-parity views.  Run the host code on CPU with the kernel
+    replaced by a literal restatement of its contract and compare with torch's own stride-2 convolutions."""
+    import torch.nn.functional as F
+    from lanedetection_end2end_b200 import ops_net as o, _capi
+    live = []
+    monkeypatch.setattr(o, "_stream", lambda: None)
+    monkeypatch.setattr(_capi, "call", lambda name, ref, *rest, **kw: _emulate_conv_tcg(ref._obj, live))
+    g = torch.Generator().manual_seed(7)
+    # ---- Conv2d 3x3 stride 2 (DownsamplerBlock: 16 -> 48 into a 64-channel concat buffer) and its input gradient
+    for (C, O, tot, H, W) in [(16, 48, 64, 16, 32), (64, 64, 128, 8, 32)]:
+        N = 2
+        x = torch.randn(N, H, W, C, generator=g)
+        w = torch.randn(O, C, 3, 3, generator=g) * 0.1
+        b = torch.randn(O, generator=g)
+        cat = torch.full((N, H // 2, W // 2, tot), 7.0)
+        wg = o.pack_tcg_s2conv(w)
+        bp = torch.cat([b, torch.zeros(wg.shape[0] - O)])
+        live[:] = [x, wg, bp, cat]
+        o.run_tcg_s2conv(x, wg, O, cat, bias=bp)
+        ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=2, padding=1).permute(0, 2, 3, 1)
+        assert torch.allclose(cat[..., :O].double(), ref, atol=1e-5), (C, O)
+        assert bool((cat[..., wg.shape[0]:] == 7.0).all())             # channels beyond pad16(O) untouched
+        # input gradient of that conv = transposed conv of the output gradient with the same weight
+        dcat = torch.randn(N, H // 2, W // 2, tot, generator=g)
+        kc = ((O + 31) // 32) * 32
+        wgs = (o.pack_tcg_s2convT(w, 0, kc), o.pack_tcg_s2convT(w, 1, kc))
+        dx = torch.full((N, H, W, C), 3.0)
+        live[:] = [dcat, wgs[0], wgs[1], dx]
+        o.run_tcg_s2convT(dcat, O, wgs, C, dx)
+        ref = F.conv_transpose2d(dcat[..., :O].permute(0, 3, 1, 2).double(), w.double(), stride=2, padding=1,
+                                 output_padding=1).permute(0, 2, 3, 1)
+        assert torch.allclose(dx.double(), ref, atol=1e-5), (C, O)
+    # ---- ConvTranspose2d 3x3 stride 2 (UpsamplerBlock) and its input gradient
+    for (I, O, H, W) in [(128, 64, 8, 16), (64, 16, 8, 32)]:
+        N = 2
+        x = torch.randn(N, H, W, I, generator=g)
+        w = torch.randn(I, O, 3, 3, generator=g) * 0.1
+        b = torch.randn(O, generator=g)
+        wgs = (o.pack_tcg_s2convT(w, 0, I), o.pack_tcg_s2convT(w, 1, I))
+        u = torch.zeros(N, 2 * H, 2 * W, O)
+        b2 = b.repeat(2)
+        live[:] = [x, wgs[0], wgs[1], b2, u]
+        o.run_tcg_s2convT(x, I, wgs, O, u, bias2=b2)
+        ref = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=2, padding=1,
+                                 output_padding=1).permute(0, 2, 3, 1)
+        assert torch.allclose(u.double(), ref, atol=1e-5), (I, O)
+        du = torch.randn(N, 2 * H, 2 * W, O, generator=g)
+        wg = o.pack_tcg_s2conv(w)                                      # [I][6*2*O]: out = I, in = O
+        dx = torch.zeros(N, H, W, I)
+        live[:] = [du, wg, dx]
+        o.run_tcg_s2conv(du, wg, I, dx)
+        xin = x.permute(0, 3, 1, 2).double().requires_grad_(True)
+        F.conv_transpose2d(xin, w.double(), stride=2, padding=1, output_padding=1).backward(du.permute(0, 3, 1, 2).double())
+        assert torch.allclose(dx.double(), xin.grad.permute(0, 2, 3, 1), atol=1e-5), (I, O)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU session 9: one-launch weight packing (WeightPackCache), residual-operand prefetch at C=64.
+# GPU session 10: small-channel wgrad kernel, lf_conv_tcg (Down/Up blocks on tensor cores).
 set -x
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu --maxfail=60 -q > gpurun_out/pytest_gpu.log 2>&1; echo "gpu tests rc=$?" >> gpurun_out/pytest_gpu.log
