@@ -198,6 +198,8 @@ typedef struct LfWgradArgs {
     int nsplit;
 } LfWgradArgs;
 int lf_wgrad_f32(const LfWgradArgs* args, lf_stream_t stream);
+/* split count lf_wgrad_f32 prefers for these arguments (nsplit field ignored), 0 = no preference */
+int lf_wgrad_f32_nsplit(const LfWgradArgs* args);
 int lf_wgrad_reduce(const float* partial, int nsplit, int ntaps, int Cp, int Cq, int CpPad, int CqPad,
                     float* dst, int st, int sp, int sq, lf_stream_t stream);
 /* dst[c] = sum over splits of partial[s][c]  (bias gradients) */

@@ -88,6 +88,7 @@ _NET_PROTOS = {
     "lf_conv_tcg": (_i, [ctypes.POINTER(LfConvTcgArgs), _p]),
     "lf_conv_f32": (_i, [ctypes.POINTER(LfConvArgs), _p]),
     "lf_wgrad_f32": (_i, [ctypes.POINTER(LfWgradArgs), _p]),
+    "lf_wgrad_f32_nsplit": (_i, [ctypes.POINTER(LfWgradArgs)]),
     "lf_conv1d_tc": (_i, [ctypes.POINTER(LfConvTcArgs), _p]),
     "lf_conv1d_tc_supported": (_i, [_i, _i, _i, _i]),
     "lf_conv1d_tc_set_variant": (None, [_i]),

@@ -190,9 +190,8 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const WgradArgs a
 // The generic tile kernel above spent 316-443 us per launch on these layers; this one is FMA/HBM-bound.
 // ------------------------------------------------------------------------------------------
 struct WsPlan {
-    int LU, LV, TPG, G, PXG, PXS, threads, taps_on_p, smem_bytes, nslot;
+    int LU, LV, TPG, G, PXG, PXS, threads, taps_on_p, smem_bytes, ppp, passes;
 };
-constexpr int WS_MAXSLOT = 8;
 
 static bool ws_make_plan(const WgradArgs& a, WsPlan* p) {
     bool p_same = true, q_same = true;
@@ -213,16 +212,23 @@ static bool ws_make_plan(const WgradArgs& a, WsPlan* p) {
     p->threads = ((p->G * p->TPG + 31) / 32) * 32;
     p->PXG = p->G >= 8 ? 4 : 16;
     p->PXS = p->PXG * p->G;
+    const int per_px4 = (p->LU + p->LV) / 4;
+    if (per_px4 > p->threads) return false;
+    p->ppp = p->threads / per_px4;                       // pixels fetched per pass (one float4 per thread)
+    p->passes = (p->PXS + p->ppp - 1) / p->ppp;
     const int tile_floats = 2 * p->PXS * (p->LU + p->LV);
     if (p->G > 1 && p->LU * p->LV + p->LV > tile_floats) return false;  // group reduction reuses the tiles
     p->smem_bytes = tile_floats * 4;
-    if (p->smem_bytes > 96 * 1024) return false;
-    const int total4 = p->PXS * (p->LU + p->LV) / 4;
-    p->nslot = (total4 + p->threads - 1) / p->threads;
-    return p->nslot <= WS_MAXSLOT;
+    return p->smem_bytes <= 96 * 1024;
 }
 
-__global__ void __launch_bounds__(256) wgrad_small_kernel(const WgradArgs a, const WsPlan pl) {
+__device__ __forceinline__ void ws_cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 16 : 0;  // 0 -> the 16 destination bytes are zero-filled, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) wgrad_small_kernel(const WgradArgs a, const WsPlan pl) {
     extern __shared__ __align__(16) float ws_smem[];
     const int LU = pl.LU, LV = pl.LV, PXS = pl.PXS, G = pl.G;
     float* sU = ws_smem;                  // [2][PXS][LU]
@@ -236,64 +242,46 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(const WgradArgs a, con
     const int m_end = min(M, m_begin + per);
     const int HW = a.Hs * a.Ws;
 
-    // ---- load slots: which float4 of the (pixel, U|V) tile this thread fetches; fixed for the whole kernel
-    const int nU4 = LU / 4, per_px4 = (LU + LV) / 4, total4 = PXS * per_px4;
-    int s_lp[WS_MAXSLOT], s_soff[WS_MAXSLOT], s_goff[WS_MAXSLOT], s_dy[WS_MAXSLOT], s_dx[WS_MAXSLOT];
-    unsigned s_valid = 0, s_isu = 0;
-#pragma unroll
-    for (int q = 0; q < WS_MAXSLOT; ++q) {
-        s_lp[q] = s_soff[q] = s_goff[q] = s_dy[q] = s_dx[q] = 0;
-        const int f = tid + q * pl.threads;
-        if (q < pl.nslot && f < total4) {
-            s_valid |= 1u << q;
-            const int lp = f / per_px4, e = f - lp * per_px4;
-            s_lp[q] = lp;
-            if (e < nU4) {
-                s_isu |= 1u << q;
-                const int u = 4 * e;
-                const int t = pl.taps_on_p ? u / a.Cp : 0;
-                s_goff[q] = a.p_coff + (pl.taps_on_p ? u - t * a.Cp : u);
-                s_dy[q] = a.pdy[t];
-                s_dx[q] = a.pdx[t];
-                s_soff[q] = lp * LU + u;
-            } else {
-                const int v = 4 * (e - nU4);
-                const int t = pl.taps_on_p ? 0 : v / a.Cq;
-                s_goff[q] = a.q_coff + (pl.taps_on_p ? v : v - t * a.Cq);
-                s_dy[q] = a.qdy[t];
-                s_dx[q] = a.qdx[t];
-                s_soff[q] = lp * LV + v;
-            }
-        }
+    // ---- fetch role: this thread always fetches float4 number `e` of a pixel's (U | V) vector, for pixel
+    // lp0, lp0 + ppp, ... of the step (cp.async straight into shared memory, zero fill outside the image)
+    const int nU4 = LU / 4, per_px4 = (LU + LV) / 4;
+    const int lp0 = tid / per_px4, e = tid - lp0 * per_px4;
+    const bool fetcher = lp0 < pl.ppp;
+    const bool is_u = e < nU4;
+    int f_dy, f_dx, f_goff, f_soff;
+    if (is_u) {
+        const int u = 4 * e;
+        const int t = pl.taps_on_p ? u / a.Cp : 0;
+        f_goff = a.p_coff + (pl.taps_on_p ? u - t * a.Cp : u);
+        f_dy = a.pdy[t]; f_dx = a.pdx[t]; f_soff = u;
+    } else {
+        const int v = 4 * (e - nU4);
+        const int t = pl.taps_on_p ? 0 : v / a.Cq;
+        f_goff = a.q_coff + (pl.taps_on_p ? v : v - t * a.Cq);
+        f_dy = a.qdy[t]; f_dx = a.qdx[t]; f_soff = v;
     }
-    float4 rr[WS_MAXSLOT];
-    auto load = [&](int m0) {
-#pragma unroll
-        for (int q = 0; q < WS_MAXSLOT; ++q) {
-            rr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!((s_valid >> q) & 1u)) continue;
-            const int m = m0 + s_lp[q];
-            if (m >= m_end) continue;
-            const int n = m / HW;
-            const int rem = m - n * HW;
-            const int j = rem / a.Ws, i = rem - j * a.Ws;
-            if ((s_isu >> q) & 1u) {
-                const int y = j * a.psy + s_dy[q], x = i * a.psx + s_dx[q];
-                if (y >= 0 && y < a.Hp && x >= 0 && x < a.Wp)
-                    rr[q] = __ldg(reinterpret_cast<const float4*>(a.P + ((size_t)(n * a.Hp + y) * a.Wp + x) * a.p_cstride + s_goff[q]));
-            } else {
-                const int y = j * a.qsy + s_dy[q], x = i * a.qsx + s_dx[q];
-                if (y >= 0 && y < a.Hq && x >= 0 && x < a.Wq)
-                    rr[q] = __ldg(reinterpret_cast<const float4*>(a.Q + ((size_t)(n * a.Hq + y) * a.Wq + x) * a.q_cstride + s_goff[q]));
+    const float* f_base = is_u ? a.P : a.Q;
+    const int f_H = is_u ? a.Hp : a.Hq, f_W = is_u ? a.Wp : a.Wq, f_cs = is_u ? a.p_cstride : a.q_cstride;
+    const int f_sy = is_u ? a.psy : a.qsy, f_sx = is_u ? a.psx : a.qsx;
+    const int f_L = is_u ? LU : LV;
+    auto fetch = [&](int m0, int buf) {
+        if (!fetcher) return;
+        float* sdst = (is_u ? sU + buf * PXS * LU : sV + buf * PXS * LV) + f_soff;
+        // decode the first pixel once, then step by ppp pixels with carries (no division per pixel)
+        int m = m0 + lp0;
+        int n = m / HW;
+        int rem = m - n * HW;
+        int j = rem / a.Ws, i = rem - j * a.Ws;
+        for (int k = 0, lp = lp0; k < pl.passes; ++k, lp += pl.ppp, m += pl.ppp) {
+            if (lp < PXS) {
+                const int y = j * f_sy + f_dy, x = i * f_sx + f_dx;
+                const bool ok = m < m_end && y >= 0 && y < f_H && x >= 0 && x < f_W;
+                const float* src = ok ? f_base + ((size_t)(n * f_H + y) * f_W + x) * f_cs + f_goff : f_base;
+                ws_cp_async16(sdst + lp * f_L, src, ok);
             }
-        }
-    };
-    auto store = [&](int buf) {
-#pragma unroll
-        for (int q = 0; q < WS_MAXSLOT; ++q) {
-            if (!((s_valid >> q) & 1u)) continue;
-            float* base = ((s_isu >> q) & 1u) ? sU + buf * PXS * LU : sV + buf * PXS * LV;
-            *reinterpret_cast<float4*>(base + s_soff[q]) = rr[q];
+            i += pl.ppp;
+            while (i >= a.Ws) { i -= a.Ws; ++j; }
+            while (j >= a.Hs) { j -= a.Hs; ++n; }
         }
     };
 
@@ -312,20 +300,19 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(const WgradArgs a, con
         for (int i = 0; i < 4; ++i) acc[i][c] = 0.f;
     }
 
-    if (m_begin < m_end) {
-        load(m_begin);
-        store(0);
-    }
+    if (m_begin < m_end) fetch(m_begin, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     int it = 0;
     for (int m0 = m_begin; m0 < m_end; m0 += PXS, ++it) {
         const int buf = it & 1;
-        const bool more = (m0 + PXS) < m_end;
-        if (more) load(m0 + PXS);
+        if (m0 + PXS < m_end) fetch(m0 + PXS, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         if (active) {
             const float* bu = sU + buf * PXS * LU + 4 * ug;
             const float* bv = sV + buf * PXS * LV + 16 * vg;
-#pragma unroll 4
+#pragma unroll 2
             for (int pp = 0; pp < pl.PXG; ++pp) {
                 const int p = pp * G + g;  // groups interleave the pixels of a step
                 const float4 u4 = *reinterpret_cast<const float4*>(bu + p * LU);
@@ -346,7 +333,7 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(const WgradArgs a, con
                 }
             }
         }
-        if (more) store(buf ^ 1);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
     }
 
@@ -384,22 +371,22 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(const WgradArgs a, con
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
-                    float* e = red + (4 * ug + i) * LV + 16 * vg + c;
-                    *e = (gg == 0) ? acc[i][c] : *e + acc[i][c];
+                    float* ep = red + (4 * ug + i) * LV + 16 * vg + c;
+                    *ep = (gg == 0) ? acc[i][c] : *ep + acc[i][c];
                 }
             if (do_qsum) {
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
-                    float* e = redq + 16 * vg + c;
-                    *e = (gg == 0) ? qs[c] : *e + qs[c];
+                    float* ep = redq + 16 * vg + c;
+                    *ep = (gg == 0) ? qs[c] : *ep + qs[c];
                 }
             }
         }
         __syncthreads();
     }
-    for (int e = tid; e < LU * LV; e += blockDim.x) dst[out_index(e / LV, e % LV)] = red[e];
+    for (int o = tid; o < LU * LV; o += blockDim.x) dst[out_index(o / LV, o % LV)] = red[o];
     if (a.qsum_partial != nullptr)
-        for (int e = tid; e < LV; e += blockDim.x) a.qsum_partial[(size_t)split * a.CqPad + e] = redq[e];
+        for (int o = tid; o < LV; o += blockDim.x) a.qsum_partial[(size_t)split * a.CqPad + o] = redq[o];
 }
 
 // dst[t*st + cp*sp + cq*sq] = sum_k partial[k][t][cp][cq], fixed order.  One thread = 4 consecutive cq
@@ -524,6 +511,22 @@ extern "C" int lf_wgrad_f32(const LfWgradArgs* args, lf_stream_t stream_) {
     else
         wgrad_f32_kernel<64, 64><<<grid, WG_THREADS, 0, stream>>>(b);
     return check_launch();
+}
+
+// Split count the small-channel kernel wants for these arguments (its grid IS the split count: two CTAs per
+// SM), or 0 when the generic tile kernel will run and the caller's own choice stands.
+extern "C" int lf_wgrad_f32_nsplit(const LfWgradArgs* args) {
+    if (!args) return 0;
+    WsPlan wsp;
+    if (!ws_make_plan(*args, &wsp)) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long M = (long long)args->N * args->Hs * args->Ws;
+    long long n = 2LL * sms;
+    const long long max_split = (M + 4LL * wsp.PXS - 1) / (4LL * wsp.PXS);   // at least 4 steps per CTA
+    if (n > max_split) n = max_split;
+    return (int)(n < 1 ? 1 : n);
 }
 
 extern "C" int lf_wgrad_reduce(const float* partial, int nsplit, int ntaps, int Cp, int Cq, int CpPad, int CqPad,

@@ -548,6 +548,11 @@ def run_wgrad(plan, P, cp, Q, cq, q_coff, N, dst_w, layout, dst_b=None, cp_true=
     tiles = (a.CpPad // 64) * (a.CqPad // 64) * ntaps
     M = N * plan["Hs"] * plan["Ws"]
     a.nsplit = _nsplit_for(tiles, M)
+    a.qsum_partial = 1 if dst_b is not None else None      # the query only looks at whether it is requested
+    pref = int(h.lf_wgrad_f32_nsplit(ctypes.byref(a)))
+    if pref > 0:
+        a.nsplit = pref
+    a.qsum_partial = None
     partial = torch.empty(a.nsplit * ntaps * a.CpPad * a.CqPad, dtype=torch.float32, device=P.device)
     a.partial = partial.data_ptr()
     qpart = None
