@@ -202,6 +202,15 @@ int lf_wgrad_f32(const LfWgradArgs* args, lf_stream_t stream);
 int lf_wgrad_f32_nsplit(const LfWgradArgs* args);
 int lf_wgrad_reduce(const float* partial, int nsplit, int ntaps, int Cp, int Cq, int CpPad, int CqPad,
                     float* dst, int st, int sp, int sq, lf_stream_t stream);
+/* up to LF_REDUCE_MAX_JOBS such reductions in one launch (a bias-gradient reduction is the job ntaps = Cp = CpPad = 1,
+ * sq = 1): the per-block weight and bias gradients of non_bottleneck_1d (host array, copied into the launch) */
+#define LF_REDUCE_MAX_JOBS 8
+typedef struct LfReduceJob {
+    const float* partial;
+    float* dst;
+    int nsplit, ntaps, Cp, Cq, CpPad, CqPad, st, sp, sq;
+} LfReduceJob;
+int lf_reduce_multi(const LfReduceJob* jobs, int njobs, lf_stream_t stream);
 /* dst[c] = sum over splits of partial[s][c]  (bias gradients) */
 int lf_vec_reduce(const float* partial, int nsplit, int C, int Cpad, float* dst, lf_stream_t stream);
 /* partial[blk][c] = sum over a pixel range of src[pix*cstride + coff + c]; nblk returned by the query */

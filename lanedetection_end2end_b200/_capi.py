@@ -83,7 +83,16 @@ class LfConvTcgArgs(ctypes.Structure):
                 ("map", _i * TCG_MAX_TAPS), ("dy", _i * TCG_MAX_TAPS), ("dx", _i * TCG_MAX_TAPS)]
 
 
+REDUCE_MAX_JOBS = 8
+
+
+class LfReduceJob(ctypes.Structure):
+    _fields_ = [("partial", _p), ("dst", _p), ("nsplit", _i), ("ntaps", _i), ("Cp", _i), ("Cq", _i), ("CpPad", _i),
+                ("CqPad", _i), ("st", _i), ("sp", _i), ("sq", _i)]
+
+
 _NET_PROTOS = {
+    "lf_reduce_multi": (_i, [ctypes.POINTER(LfReduceJob), _i, _p]),
     "lf_conv_tcg_supported": (_i, [_i, _i, _i, _i, _i]),
     "lf_conv_tcg": (_i, [ctypes.POINTER(LfConvTcgArgs), _p]),
     "lf_conv_f32": (_i, [ctypes.POINTER(LfConvArgs), _p]),

@@ -211,7 +211,6 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else {
         // ================= epilogue (warps 2..) =================
         constexpr int NH = Cfg::HALVES;
-        constexpr bool PRE_BOTH = (NH == 1);
         const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may access
         const int m = lane_base + lane;         // phase 1: this thread's pixel row of the tile
         const int grp = (threadIdx.x - 64) >> 7;  // epilogue group (0 when there is only one)
@@ -227,6 +226,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float4 csum[NH], csq[NH];               // running column sums / sums of squares, per channel half
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) csum[hh] = csq[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 nxt_a[NH == 1 ? 8 : 1], nxt_m[NH == 1 ? 8 : 1];  // operands of the next tile in flight (C=64)
         int it = 0;
         for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
             const int buf = it & 1;
@@ -244,11 +244,42 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int y = a.vertical ? pa : pb, x = a.vertical ? pb : pa;
                 roff[j] = ((size_t)(n * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN + 32 * h_first + 4 * c4;
             }
-            // Prefetch the ReLU mask (or the gated residual gradient) of this tile while the MMAs are still
-            // running: the loads' latency hides behind the wait for the accumulator.
+            // Prefetch the ReLU mask (or the gated residual gradient).  One half per thread (C=64): ONE TILE AHEAD —
+            // the loads for tile i+1 are issued before tile i is processed, so their latency hides behind a whole
+            // tile of epilogue work (the epilogue, not the tensor pipe, bounds these layers).  Two halves per
+            // thread (C=128): no registers for that; prefetch this tile's operands before waiting on the accumulator.
             float4 pre[NH][8];
-            float4 pre2[PRE_BOTH ? 8 : 1];
-            if (pre_mask || pre_add) {
+            if constexpr (NH == 1) {
+                if (pre_mask || pre_add) {
+                    auto issue = [&](int mtn) {
+                        const int tan = mtn % a.tiles_a;
+                        const int tbn = (mtn / a.tiles_a) % a.tiles_b;
+                        const int nn = mtn / (a.tiles_a * a.tiles_b);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int r = r0 + 16 * j;
+                            const int ap = r >> tb_shift, bp = r & (a.TB - 1);
+                            const int pa = tan * a.TA + ap, pb = tbn * a.TB + bp;
+                            const int y = a.vertical ? pa : pb, x = a.vertical ? pb : pa;
+                            const size_t off = ((size_t)(nn * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN + 32 * h_first + 4 * c4;
+                            nxt_a[j] = __ldg(reinterpret_cast<const float4*>((pre_mask ? a.mask_src : a.add_src) + off));
+                            if (!pre_mask && a.add_mask) nxt_m[j] = __ldg(reinterpret_cast<const float4*>(a.add_mask + off));
+                        }
+                    };
+                    if (it == 0) issue(mt);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v = nxt_a[j];
+                        if (!pre_mask && a.add_mask) {
+                            const float4 mk = nxt_m[j];
+                            v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
+                            v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+                        }
+                        pre[0][j] = v;
+                    }
+                    if (mt + m_stride < a.total_m_tiles) issue(mt + m_stride);
+                }
+            } else if (pre_mask || pre_add) {
 #pragma unroll
                 for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
@@ -265,20 +296,6 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             pre[hh][j] = ad;
                         }
                     }
-                if (PRE_BOTH && pre_mask && a.add_src) {
-                    // mask AND gated residual (the block's first dgrad): with one half per thread there are
-                    // registers to prefetch the second operand as well
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + roff[j]));
-                        if (a.add_mask) {
-                            const float4 mk = __ldg(reinterpret_cast<const float4*>(a.add_mask + roff[j]));
-                            ad.x = mk.x > 0.f ? ad.x : 0.f; ad.y = mk.y > 0.f ? ad.y : 0.f;
-                            ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
-                        }
-                        pre2[j] = ad;
-                    }
-                }
             }
             mbar_wait(&tfull[buf], use_parity);
             tc_fence_after();
@@ -327,8 +344,6 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     if (pre_add) {
                         o.x += pre[hh][j].x; o.y += pre[hh][j].y; o.z += pre[hh][j].z; o.w += pre[hh][j].w;
-                    } else if (PRE_BOTH && a.add_src) {
-                        o.x += pre2[j].x; o.y += pre2[j].y; o.z += pre2[j].z; o.w += pre2[j].w;
                     } else if (a.add_src) {
                         float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + off));
                         if (a.add_mask) {

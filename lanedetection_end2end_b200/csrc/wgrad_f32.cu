@@ -210,7 +210,7 @@ static bool ws_make_plan(const WgradArgs& a, WsPlan* p) {
     if (p->TPG > 256 || p->TPG < 1) return false;
     p->G = 256 / p->TPG;
     p->threads = ((p->G * p->TPG + 31) / 32) * 32;
-    p->PXG = p->G >= 8 ? 4 : 16;
+    p->PXG = p->G >= 8 ? 4 : (p->G >= 2 ? 16 : 32);
     p->PXS = p->PXG * p->G;
     const int per_px4 = (p->LU + p->LV) / 4;
     if (per_px4 > p->threads) return false;
@@ -288,8 +288,10 @@ __global__ void __launch_bounds__(256, 2) wgrad_small_kernel(const WgradArgs a, 
     // ---- compute role
     const bool active = tid < G * pl.TPG;
     const int g = tid / pl.TPG, r = tid - g * pl.TPG;
-    const int nvg = LV / 16;
-    const int ug = r / nvg, vg = r - ug * nvg;
+    // U index fastest inside a warp: a quarter-warp reads 8 consecutive float4s of U (conflict-free) and ONE
+    // broadcast address of V.  (V fastest made every V load a 4-way bank conflict: 64-byte stride.)
+    const int nug = LU / 4;
+    const int vg = r / nug, ug = r - vg * nug;
     const bool do_qsum = active && a.qsum_partial != nullptr && ug == 0;
     float acc[4][16];
     float qs[16];
@@ -428,6 +430,48 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     }
 }
 
+// Several split reductions in one launch (blockIdx.y = job): the four weight gradients and two bias gradients
+// of a non_bottleneck_1d block are ~12 us latency-bound launches each when reduced one by one.
+struct ReduceJobs {
+    LfReduceJob job[LF_REDUCE_MAX_JOBS];
+    int njobs;
+};
+__global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceJobs js) {
+    __shared__ float4 red[256];
+    const LfReduceJob& j = js.job[blockIdx.y];
+    const int Cq4 = (j.Cq + 3) >> 2;
+    const int total4 = j.ntaps * j.Cp * Cq4;
+    if ((int)(blockIdx.x * (256 / WR_LANES)) >= total4) return;   // whole block beyond this job (uniform)
+    const int o = blockIdx.x * (256 / WR_LANES) + (threadIdx.x / WR_LANES);
+    const int lane = threadIdx.x % WR_LANES;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cq = 0, cp = 0, t = 0;
+    if (o < total4) {
+        cq = (o % Cq4) * 4;
+        cp = (o / Cq4) % j.Cp;
+        t = o / (Cq4 * j.Cp);
+        const size_t stride = (size_t)j.ntaps * j.CpPad * j.CqPad;
+        const float* p = j.partial + ((size_t)t * j.CpPad + cp) * j.CqPad + cq;
+        for (int k = lane; k < j.nsplit; k += WR_LANES) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)k * stride));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (lane == 0 && o < total4) {
+        float4 s4 = red[threadIdx.x];
+#pragma unroll
+        for (int l = 1; l < WR_LANES; ++l) {
+            const float4 v = red[threadIdx.x + l];
+            s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+        }
+        const float vals[4] = {s4.x, s4.y, s4.z, s4.w};
+        for (int e = 0; e < 4 && cq + e < j.Cq; ++e)
+            j.dst[(size_t)t * j.st + (size_t)cp * j.sp + (size_t)(cq + e) * j.sq] = vals[e];
+    }
+}
+
 __global__ void vec_reduce_kernel(const float* __restrict__ partial, int nsplit, int C, int Cpad, float* __restrict__ dst) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -538,6 +582,25 @@ extern "C" int lf_wgrad_reduce(const float* partial, int nsplit, int ntaps, int 
     const int per_block = 256 / WR_LANES;
     wgrad_reduce_kernel<<<(total4 + per_block - 1) / per_block, 256, 0, stream>>>(partial, nsplit, ntaps, Cp, Cq, CpPad, CqPad,
                                                                                    dst, st, sp, sq);
+    return check_launch();
+}
+
+extern "C" int lf_reduce_multi(const LfReduceJob* jobs, int njobs, lf_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    LF_REQUIRE(jobs && njobs >= 1 && njobs <= LF_REDUCE_MAX_JOBS);
+    ReduceJobs js{};
+    js.njobs = njobs;
+    int max_blocks = 1;
+    const int per_block = 256 / WR_LANES;
+    for (int i = 0; i < njobs; ++i) {
+        const LfReduceJob& j = jobs[i];
+        LF_REQUIRE(j.partial && j.dst && j.nsplit >= 1 && j.ntaps >= 1 && j.Cp >= 1 && j.Cq >= 1 && j.CqPad % 4 == 0);
+        js.job[i] = j;
+        const int total4 = j.ntaps * j.Cp * ((j.Cq + 3) / 4);
+        const int nb = (total4 + per_block - 1) / per_block;
+        if (nb > max_blocks) max_blocks = nb;
+    }
+    reduce_multi_kernel<<<dim3(max_blocks, njobs), 256, 0, stream>>>(js);
     return check_launch();
 }
 

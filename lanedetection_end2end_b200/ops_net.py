@@ -435,8 +435,38 @@ def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_s
     a.relu = int(relu)
     _capi.call("lf_conv1d_tc", ctypes.byref(a), _stream(), flops=2 * N * H * W * 3 * C * C, nbytes=8 * N * H * W * C)
     if part is not None:
-        _capi.call("lf_vec_reduce", ptr(part), rows, C, C, ptr(colsum), _stream())
+        if _DEFERRED is not None:
+            _reduce(part, rows, 1, 1, C, 1, C, colsum, 0, 0, 1)
+        else:
+            _capi.call("lf_vec_reduce", ptr(part), rows, C, C, ptr(colsum), _stream())
     return out
+
+
+# Deferred split reductions: inside Nb1dFunction.backward the weight / bias gradient reductions of the block are
+# collected here and run by ONE lf_reduce_multi launch at the end (instead of six ~12 us launches).
+_DEFERRED = None
+
+
+def _reduce(partial, nsplit, ntaps, cp, cq, cp_pad, cq_pad, dst, st, sp, sq):
+    if _DEFERRED is not None:
+        _DEFERRED.append((partial, nsplit, ntaps, cp, cq, cp_pad, cq_pad, dst, st, sp, sq))
+        return
+    _capi.call("lf_wgrad_reduce", ptr(partial), nsplit, ntaps, cp, cq, cp_pad, cq_pad, ptr(dst), st, sp, sq, _stream())
+
+
+def flush_deferred_reductions(jobs):
+    for k in range(0, len(jobs), _capi.REDUCE_MAX_JOBS):
+        chunk = jobs[k:k + _capi.REDUCE_MAX_JOBS]
+        arr = (_capi.LfReduceJob * len(chunk))()
+        for j, (partial, nsplit, ntaps, cp, cq, cp_pad, cq_pad, dst, st, sp, sq) in zip(arr, chunk):
+            j.partial, j.dst = partial.data_ptr(), dst.data_ptr()
+            j.nsplit, j.ntaps, j.Cp, j.Cq, j.CpPad, j.CqPad, j.st, j.sp, j.sq = nsplit, ntaps, cp, cq, cp_pad, cq_pad, st, sp, sq
+        _capi.call("lf_reduce_multi", arr, len(chunk), _stream())
+
+
+def _super_conv_launch(taps, xs, w, vertical, transposed, out, N, H, W, C, cs, epi_s):
+    run_conv_tc(taps, xs, packed(w, "tc_super_%d%d" % (vertical, transposed), lambda t: pack_tc_super(t, vertical, transposed)),
+                out.view(N, H, W // SUPER, SUPER * C), colsum=cs, **epi_s)
 
 
 def conv3(x, w, vertical, dil, transposed, colsum=None, **epi):
@@ -453,8 +483,12 @@ def conv3(x, w, vertical, dil, transposed, colsum=None, **epi):
         if epi_s.get("bias") is not None:
             epi_s["bias"] = epi_s["bias"].repeat(SUPER)
         cs = torch.empty(SUPER * C, dtype=torch.float32, device=x.device) if colsum is not None else None
-        run_conv_tc(taps, xs, packed(w, "tc_super_%d%d" % (vertical, transposed), lambda t: pack_tc_super(t, vertical, transposed)), out.view(N, H, W // SUPER, SUPER * C), colsum=cs,
-                    **epi_s)
+        global _DEFERRED
+        saved, _DEFERRED = _DEFERRED, None     # the column sums are post-processed right below: reduce them now
+        try:
+            _super_conv_launch(taps, xs, w, vertical, transposed, out, N, H, W, C, cs, epi_s)
+        finally:
+            _DEFERRED = saved
         if colsum is not None:
             colsum.copy_(cs.view(SUPER, C).sum(0))
         return out
@@ -510,7 +544,7 @@ def wgrad3(x_in, d_out, w, vertical, dil, bias_grad="compute"):
         st = _stream()
         _capi.call("lf_wgrad3_tc", ptr(x_in), ptr(d_out), N, H, W, C, tdy, tdx, ptr(partial), nctas, st,
                    flops=2 * N * H * W * 3 * C * C, nbytes=8 * N * H * W * C)
-        _capi.call("lf_wgrad_reduce", ptr(partial), nctas, 3, C, C, C, C, ptr(dw), lay[0], lay[1], lay[2], st)
+        _reduce(partial, nctas, 3, C, C, C, C, dw, lay[0], lay[1], lay[2])
         if db is not None:
             run_colsum(d_out, C, 0, db)
         return dw, db
@@ -762,6 +796,16 @@ class Nb1dFunction(torch.autograd.Function):
         s1, s2 = BNState(), BNState()
         s1.mean, s1.invstd, s2.mean, s2.invstd = m1, is1, m2, is2
 
+        global _DEFERRED
+        _DEFERRED = jobs = []
+        try:
+            return Nb1dFunction._backward_body(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1, s2, drop, dil, dy, jobs)
+        finally:
+            _DEFERRED = None
+
+    @staticmethod
+    def _backward_body(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1, s2, drop, dil, dy, jobs):
+        N, H, W, C = x.shape
         # y = relu(bn2(t5)*drop + x)
         d5, dg2, dbe2 = bn_backward(dy, y, drop, t5, s2, g2)
         # Bias gradients.  conv1x3_1 / conv1x3_2 feed a BatchNorm: sum_pixels(BN backward output) == 0
@@ -784,6 +828,8 @@ class Nb1dFunction(torch.autograd.Function):
         # conv3x1_1, plus the residual branch: dx = dgrad + dy*(y>0)
         dw1, _ = wgrad3(x, d1, w1, True, 1, bias_grad="skip")
         dx = conv3(d1, w1, True, 1, True, add_src=dy, add_mask=y)
+        if jobs:
+            flush_deferred_reductions(jobs)
         return (dx, dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2, None, None, None, None, None, None,
                 None)
 
