@@ -153,6 +153,11 @@ typedef struct LfConvTcArgs {
     double* stats_partial; /* NULL, or [lf_conv1d_tc_supported(...)][2][C]: per-CTA sum and sum of squares of `out`
                               = the `partial` input of lf_bn_finalize (replaces an lf_bn_stats pass over `out`);
                               LF_ERR_UNSUPPORTED when the launch has to use the per-tap variant */
+    const float* stats_beta; /* NULL, or [C] (needs mask_src and stats_partial): the second statistic becomes
+                              sum(out * (mask_src - stats_beta[c])) instead of sum(out^2).  With mask_src = relu(bn(x))
+                              and stats_beta = the BatchNorm bias, mask_src - beta == gamma * xhat wherever out != 0,
+                              so the launch that produces the gradient w.r.t. relu(bn(x)) also delivers BatchNorm
+                              backward's two reductions (lf_bn_bwd_finalize_masked) without a pass over x. */
     int N, H, W, C;
     int dy[3], dx[3];
     int relu;
@@ -248,6 +253,12 @@ int lf_bn_bwd_reduce(const float* dy, const float* ymask, const float* drop, con
                      lf_stream_t stream);
 int lf_bn_bwd_finalize(const double* partial, int nblk, long long npix, int C, float* dgamma, float* dbeta,
                        float* c1, float* c2, lf_stream_t stream);
+/* Finalize for statistics gathered by lf_conv1d_tc with stats_beta: partial[nblk][2][C*fold] holds
+ * sum g and sum g*(y - beta) = gamma * sum g*xhat per (folded) channel; fold > 1 sums `fold` consecutive groups of C
+ * channels (super-pixel launches).  gamma[c] == 0 makes sum g*xhat unrecoverable: *status |= status_bit. */
+int lf_bn_bwd_finalize_masked(const double* partial, int nblk, long long npix, int C, int fold, const float* gamma,
+                              float* dgamma, float* dbeta, float* c1, float* c2, int* status, int status_bit,
+                              lf_stream_t stream);
 int lf_bn_bwd_apply(const float* dy, const float* ymask, const float* drop, const float* x, long long npix,
                     int C, int pix_per_image, const float* mean, const float* invstd, const float* gamma,
                     const float* c1, const float* c2, float* dx, lf_stream_t stream);

@@ -62,6 +62,7 @@ struct TcArgs {
     const float* add_mask;
     float* colsum_partial;  // [gridDim.x / n_halves][Ctot] per-CTA column sums of the output, or NULL
     double* stats_partial;  // [gridDim.x / n_halves][2][Ctot] per-CTA sum and sum of squares (BatchNorm), or NULL
+    const float* stats_beta;  // non-NULL: second statistic = sum out*(mask - beta[c])  (BatchNorm backward)
     int N, H, W, Ctot;
     int vertical;           // conv axis: 1 = y (3x1), 0 = x (1x3)
     int TA, TB;             // tile extent along / across the conv axis (TA*TB = 128)
@@ -83,7 +84,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 <<17, M>>4 <<24
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
 
-template <int C>
+template <int C, bool AHEAD = false>
 struct TcCfg {
     static constexpr int KCHUNKS = C / TC_KCH;  // 32-channel chunks (= slabs per tile)
     static constexpr int B_BYTES = 3 * KCHUNKS * TC_B_ATOM_BYTES;
@@ -91,16 +92,21 @@ struct TcCfg {
     // C=128 tile but the same 128x64 output, so one group cannot drain the accumulator as fast as the tensor
     // pipe fills it (measured: epilogue-bound at 1.5-2.4x the MMA floor); two groups each take one 32-channel
     // half with their own staging tile.  At C=128 the shared memory goes to slab stages instead.
-    static constexpr int EPI_GROUPS = (C == 64) ? 2 : 1;
+    // The residual-add launches (AHEAD) of C=128 also run two groups: they are epilogue-bound (two extra operand
+    // tensors per tile) and the second group's 18 KB staging tile costs one slab stage.
+    static constexpr int EPI_GROUPS = (C == 64 || AHEAD) ? 2 : 1;
     static constexpr int HALVES = 2 / EPI_GROUPS;  // 32-channel halves each group walks per tile
     static constexpr int THREADS = 64 + 128 * EPI_GROUPS;
     static constexpr int STG_BYTES = EPI_GROUPS * TC_STG_BYTES;
 };
 
-template <int C>
-__global__ void __launch_bounds__(TcCfg<C>::THREADS, 1)
+// AHEAD (C=64 only): the residual-gradient operands (add_src, add_mask) of tile i+1 are fetched while tile i is
+// processed.  A separate instantiation because the extra 64 live registers cost the plain / mask-only launches
+// ~10 us each through spills (measured), while the add launches gain ~25 us.
+template <int C, bool AHEAD>
+__global__ void __launch_bounds__(TcCfg<C, AHEAD>::THREADS, 1)
 conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-    using Cfg = TcCfg<C>;
+    using Cfg = TcCfg<C, AHEAD>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sB = smem;
@@ -224,9 +230,14 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool pre_mask = a.mask_src != nullptr;
         const bool pre_add = (a.add_src != nullptr) && !pre_mask;  // both given: add_src is read in the loop
         float4 csum[NH], csq[NH];               // running column sums / sums of squares, per channel half
+        float4 sbeta[NH];                       // BatchNorm bias of this thread's columns (stats_beta mode)
 #pragma unroll
-        for (int hh = 0; hh < NH; ++hh) csum[hh] = csq[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 nxt_a[NH == 1 ? 8 : 1], nxt_m[NH == 1 ? 8 : 1];  // operands of the next tile in flight (C=64)
+        for (int hh = 0; hh < NH; ++hh) {
+            csum[hh] = csq[hh] = sbeta[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.stats_beta)
+                sbeta[hh] = __ldg(reinterpret_cast<const float4*>(a.stats_beta + n_half * TC_BN + 32 * (h_first + hh) + 4 * c4));
+        }
+        float4 nxt_a[AHEAD ? 8 : 1], nxt_m[AHEAD ? 8 : 1];  // operands of the next tile in flight
         int it = 0;
         for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
             const int buf = it & 1;
@@ -249,7 +260,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // tile of epilogue work (the epilogue, not the tensor pipe, bounds these layers).  Two halves per
             // thread (C=128): no registers for that; prefetch this tile's operands before waiting on the accumulator.
             float4 pre[NH][8];
-            if constexpr (NH == 1) {
+            if constexpr (NH == 1 && AHEAD) {
                 if (pre_mask || pre_add) {
                     auto issue = [&](int mtn) {
                         const int tan = mtn % a.tiles_a;
@@ -355,8 +366,14 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     *reinterpret_cast<float4*>(a.out + off) = o;
                     csum[hh].x += o.x; csum[hh].y += o.y; csum[hh].z += o.z; csum[hh].w += o.w;
-                    csq[hh].x = fmaf(o.x, o.x, csq[hh].x); csq[hh].y = fmaf(o.y, o.y, csq[hh].y);
-                    csq[hh].z = fmaf(o.z, o.z, csq[hh].z); csq[hh].w = fmaf(o.w, o.w, csq[hh].w);
+                    if (a.stats_beta) {   // pre_mask holds: pre[hh][j] is the mask operand relu(bn(x))
+                        const float4 mk = pre[hh][j];
+                        csq[hh].x = fmaf(o.x, mk.x - sbeta[hh].x, csq[hh].x); csq[hh].y = fmaf(o.y, mk.y - sbeta[hh].y, csq[hh].y);
+                        csq[hh].z = fmaf(o.z, mk.z - sbeta[hh].z, csq[hh].z); csq[hh].w = fmaf(o.w, mk.w - sbeta[hh].w, csq[hh].w);
+                    } else {
+                        csq[hh].x = fmaf(o.x, o.x, csq[hh].x); csq[hh].y = fmaf(o.y, o.y, csq[hh].y);
+                        csq[hh].z = fmaf(o.z, o.z, csq[hh].z); csq[hh].w = fmaf(o.w, o.w, csq[hh].w);
+                    }
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // staging half-tile may be overwritten
             }
@@ -404,7 +421,8 @@ struct TcPlan {
 };
 
 // Derive the plan from the public arguments; false = shape / tap pattern not served by this kernel.
-static bool tc_make_plan(int N, int H, int W, int C, const int* dy, const int* dx, TcPlan* p) {
+static bool tc_make_plan(int N, int H, int W, int C, const int* dy, const int* dx, TcPlan* p, int epi_groups = 0) {
+    if (epi_groups == 0) epi_groups = (C == 64) ? 2 : 1;
     if (!(C == 64 || C == 128) || N <= 0) return false;
     const bool vert = dy[0] != 0 || dy[2] != 0;
     const int* o = vert ? dy : dx;
@@ -428,7 +446,7 @@ static bool tc_make_plan(int N, int H, int W, int C, const int* dy, const int* d
     p->tiles_b = ext_b / p->TB;
     p->stage_bytes = (p->TA + 2 * p->dil) * p->TB * 128;
     const int b_bytes = 3 * (C / 32) * TC_B_ATOM_BYTES;
-    const int fixed = 1024 + b_bytes + (C == 64 ? 2 : 1) * TC_STG_BYTES + 512;  // alignment slack + B + epilogue staging + barriers
+    const int fixed = 1024 + b_bytes + epi_groups * TC_STG_BYTES + 512;  // alignment slack + B + epilogue staging + barriers
     int stages = (TC_SMEM_LIMIT - fixed) / p->stage_bytes;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return false;
@@ -473,11 +491,20 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     LF_REQUIRE(p.in && p.wpack && p.out);
     TcPlan pl;
     if (!tc_make_plan(p.N, p.H, p.W, p.C, p.dy, p.dx, &pl)) return lf_conv1d_tc_v1(args, stream_);
+    // residual-add launches: operands one tile ahead + two epilogue groups (if the extra staging tile still leaves
+    // two slab stages at C=128)
+    bool ahead = p.add_src && !p.mask_src;
+    if (ahead && p.C == 128) {
+        TcPlan pl2;
+        if (tc_make_plan(p.N, p.H, p.W, p.C, p.dy, p.dx, &pl2, 2)) pl = pl2; else ahead = false;
+    }
     TcEncodeTiledFn enc = tc_get_encode_fn();
     TcArgs a{};
     a.out = p.out; a.bias = p.bias; a.mask_src = p.mask_src; a.add_src = p.add_src; a.add_mask = p.add_mask;
     a.colsum_partial = p.colsum_partial;
     a.stats_partial = p.stats_partial;
+    a.stats_beta = p.stats_beta;
+    LF_REQUIRE(!p.stats_beta || (p.mask_src && p.stats_partial));
     a.N = p.N; a.H = p.H; a.W = p.W; a.Ctot = p.C; a.relu = p.relu;
     a.vertical = pl.vertical; a.TA = pl.TA; a.TB = pl.TB; a.dil = pl.dil;
     a.tiles_a = pl.tiles_a; a.tiles_b = pl.tiles_b;
@@ -514,14 +541,22 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     }
     const int grid = pl.m_ctas * a.n_halves;
     cudaError_t e;
-    if (p.C == 128) {
-        e = cudaFuncSetAttribute(conv1d_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    if (p.C == 128 && ahead) {
+        e = cudaFuncSetAttribute(conv1d_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_kernel<128><<<grid, TcCfg<128>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
+        conv1d_tc_kernel<128, true><<<grid, TcCfg<128, true>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
+    } else if (p.C == 128) {
+        e = cudaFuncSetAttribute(conv1d_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
+        conv1d_tc_kernel<128, false><<<grid, TcCfg<128>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
+    } else if (ahead) {
+        e = cudaFuncSetAttribute(conv1d_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+        if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
+        conv1d_tc_kernel<64, true><<<grid, TcCfg<64, true>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
     } else {
-        e = cudaFuncSetAttribute(conv1d_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+        e = cudaFuncSetAttribute(conv1d_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_kernel<64><<<grid, TcCfg<64>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
+        conv1d_tc_kernel<64, false><<<grid, TcCfg<64>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
     }
     return check_launch();
 }

@@ -411,7 +411,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
         t = o / (Cq4 * Cp);
         const size_t stride = (size_t)ntaps * CpPad * CqPad;
         const float* p = partial + ((size_t)t * CpPad + cp) * CqPad + cq;   // CqPad % 64 == 0 -> 16B aligned
-        for (int k = lane; k < nsplit; k += WR_LANES) {
+        int k = lane;
+        for (; k + 3 * WR_LANES < nsplit; k += 4 * WR_LANES) {   // 4 loads in flight per lane, fixed order
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + (size_t)k * stride));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(k + WR_LANES) * stride));
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(k + 2 * WR_LANES) * stride));
+            const float4 v3 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(k + 3 * WR_LANES) * stride));
+            acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+            acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+        }
+        for (; k < nsplit; k += WR_LANES) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)k * stride));
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
@@ -452,7 +461,16 @@ __global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceJobs js) 
         t = o / (Cq4 * j.Cp);
         const size_t stride = (size_t)j.ntaps * j.CpPad * j.CqPad;
         const float* p = j.partial + ((size_t)t * j.CpPad + cp) * j.CqPad + cq;
-        for (int k = lane; k < j.nsplit; k += WR_LANES) {
+        int k = lane;
+        for (; k + 3 * WR_LANES < j.nsplit; k += 4 * WR_LANES) {   // 4 loads in flight per lane, fixed order
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(p + (size_t)k * stride));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(k + WR_LANES) * stride));
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(k + 2 * WR_LANES) * stride));
+            const float4 v3 = __ldg(reinterpret_cast<const float4*>(p + (size_t)(k + 3 * WR_LANES) * stride));
+            acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+            acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+        }
+        for (; k < j.nsplit; k += WR_LANES) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)k * stride));
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }

@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU session 12: batched block reductions (lf_reduce_multi), one-tile-ahead epilogue prefetch (C=64), conflict-free small wgrad.
+# GPU session 13: fused BN1 backward reductions in the dgrad epilogue, AHEAD instantiations for residual-add launches, unrolled finalize/reduce loops.
 set -x
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu --maxfail=60 -q > gpurun_out/pytest_gpu.log 2>&1; echo "gpu tests rc=$?" >> gpurun_out/pytest_gpu.log
