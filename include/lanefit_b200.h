@@ -305,6 +305,24 @@ typedef struct LfConvTcgArgs {
 int lf_conv_tcg_supported(int N, int Hs, int Ws, int Kc, int Ng);
 int lf_conv_tcg(const LfConvTcgArgs* args, lf_stream_t stream);
 
+/* Weight gradients of the same layers on tcgen05 (csrc/wgrad_tcg.cu), over the same views:
+ *   D[blk*32 + c][n] = sum_{img,y,x} A_{map[blk]}(img, y+dy[blk], x+dx[blk], cblk[blk]*32 + c) * B(img, y, x, n)
+ * for blk < nblocks (<= LF_WGRAD_TCG_MAX_BLOCKS), c < 32, n < Nn (multiple of 32, <= 128; ceil(nblocks/4)*Nn <= 512).
+ * partial: [nctas][nblocks*32][Nn] per-CTA partial sums (nctas from lf_wgrad_tcg_ctas); reduce with lf_wgrad_reduce
+ * (ntaps = 1, Cp = nblocks*32, Cq = Nn), then gather into [Co,Ci,3,3] (ops_net.wgrad_tcg_*). */
+#define LF_WGRAD_TCG_MAX_BLOCKS 24
+typedef struct LfWgradTcgArgs {
+    LfTcgView a[2];
+    LfTcgView b;
+    float* partial;
+    int N, Hs, Ws;
+    int Ka, Nn, nblocks;
+    int map[LF_WGRAD_TCG_MAX_BLOCKS], dy[LF_WGRAD_TCG_MAX_BLOCKS], dx[LF_WGRAD_TCG_MAX_BLOCKS], cblk[LF_WGRAD_TCG_MAX_BLOCKS];
+    int nctas;
+} LfWgradTcgArgs;
+int lf_wgrad_tcg_ctas(int N, int Hs, int Ws, int Ka, int Nn, int nblocks);
+int lf_wgrad_tcg(const LfWgradTcgArgs* args, lf_stream_t stream);
+
 /* Batched weight packing (host side: ops_net.WeightPackCache).  The reference keeps Conv2d / ConvTranspose2d
  * weights as [Co,Ci,kh,kw] (Networks/ERFNet.py:18-55 builds them with nn.Conv2d); every kernel above wants a
  * GEMM layout.  Each job gathers dst[k] = idx[k] >= 0 ? src[idx[k]] : 0 for k < n; one launch runs all jobs.

@@ -92,7 +92,18 @@ class LfReduceJob(ctypes.Structure):
                 ("CqPad", _i), ("st", _i), ("sp", _i), ("sq", _i)]
 
 
+WGRAD_TCG_MAX_BLOCKS = 24
+
+
+class LfWgradTcgArgs(ctypes.Structure):
+    _fields_ = [("a", LfTcgView * 2), ("b", LfTcgView), ("partial", _p), ("N", _i), ("Hs", _i), ("Ws", _i), ("Ka", _i),
+                ("Nn", _i), ("nblocks", _i), ("map", _i * WGRAD_TCG_MAX_BLOCKS), ("dy", _i * WGRAD_TCG_MAX_BLOCKS),
+                ("dx", _i * WGRAD_TCG_MAX_BLOCKS), ("cblk", _i * WGRAD_TCG_MAX_BLOCKS), ("nctas", _i)]
+
+
 _NET_PROTOS = {
+    "lf_wgrad_tcg_ctas": (_i, [_i, _i, _i, _i, _i, _i]),
+    "lf_wgrad_tcg": (_i, [ctypes.POINTER(LfWgradTcgArgs), _p]),
     "lf_reduce_multi": (_i, [ctypes.POINTER(LfReduceJob), _i, _p]),
     "lf_conv_tcg_supported": (_i, [_i, _i, _i, _i, _i]),
     "lf_conv_tcg": (_i, [ctypes.POINTER(LfConvTcgArgs), _p]),

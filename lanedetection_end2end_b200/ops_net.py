@@ -190,6 +190,81 @@ def run_tcg_s2convT(x, I, wgs, O, out, bias2=None):
     return out
 
 
+# weight gradients of the same layers (csrc/wgrad_tcg.cu): D[(t, k)][n] over the pair-pixel taps, then one gather
+_TCG_WGRAD_IDX = {}
+
+
+def _tcg_wgrad_index(kind, C, O, Nn, device):
+    """Gather indices from the reduced [6*2C][Nn] tap-major result into the reference weight layout.
+    kind "conv":  A = layer input (pair view, C channels), B = output gradient -> dW[O][C][3][3]   (row = t*2C + b*C + c, col = o)
+    kind "convT": A = output gradient (pair view, C = Cout_T channels), B = layer input -> dW[O=Cin_T][C][3][3] (col = o)"""
+    key = (kind, C, O, Nn, str(device))
+    if key not in _TCG_WGRAD_IDX:
+        idx = torch.empty(O, C, 3, 3, dtype=torch.long)
+        o = torch.arange(O).view(O, 1)
+        c = torch.arange(C).view(1, C)
+        for ky in range(3):
+            for kx, (dxi, b) in enumerate(((0, 1), (1, 0), (1, 1))):
+                idx[:, :, ky, kx] = ((2 * ky + dxi) * 2 * C + b * C + c) * Nn + o
+        _TCG_WGRAD_IDX[key] = idx.reshape(-1).to(device)
+    return _TCG_WGRAD_IDX[key]
+
+
+def wgrad_tcg_ok(a_t, C, b_t, Nn):
+    """A = dense [N,2Hs,2Ws,C] tensor (pair view 2C channels), B = [N,Hs,Ws,>=Nn] tensor."""
+    N, H2, W2, ca = a_t.shape
+    if not (CONV_MODE == "tf32" and ca == C and (2 * C) % 32 == 0 and H2 % 2 == 0 and W2 % 2 == 0 and Nn % 32 == 0 and Nn <= 128
+            and b_t.shape[-1] >= Nn and b_t.shape[1] == H2 // 2 and b_t.shape[2] == W2 // 2
+            and a_t.is_contiguous() and b_t.is_contiguous()):
+        return False
+    per_tap = (2 * C) // 32
+    taps_per_launch = 6 if ((6 * per_tap + 3) // 4) * Nn <= 512 and 6 * per_tap <= _capi.WGRAD_TCG_MAX_BLOCKS else 3
+    return int(_lib().lf_wgrad_tcg_ctas(N, H2 // 2, W2 // 2, 2 * C, Nn, taps_per_launch * per_tap)) > 0
+
+
+def run_wgrad_tcg(a_t, C, b_t, Nn):
+    """-> reduced [6*2C][Nn] tensor: row (t*2C + k) = sum over pixels of A_t(pixel + tap t)[k] * B(pixel)[:Nn]
+    with the six pair-pixel taps of TCG_S2CONV_TAPS."""
+    N, H2, W2, _ = a_t.shape
+    Hs, Ws = H2 // 2, W2 // 2
+    Ka = 2 * C
+    per_tap = Ka // 32
+    cb_tot = b_t.shape[-1]
+    taps_per_launch = 6 if ((6 * per_tap + 3) // 4) * Nn <= 512 and 6 * per_tap <= _capi.WGRAD_TCG_MAX_BLOCKS else 3
+    res = torch.empty(6 * Ka, Nn, dtype=torch.float32, device=a_t.device)
+    st = _stream()
+    for t0 in range(0, 6, taps_per_launch):
+        nblocks = taps_per_launch * per_tap
+        nctas = int(_lib().lf_wgrad_tcg_ctas(N, Hs, Ws, Ka, Nn, nblocks))
+        partial = torch.empty(nctas * nblocks * 32 * Nn, dtype=torch.float32, device=a_t.device)
+        a = _capi.LfWgradTcgArgs()
+        a.a[0] = _tcg_view(a_t, Hs, Ws, H2 * W2 * C, 2 * W2 * C, 2 * C)
+        a.a[1] = _tcg_view(a_t, Hs, Ws, H2 * W2 * C, 2 * W2 * C, 2 * C, W2 * C)
+        a.b = _tcg_view(b_t, Hs, Ws, Hs * Ws * cb_tot, Ws * cb_tot, cb_tot)
+        a.partial, a.N, a.Hs, a.Ws, a.Ka, a.Nn, a.nblocks, a.nctas = partial.data_ptr(), N, Hs, Ws, Ka, Nn, nblocks, nctas
+        for i in range(nblocks):
+            m, dy, dx = TCG_S2CONV_TAPS[t0 + i // per_tap]
+            a.map[i], a.dy[i], a.dx[i], a.cblk[i] = m, dy, dx, i % per_tap
+        _capi.call("lf_wgrad_tcg", ctypes.byref(a), st, flops=2 * N * Hs * Ws * nblocks * 32 * Nn,
+                   nbytes=4 * N * Hs * Ws * (nblocks * 32 + Nn))
+        _capi.call("lf_wgrad_reduce", ptr(partial), nctas, 1, nblocks * 32, Nn, nblocks * 32, Nn,
+                   res.data_ptr() + 4 * t0 * Ka * Nn, 0, Nn, 1, st)
+    return res
+
+
+def wgrad_tcg_conv(x, cin, dcat, cc):
+    """dW [cc, cin, 3, 3] of the stride-2 Conv2d (DownsamplerBlock): A = x, B = dcat[..., :pad32(cc)]."""
+    Nn = plans.pad_to(cc, 32)
+    res = run_wgrad_tcg(x, cin, dcat, Nn)
+    return res.reshape(-1)[_tcg_wgrad_index("conv", cin, cc, Nn, x.device)].view(cc, cin, 3, 3)
+
+
+def wgrad_tcg_convT(x, ci, du, co):
+    """dW [ci, co, 3, 3] of the stride-2 ConvTranspose2d (UpsamplerBlock): A = du (output gradient), B = x."""
+    res = run_wgrad_tcg(du, co, x, ci)
+    return res.reshape(-1)[_tcg_wgrad_index("convT", co, ci, ci, x.device)].view(ci, co, 3, 3)
+
+
 # --------------------------------------------------------------------------------------
 # one-launch weight packing
 # --------------------------------------------------------------------------------------
@@ -435,7 +510,8 @@ def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_s
     for t, (dy, dx) in enumerate(taps):
         a.dy[t], a.dx[t] = dy, dx
     a.relu = int(relu)
-    _capi.call("lf_conv1d_tc", ctypes.byref(a), _stream(), flops=2 * N * H * W * 3 * C * C, nbytes=8 * N * H * W * C)
+    n_operands = 2 + (mask_src is not None) + (add_src is not None) + (add_mask is not None)
+    _capi.call("lf_conv1d_tc", ctypes.byref(a), _stream(), flops=2 * N * H * W * 3 * C * C, nbytes=4 * n_operands * N * H * W * C)
     if part is not None:
         if _DEFERRED is not None:
             _reduce(part, rows, 1, 1, C, 1, C, colsum, 0, 0, 1)
@@ -790,7 +866,11 @@ class DownFunction(torch.autograd.Function):
         wplan = plans.conv_wgrad_plan(H, W, 3, 3, 2, 1, 1, 1, 1)
         cin_gemm = plans.pad_to(cin, 4)
         cq_gemm = plans.pad_to(cc, 4)
-        run_wgrad(wplan, x, cin_gemm, dcat, cq_gemm, 0, N, dw, (1, 9, cin * 9), db, cp_true=cin, cq_true=cc)
+        if cx == cin and wgrad_tcg_ok(x, cin, dcat, plans.pad_to(cc, 32)):
+            dw = wgrad_tcg_conv(x, cin, dcat, cc)
+            run_colsum(dcat, cc, 0, db)
+        else:
+            run_wgrad(wplan, x, cin_gemm, dcat, cq_gemm, 0, N, dw, (1, 9, cin * 9), db, cp_true=cin, cq_true=cc)
         dx = None
         if need_dx:
             dx = _empty((N, H, W, cx), x)
@@ -912,7 +992,10 @@ class UpFunction(torch.autograd.Function):
         s.mean, s.invstd = mean, invstd
         du, dgamma, dbeta = bn_backward(dy, y, None, u, s, gamma)
         dw, db = torch.empty_like(w), _empty((co,), x)
-        run_wgrad(plans.convT_wgrad_plan(H, W, 3, 1), x, ci, du, co, 0, N, dw, (1, co * 9, 9))
+        if wgrad_tcg_ok(du, co, x, ci):
+            dw = wgrad_tcg_convT(x, ci, du, co)
+        else:
+            run_wgrad(plans.convT_wgrad_plan(H, W, 3, 1), x, ci, du, co, 0, N, dw, (1, co * 9, 9))
         run_colsum(du, co, 0, db)
         if ci % 16 == 0 and tcg_s2conv_ok(du, co, ci):
             dx = run_tcg_s2conv(du, packed(w, "tcg_s2conv", pack_tcg_s2conv), ci, torch.empty_like(x))

@@ -38,7 +38,8 @@ def test_ctypes_struct_layout_matches_header():
     hdr = open(os.path.join(ROOT, "include", "lanefit_b200.h")).read()
     for cname, cls in (("LfConvArgs", _capi.LfConvArgs), ("LfWgradArgs", _capi.LfWgradArgs),
                        ("LfConvTcArgs", _capi.LfConvTcArgs), ("LfTcgView", _capi.LfTcgView),
-                       ("LfConvTcgArgs", _capi.LfConvTcgArgs), ("LfReduceJob", _capi.LfReduceJob)):
+                       ("LfConvTcgArgs", _capi.LfConvTcgArgs), ("LfReduceJob", _capi.LfReduceJob),
+                       ("LfWgradTcgArgs", _capi.LfWgradTcgArgs)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []

@@ -302,3 +302,34 @@ def test_fused_batchnorm_backward_in_dgrad_epilogue(C, H, W, dil):
         o.bn_status_word(x.device).zero_()
     finally:
         o.set_conv_mode("fp32")
+
+
+@pytest.mark.parametrize("kind,C,O,tot,H,W,N", [("conv", 16, 48, 64, 128, 256, 2), ("conv", 64, 64, 128, 64, 128, 3),
+                                                ("convT", 64, 128, 0, 32, 64, 2), ("convT", 16, 64, 0, 64, 128, 2)])
+def test_tcg_weight_gradients(kind, C, O, tot, H, W, N):
+    """lf_wgrad_tcg: weight gradients of the stride-2 Conv2d (A = input, B = output gradient) and of the stride-2
+    ConvTranspose2d (A = output gradient, B = input) vs autograd in fp64 (TF32-exact operands)."""
+    o = ops()
+    o.set_conv_mode("tf32")
+    try:
+        g = torch.Generator().manual_seed(C * 7 + O)
+        if kind == "conv":
+            x = tf32_exact(torch.randn(N, H, W, C, generator=g).cuda())
+            dcat = tf32_exact(torch.randn(N, H // 2, W // 2, tot, generator=g).cuda())
+            assert o.wgrad_tcg_ok(x, C, dcat, ((O + 31) // 32) * 32)
+            dw = o.wgrad_tcg_conv(x, C, dcat, O)
+            w = torch.zeros(O, C, 3, 3, dtype=torch.float64, device="cuda", requires_grad=True)
+            F.conv2d(x.permute(0, 3, 1, 2).double(), w, stride=2, padding=1).backward(dcat[..., :O].permute(0, 3, 1, 2).double())
+        else:
+            # C = Cout_T (channels of the output gradient), O = Cin_T
+            x = tf32_exact(torch.randn(N, H, W, O, generator=g).cuda())
+            du = tf32_exact(torch.randn(N, 2 * H, 2 * W, C, generator=g).cuda())
+            assert o.wgrad_tcg_ok(du, C, x, O)
+            dw = o.wgrad_tcg_convT(x, O, du, C)
+            w = torch.zeros(O, C, 3, 3, dtype=torch.float64, device="cuda", requires_grad=True)
+            F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), w, stride=2, padding=1, output_padding=1).backward(
+                du.permute(0, 3, 1, 2).double())
+        err = float((dw.double() - w.grad).abs().max() / w.grad.abs().max())
+        assert err < 2e-5, err
+    finally:
+        o.set_conv_mode("fp32")

@@ -316,3 +316,95 @@ def test_tcg_pair_pixel_forms_match_torch_convs(monkeypatch):
         xin = x.permute(0, 3, 1, 2).double().requires_grad_(True)
         F.conv_transpose2d(xin, w.double(), stride=2, padding=1, output_padding=1).backward(du.permute(0, 3, 1, 2).double())
         assert torch.allclose(dx.double(), xin.grad.permute(0, 2, 3, 1), atol=1e-5), (I, O)
+
+
+def _emulate_wgrad_tcg(a, tensors):
+    """CPU restatement of the lf_wgrad_tcg contract: every CTA's partial holds 1/nctas of the total (so that the
+    reduction that follows is exercised), computed in fp64."""
+    def locate(ptr):
+        for t in tensors:
+            if t.data_ptr() <= ptr < t.data_ptr() + t.numel() * 4:
+                return t, (ptr - t.data_ptr()) // 4
+        raise AssertionError("pointer outside the known tensors")
+
+    def gather(v, dy, dx, c0, nc):
+        base, off = locate(v.ptr)
+        flat = base.reshape(-1).double()
+        ys, xs = torch.arange(a.Hs) + dy, torch.arange(a.Ws) + dx
+        ok = ((ys >= 0) & (ys < v.H)).view(1, -1, 1, 1) & ((xs >= 0) & (xs < v.W)).view(1, 1, -1, 1)
+        idx = (off + torch.arange(a.N).view(-1, 1, 1, 1) * v.sn + ys.clamp(0, v.H - 1).view(1, -1, 1, 1) * v.sy
+               + xs.clamp(0, v.W - 1).view(1, 1, -1, 1) * v.sx + (c0 + torch.arange(nc)).view(1, 1, 1, -1))
+        return flat[idx] * ok
+
+    B = gather(a.b, 0, 0, 0, a.Nn)
+    D = torch.zeros(a.nblocks * 32, a.Nn, dtype=torch.float64)
+    for blk in range(a.nblocks):
+        A = gather(a.a[a.map[blk]], a.dy[blk], a.dx[blk], a.cblk[blk] * 32, 32)
+        D[blk * 32:(blk + 1) * 32] = torch.einsum("nyxc,nyxo->co", A, B)
+    pt, poff = locate(a.partial)
+    part = pt.reshape(-1)[poff:poff + a.nctas * D.numel()].view(a.nctas, *D.shape)
+    part[:] = (D / a.nctas).float()
+
+
+def test_tcg_weight_gradients_match_torch(monkeypatch):
+    """wgrad_tcg_conv / wgrad_tcg_convT (pair-pixel taps, block lists, split launches, partial reduction, final gather)
+    against autograd's weight gradients of the stride-2 Conv2d / ConvTranspose2d, with the kernel replaced by a literal
+    restatement of its contract."""
+    import ctypes
+    import torch.nn.functional as F
+    from lanedetection_end2end_b200 import ops_net as o, _capi
+    live = []
+
+    class FakeLib:
+        @staticmethod
+        def lf_wgrad_tcg_ctas(N, Hs, Ws, Ka, Nn, nblocks):
+            return 3 if ((nblocks + 3) // 4) * Nn <= 512 else 0
+
+    def fake_call(name, *args, **kw):
+        if name == "lf_wgrad_tcg":
+            _emulate_wgrad_tcg(args[0]._obj, live)
+        elif name == "lf_wgrad_reduce":
+            partial, nsplit, ntaps, cp, cq, cpp, cqp, dst, st_, sp, sq, _stream = args
+            src = next(t for t in live if t.data_ptr() == partial)
+            red = src.view(nsplit, cp, cq).double().sum(0).float()
+            res = next(t for t in live if t.data_ptr() <= dst < t.data_ptr() + t.numel() * 4)
+            off = (dst - res.data_ptr()) // 4
+            res.reshape(-1)[off:off + cp * cq] = red.reshape(-1)
+        else:
+            raise AssertionError(name)
+
+    real_empty = torch.empty
+
+    def tracking_empty(*a_, **kw):
+        t = real_empty(*a_, **kw)
+        live.append(t)
+        return t
+
+    monkeypatch.setattr(o, "_stream", lambda: None)
+    monkeypatch.setattr(o, "_lib", lambda: FakeLib)
+    monkeypatch.setattr(o, "ptr", lambda t: t.data_ptr() if t is not None else None)
+    monkeypatch.setattr(_capi, "call", fake_call)
+    monkeypatch.setattr(o, "CONV_MODE", "tf32")
+    monkeypatch.setattr(torch, "empty", tracking_empty)
+    g = torch.Generator().manual_seed(11)
+    for (C, O, tot, H, W) in [(16, 48, 64, 16, 32), (64, 64, 128, 8, 16)]:
+        N = 2
+        x = torch.randn(N, H, W, C, generator=g)
+        dcat = torch.randn(N, H // 2, W // 2, tot, generator=g)
+        live[:] = [x, dcat]
+        assert o.wgrad_tcg_ok(x, C, dcat, ((O + 31) // 32) * 32)
+        dw = o.wgrad_tcg_conv(x, C, dcat, O)
+        w = torch.zeros(O, C, 3, 3, dtype=torch.float64, requires_grad=True)
+        F.conv2d(x.permute(0, 3, 1, 2).double(), w, stride=2, padding=1).backward(dcat[..., :O].permute(0, 3, 1, 2).double())
+        assert torch.allclose(dw.double(), w.grad, atol=1e-4, rtol=1e-5), (C, O)
+    for (I, O, H, W) in [(128, 64, 4, 8), (64, 16, 8, 16)]:
+        N = 2
+        x = torch.randn(N, H, W, I, generator=g)
+        du = torch.randn(N, 2 * H, 2 * W, O, generator=g)
+        live[:] = [x, du]
+        assert o.wgrad_tcg_ok(du, O, x, I)
+        dw = o.wgrad_tcg_convT(x, I, du, O)
+        w = torch.zeros(I, O, 3, 3, dtype=torch.float64, requires_grad=True)
+        F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), w, stride=2, padding=1, output_padding=1).backward(
+            du.permute(0, 3, 1, 2).double())
+        assert torch.allclose(dw.double(), w.grad, atol=1e-4, rtol=1e-5), (I, O)
