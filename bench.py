@@ -196,6 +196,21 @@ def run_reference_arm(a, cfg):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def _arm_watchdog(seconds):
+    """A hung collective must not burn the box: after `seconds` of wall clock dump the stacks and exit non-zero."""
+    import faulthandler
+    import signal
+
+    def on_alarm(signum, frame):
+        sys.stderr.write("bench.py watchdog: no result after %d s, aborting\n" % seconds)
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        sys.stderr.flush()
+        os._exit(3)
+
+    signal.signal(signal.SIGALRM, on_alarm)
+    signal.alarm(seconds)
+
+
 def run_ours(a, cfg):
     import torch
     import torch.distributed as dist
@@ -280,16 +295,25 @@ def run_ours(a, cfg):
     gstep = None
     if a.graph:
         from lanedetection_end2end_b200.engine import GraphedTrainStep
+        ok = 1
         try:
-            gstep = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, reducer)
+            gstep = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, reducer,
+                                     capture_error_mode="thread_local" if world > 1 else "global")
+        except Exception as e:        # capture failed: report it and measure eagerly instead
+            sys.stderr.write("CUDA graph capture failed (%s: %s); falling back to eager launches\n" % (type(e).__name__, e))
+            ok = 0
+            torch.cuda.synchronize()
+        if world > 1:                 # every rank must take the same path (the graph holds the all-reduce)
+            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if ok:
             for _ in range(max(a.warmup, 3)):
                 gstep()
             barrier()
-        except Exception as e:        # capture failed: report it and measure eagerly instead
-            sys.stderr.write("CUDA graph capture failed (%s: %s); falling back to eager launches\n" % (type(e).__name__, e))
+        else:
             gstep = None
             a.graph = False
-            torch.cuda.synchronize()
 
     def dev_step():
         if gstep is not None:
@@ -347,10 +371,12 @@ def run_ours(a, cfg):
     # one traced step: CUDA events around every C-ABI launch on the launching stream
     table, roofline, roofline_lsq = None, None, None
     peaks = load_peaks()
+    # every rank runs the step (it contains the gradient all-reduce); only rank 0 records the events
     if rank == 0:
         _capi.TRACE = []
-        step(dx, dxgt, dvalid)
-        torch.cuda.synchronize()
+    step(dx, dxgt, dvalid)
+    torch.cuda.synchronize()
+    if rank == 0:
         trace, _capi.TRACE = _capi.TRACE, None
         agg = {}
         for name, e0, e1, flops, nbytes in trace:
@@ -456,7 +482,11 @@ def main():
                     help="skip the extra fp32 (CUDA-core, 1e-4-parity) timing reported next to the tf32 headline")
     ap.add_argument("--conv-mode", dest="conv_mode", default=os.environ.get("LANEFIT_CONV_MODE", "tf32"),
                     choices=["fp32", "tf32"], help="fp32 = CUDA-core parity mode, tf32 = tcgen05 tensor cores")
+    ap.add_argument("--max-seconds", dest="max_seconds", type=int, default=int(os.environ.get("LANEFIT_BENCH_MAX_SECONDS", "600")),
+                    help="wall-clock watchdog: abort (exit 3, stacks on stderr) instead of hanging the box")
     a = ap.parse_args()
+    if a.max_seconds > 0:
+        _arm_watchdog(a.max_seconds)
     cfg = dict(CONFIGS[a.config])
     if a.batch:
         cfg["batch"] = a.batch

@@ -22,26 +22,45 @@ class FlatGradAllReduce:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
 
+    def attach(self):
+        """Make every existing ``p.grad`` a view into the flat buffer (like DDP's gradient_as_bucket_view): backward then
+        accumulates straight into the buffer and a step needs no pack / unpack copies at all.  Call after a backward
+        (so the gradients exist) and keep the gradients alive (zero them in place, never ``set_to_none``)."""
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            if p.grad is not None:
+                v.copy_(p.grad)
+                p.grad = v
+        self.attached = True
+
+    def _is_attached(self):
+        return getattr(self, "attached", False) and all(
+            p.grad is None or p.grad.data_ptr() == v.data_ptr() for p, v in zip(self.params, self.views))
+
     def pack(self):
+        have = [(v, p.grad) for p, v in zip(self.params, self.views) if p.grad is not None]
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()
-            else:
-                v.copy_(p.grad)
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])     # one fused launch
 
     def unpack(self):
-        for p, v in zip(self.params, self.views):
-            if p.grad is not None:
-                p.grad.copy_(v)
+        have = [(p.grad, v) for p, v in zip(self.params, self.views) if p.grad is not None]
+        if have:
+            torch._foreach_copy_([g for g, _ in have], [v for _, v in have])
 
     def __call__(self):
         """Average gradients over the group; returns the flat buffer (for tests)."""
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        self.pack()
+        attached = self._is_attached()
+        if not attached:
+            self.pack()
         if world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.mul_(1.0 / world)
-        self.unpack()
+        if not attached:
+            self.unpack()
         return self.flat
 
 

@@ -14,7 +14,8 @@ import torch
 
 
 class GraphedTrainStep:
-    def __init__(self, model, criterion, nclasses, example_x, example_xgt, example_valid, reducer=None, warmup=3):
+    def __init__(self, model, criterion, nclasses, example_x, example_xgt, example_valid, reducer=None, warmup=3,
+                 capture_error_mode="global"):
         self.model = model
         self.crit = criterion
         self.L = nclasses
@@ -35,9 +36,13 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         # gradients now exist as persistent tensors; the captured step zeroes and re-accumulates them
+        if reducer is not None and hasattr(reducer, "attach"):
+            reducer.attach()          # gradients become views of the flat all-reduce buffer: no pack / unpack copies
         self.grads = [p.grad for p in self.params if p.grad is not None]
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # with NCCL in the graph use capture_error_mode="thread_local": the process group's watchdog thread polls CUDA
+        # events, which the default "global" mode treats as a capture violation
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.loss = self._eager_step(first=False)
         self.status = model.lsq_status
 

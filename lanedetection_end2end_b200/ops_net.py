@@ -210,10 +210,13 @@ def _tcg_wgrad_index(kind, C, O, Nn, device):
     return _TCG_WGRAD_IDX[key]
 
 
+WGRAD_TCG = os.environ.get("LANEFIT_WGRAD_TCG", "1") != "0"
+
+
 def wgrad_tcg_ok(a_t, C, b_t, Nn):
     """A = dense [N,2Hs,2Ws,C] tensor (pair view 2C channels), B = [N,Hs,Ws,>=Nn] tensor."""
     N, H2, W2, ca = a_t.shape
-    if not (CONV_MODE == "tf32" and ca == C and (2 * C) % 32 == 0 and H2 % 2 == 0 and W2 % 2 == 0 and Nn % 32 == 0 and Nn <= 128
+    if not (WGRAD_TCG and CONV_MODE == "tf32" and ca == C and (2 * C) % 32 == 0 and H2 % 2 == 0 and W2 % 2 == 0 and Nn % 32 == 0 and Nn <= 128
             and b_t.shape[-1] >= Nn and b_t.shape[1] == H2 // 2 and b_t.shape[2] == W2 // 2
             and a_t.is_contiguous() and b_t.is_contiguous()):
         return False

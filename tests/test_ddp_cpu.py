@@ -32,7 +32,18 @@ def _worker(rank, world, port, q):
     flat = red()
     # numpy arrays are pickled by value (torch tensors would be passed as shared-memory fds, which die
     # with this process)
-    q.put((rank, p0.numpy(), [None if g is None else g.numpy() for g in local], flat.numpy().copy(),
+    after = [None if p.grad is None else p.grad.numpy().copy() for p in net.parameters()]
+    flat1 = flat.numpy().copy()
+    # second step with the gradients ATTACHED to the flat buffer (what GraphedTrainStep does): backward accumulates
+    # straight into the buffer, the reducer only all-reduces
+    red.attach()
+    torch._foreach_zero_([p.grad for p in net.parameters() if p.grad is not None])
+    net[1](net[0](x * 2)).sum().backward()
+    assert all(p.grad is None or p.grad.data_ptr() == v.data_ptr() for p, v in zip(red.params, red.views))
+    local2 = [None if p.grad is None else p.grad.clone() for p in net.parameters()]
+    red()
+    q.put((rank, p0.numpy(), [None if g is None else g.numpy() for g in local], flat1, after,
+           [None if g is None else g.numpy() for g in local2],
            [None if p.grad is None else p.grad.numpy().copy() for p in net.parameters()]))
     dist.barrier()
     dist.destroy_process_group()
@@ -50,8 +61,12 @@ def test_flat_gradient_allreduce_two_ranks():
         p.join(60)
         assert p.exitcode == 0
     t = lambda v: None if v is None else torch.from_numpy(v)
-    res = [(r, t(p0), [t(x) for x in l], t(f), [t(x) for x in g]) for r, p0, l, f, g in res]
-    (_, p0a, la, fa, ga), (_, p0b, lb, fb, gb) = res
+    res = [(r, t(p0), [t(x) for x in l], t(f), [t(x) for x in g], [t(x) for x in l2], [t(x) for x in g2])
+           for r, p0, l, f, g, l2, g2 in res]
+    (_, p0a, la, fa, ga, l2a, g2a), (_, p0b, lb, fb, gb, l2b, g2b) = res
+    for a2, b2, g2 in zip(l2a, l2b, g2a):             # attached step: same averaging, no pack / unpack
+        if a2 is not None:
+            torch.testing.assert_close(g2, (a2 + b2) / 2)
     assert torch.equal(p0a, p0b)                      # broadcast worked
     assert torch.equal(fa, fb)                        # every rank holds the same reduced buffer
     off = 0
