@@ -404,7 +404,7 @@ def run_ours(a, cfg):
         ach_f = d["flops"] / (d["ms"] * 1e-3) / 1e12
         common = {"kernel": dom, "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
                   "share_of_step": d["share"], "traffic": traffic,
-                  "traffic_source": "profiles/r01/ncu_conv_tc_final.json (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches)" if traffic else None}
+                  "traffic_source": "profiles/r01/ncu_conv_tc_final.json (dram__bytes_read.sum + dram__bytes_write.sum, mean over the 12 captured C=128 launches: 33.5 MB input read once, the 33.5 MB output stays in the 126 MB L2)" if traffic else None}
         hbm = dict(common, bound="hbm", achieved=ach_b, peak=hbm_peak, unit="GB/s", frac=ach_b / hbm_peak,
                    peak_source=peaks["_source"] + " (copy bandwidth)",
                    algorithmic="input + output (+ mask / residual operands) tensors, 4 B per element, per launch")
