@@ -209,6 +209,9 @@ def _arm_watchdog(seconds):
 
     signal.signal(signal.SIGALRM, on_alarm)
     signal.alarm(seconds)
+    # SIGALRM handlers only run between bytecodes: a main thread blocked inside a C++ call (NCCL teardown, a hung
+    # collective) never gets there.  faulthandler's watchdog is a C thread that needs neither the GIL nor the main thread.
+    faulthandler.dump_traceback_later(seconds + 15, exit=True, file=sys.stderr)
 
 
 def run_ours(a, cfg):
@@ -463,7 +466,16 @@ def run_ours(a, cfg):
                 if a.conv_mode == "tf32" else "fp32 mode: beta within 1e-6 norm-wise of the fp64 reference (tests/test_net_gpu.py)"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without ProcessGroupNCCL's teardown: with a captured graph still referencing the communicator
+        # destroy_process_group() blocked until the launcher's timeout (session 15: the JSON line was out, the process
+        # never exited).  Every rank is past its last collective here.
+        gstep = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
