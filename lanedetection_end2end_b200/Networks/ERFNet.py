@@ -27,15 +27,47 @@ def _track(bn, training):
             bn.num_batches_tracked += 1
 
 
+# ---------------------------------------------------------------------------------------------
+# parameter containers: layer specs -> torch modules (names / shapes / registration order fixed by the
+# reference's checkpoints; the modules' own forward() is never used)
+# ---------------------------------------------------------------------------------------------
+_BN_EPS = 1e-3
+
+
+def _conv(cin, cout, kernel, stride=1, pad=0, dil=1):
+    return nn.Conv2d(cin, cout, kernel, stride=stride, padding=pad, dilation=dil, bias=True)
+
+
+def _batchnorm(c):
+    return nn.BatchNorm2d(c, eps=_BN_EPS)
+
+
+def _factorised_specs(d):
+    """(attribute, kernel, padding, dilation) of the four 1-D convolutions of a residual block with dilation d."""
+    return (("conv3x1_1", (3, 1), (1, 0), (1, 1)), ("conv1x3_1", (1, 3), (0, 1), (1, 1)),
+            ("conv3x1_2", (3, 1), (d, 0), (d, 1)), ("conv1x3_2", (1, 3), (0, d), (1, d)))
+
+
+# (kind, *args) per stage; "down"/"up": (cin, cout), "res": (channels, dropout p, dilation)
+_ENCODER_STAGES = ([("down", 16, 64)] + [("res", 64, 0.03, 1)] * 5 + [("down", 64, 128)]
+                   + [("res", 128, 0.3, d) for _ in range(2) for d in (2, 4, 8, 16)])
+_DECODER_STAGES = [("up", 128, 64), ("res", 64, 0, 1), ("res", 64, 0, 1), ("up", 64, 16), ("res", 16, 0, 1), ("res", 16, 0, 1)]
+
+
+def _build_stage(spec):
+    kind, args = spec[0], spec[1:]
+    return {"down": DownsamplerBlock, "up": UpsamplerBlock, "res": non_bottleneck_1d}[kind](*args)
+
+
 class DownsamplerBlock(nn.Module):
     """relu(bn(cat[conv3x3 stride 2 (x), maxpool2x2 (x)]))  (reference :11-22)."""
 
     def __init__(self, ninput, noutput):
         super().__init__()
-        self.conv = nn.Conv2d(ninput, noutput - ninput, (3, 3), stride=2, padding=1, bias=True)
-        self.pool = nn.MaxPool2d(2, stride=2)
-        self.bn = nn.BatchNorm2d(noutput, eps=1e-3)
         self.ninput = ninput
+        self.conv = _conv(ninput, noutput - ninput, 3, stride=2, pad=1)   # the other `ninput` channels come from the pool
+        self.pool = nn.MaxPool2d(2, stride=2)
+        self.bn = _batchnorm(noutput)
 
     def forward(self, input):
         need_dx = input.requires_grad and torch.is_grad_enabled()
@@ -57,16 +89,13 @@ class non_bottleneck_1d(nn.Module):
 
     def __init__(self, chann, dropprob, dilated):
         super().__init__()
-        self.conv3x1_1 = nn.Conv2d(chann, chann, (3, 1), stride=1, padding=(1, 0), bias=True)
-        self.conv1x3_1 = nn.Conv2d(chann, chann, (1, 3), stride=1, padding=(0, 1), bias=True)
-        self.bn1 = nn.BatchNorm2d(chann, eps=1e-03)
-        self.conv3x1_2 = nn.Conv2d(chann, chann, (3, 1), stride=1, padding=(1 * dilated, 0), bias=True,
-                                   dilation=(dilated, 1))
-        self.conv1x3_2 = nn.Conv2d(chann, chann, (1, 3), stride=1, padding=(0, 1 * dilated), bias=True,
-                                   dilation=(1, dilated))
-        self.bn2 = nn.BatchNorm2d(chann, eps=1e-03)
-        self.dropout = nn.Dropout2d(dropprob)
         self.dilated = dilated
+        specs = _factorised_specs(dilated)
+        for k, (attr, kernel, pad, dil) in enumerate(specs):
+            setattr(self, attr, _conv(chann, chann, kernel, pad=pad, dil=dil))
+            if k % 2 == 1:                                   # a BatchNorm after each (3x1, 1x3) pair: bn1, bn2
+                setattr(self, "bn%d" % (k // 2 + 1), _batchnorm(chann))
+        self.dropout = nn.Dropout2d(dropprob)
         self.drop_mask_override = None      # tests inject a fixed [N,C] mask here
 
     def _drop_mask(self, x):
@@ -96,25 +125,18 @@ class Encoder(nn.Module):
     def __init__(self, in_channels, num_classes):
         super().__init__()
         self.initial_block = DownsamplerBlock(in_channels, 16)
-        self.layers = nn.ModuleList()
-        self.layers.append(DownsamplerBlock(16, 64))
-        for _ in range(5):
-            self.layers.append(non_bottleneck_1d(64, 0.03, 1))
-        self.layers.append(DownsamplerBlock(64, 128))
-        for _ in range(2):
-            for d in (2, 4, 8, 16):
-                self.layers.append(non_bottleneck_1d(128, 0.3, d))
+        self.layers = nn.ModuleList(_build_stage(spec) for spec in _ENCODER_STAGES)
         # only used in encoder-only mode (reference :84,92-93); a 1x1 conv on 128 channels
-        self.output_conv = nn.Conv2d(128, num_classes, 1, stride=1, padding=0, bias=True)
+        self.output_conv = _conv(128, num_classes, 1)
 
     def forward(self, input, predict=False):
-        output = self.initial_block(input)
-        for layer in self.layers:
-            output = layer(output)
-        if predict:
-            # encoder-only pretraining head: not on the end-to-end hot path
-            output = torch.nn.functional.conv2d(output, self.output_conv.weight, self.output_conv.bias)
-        return output
+        feat = self.initial_block(input)
+        for stage in self.layers:
+            feat = stage(feat)
+        if not predict:
+            return feat
+        # encoder-only pretraining head: not on the end-to-end hot path
+        return torch.nn.functional.conv2d(feat, self.output_conv.weight, self.output_conv.bias)
 
 
 class UpsamplerBlock(nn.Module):
@@ -123,7 +145,7 @@ class UpsamplerBlock(nn.Module):
     def __init__(self, ninput, noutput):
         super().__init__()
         self.conv = nn.ConvTranspose2d(ninput, noutput, 3, stride=2, padding=1, output_padding=1, bias=True)
-        self.bn = nn.BatchNorm2d(noutput, eps=1e-3)
+        self.bn = _batchnorm(noutput)
 
     def forward(self, input):
         x = _ops.as_nhwc(input)
@@ -143,41 +165,28 @@ class _OutputConvT(nn.ConvTranspose2d):
 class Decoder(nn.Module):
     def __init__(self, num_classes, pretrain, do_segmentation=False):
         super().__init__()
+        def head(n_out):                 # 2x2 stride-2 transposed conv from the 16-channel decoder features
+            return _OutputConvT(16, n_out, 2, stride=2, padding=0, output_padding=0, bias=True)
+
         self.pretrain = pretrain
-        self.layers = nn.ModuleList()
-        self.layers.append(UpsamplerBlock(128, 64))
-        self.layers.append(non_bottleneck_1d(64, 0, 1))
-        self.layers.append(non_bottleneck_1d(64, 0, 1))
-        self.layers.append(UpsamplerBlock(64, 16))
-        self.layers.append(non_bottleneck_1d(16, 0, 1))
-        self.layers.append(non_bottleneck_1d(16, 0, 1))
-        self.output_conv = _OutputConvT(16, num_classes, 2, stride=2, padding=0, output_padding=0, bias=True)
+        self.layers = nn.ModuleList(_build_stage(spec) for spec in _DECODER_STAGES)
+        self.output_conv = head(num_classes)
         if pretrain:
-            self.output_conv2 = _OutputConvT(16, num_classes + 1, 2, stride=2, padding=0, output_padding=0, bias=True)
+            self.output_conv2 = head(num_classes + 1)
         self.do_segmentation = do_segmentation
-        if do_segmentation:
-            self.layers1 = nn.ModuleList()
-            self.layers1.append(UpsamplerBlock(128, 64))
-            self.layers1.append(non_bottleneck_1d(64, 0, 1))
-            self.layers1.append(non_bottleneck_1d(64, 0, 1))
-            self.layers1.append(UpsamplerBlock(64, 16))
-            self.layers1.append(non_bottleneck_1d(16, 0, 1))
-            self.layers1.append(non_bottleneck_1d(16, 0, 1))
-            self.layers1.append(_OutputConvT(16, num_classes + 1, 2, stride=2, padding=0, output_padding=0, bias=True))
+        if do_segmentation:              # second decoder for the segmentation branch (same stages + its own head)
+            self.layers1 = nn.ModuleList([_build_stage(spec) for spec in _DECODER_STAGES] + [head(num_classes + 1)])
 
     def forward(self, input, flag):
-        output = input
-        output_seg = input
-        for layer in self.layers:
-            output = layer(output)
-        if self.pretrain and not flag:
-            output = self.output_conv2(output)
-        else:
-            output = self.output_conv(output)
+        feat = input
+        for stage in self.layers:
+            feat = stage(feat)
+        head = self.output_conv2 if (self.pretrain and not flag) else self.output_conv
+        seg = input
         if self.do_segmentation:
-            for layer1 in self.layers1:
-                output_seg = layer1(output_seg)
-        return output, output_seg
+            for stage in self.layers1:
+                seg = stage(seg)
+        return head(feat), seg
 
 
 class Net(nn.Module):

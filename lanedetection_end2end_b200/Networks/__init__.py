@@ -4,16 +4,20 @@ from ._pkg import package as _package
 
 _package()          # make `lanedetection_end2end_b200` importable when used as top-level `Networks`
 
-from .ERFNet import Net  # noqa: E402
+from . import ERFNet as _erfnet  # noqa: E402
 
-model_dict = {"erfnet": Net}
+Net = _erfnet.Net
+model_dict = {"erfnet": Net}     # --mod value -> constructor
 
 
 def allowed_models():
+    """Names accepted by ``--mod`` (view of the registry keys, like the reference returns)."""
     return model_dict.keys()
 
 
 def define_model(mod, **kwargs):
-    if mod not in allowed_models():
-        raise KeyError("The requested model: {} is not implemented".format(mod))
-    return model_dict[mod](**kwargs)
+    try:
+        ctor = model_dict[mod]
+    except KeyError:
+        raise KeyError("The requested model: {} is not implemented".format(mod)) from None
+    return ctor(**kwargs)
