@@ -101,6 +101,9 @@ class non_bottleneck_1d(nn.Module):
     def _drop_mask(self, x):
         if self.drop_mask_override is not None:
             return self.drop_mask_override.to(device=x.device, dtype=torch.float32).contiguous()
+        pending = self.__dict__.pop("_pending_drop_mask", None)      # drawn for the whole net by fused_dropout_masks()
+        if pending is not None and self.training and pending.shape[0] == x.shape[0] and pending.device == x.device:
+            return pending
         p = self.dropout.p
         if not self.training or p == 0:
             return None
@@ -119,6 +122,33 @@ class non_bottleneck_1d(nn.Module):
         _track(self.bn1, self.training)
         _track(self.bn2, self.training)
         return _ops.as_nchw_view(y)
+
+
+_DROP_PLANS = {}
+
+
+def fused_dropout_masks(blocks, batch, device):
+    """Dropout2d channel masks ([batch, C] each, values 0 or 1/(1-p)) for all `blocks` from ONE uniform draw:
+    3 launches per step instead of ~4 per block (13 encoder blocks use dropout).  Each block receives a contiguous
+    slice of the flat result through ``_pending_drop_mask``."""
+    spec = tuple((b.conv3x1_1.out_channels, float(b.dropout.p)) for b in blocks)
+    key = (spec, batch, str(device))
+    plan = _DROP_PLANS.get(key)
+    if plan is None:
+        thr = torch.cat([torch.full((batch * c,), p) for c, p in spec])
+        scale = torch.cat([torch.full((batch * c,), 1.0 / (1.0 - p)) for c, p in spec])
+        plan = _DROP_PLANS[key] = (thr.to(device), scale.to(device))
+    thr, scale = plan
+    u = torch.rand(thr.numel(), device=device)
+    flat = (u >= thr).to(torch.float32) * scale
+    off = 0
+    masks = []
+    for (c, _), b in zip(spec, blocks):
+        m = flat[off:off + batch * c].view(batch, c)
+        off += batch * c
+        b.__dict__["_pending_drop_mask"] = m
+        masks.append(m)
+    return masks
 
 
 class Encoder(nn.Module):
@@ -210,6 +240,11 @@ class Net(nn.Module):
                 packs = self.__dict__["_weight_packs"] = _ops.WeightPackCache(self)
             packs.refresh()
             _ops.ACTIVE_PACKS = packs
+        if self.training and input.is_cuda:
+            drops = [m for m in self.modules() if isinstance(m, non_bottleneck_1d) and m.dropout.p > 0
+                     and m.drop_mask_override is None]
+            if drops:
+                fused_dropout_masks(drops, input.shape[0], input.device)
         try:
             encoder_output = self.encoder(input)
             decoder_output, output_seg = self.decoder.forward(encoder_output, flag)

@@ -154,3 +154,30 @@ def test_reference_main_imports_resolve_with_package_dir_on_path():
     out = subprocess.run([sys.executable, "-c", code % pkg], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0, out.stderr
     assert "erfnet" in out.stdout
+
+
+def test_fused_dropout_masks_statistics_and_layout():
+    """One uniform draw feeds the Dropout2d channel masks of every block (Networks/ERFNet.py: fused_dropout_masks):
+    right shapes, values in {0, 1/(1-p)}, keep rate ~ 1-p per block, reproducible under the global seed, and each
+    block consumes its mask exactly once."""
+    import torch
+    from lanedetection_end2end_b200.Networks import ERFNet as E
+    blocks = [E.non_bottleneck_1d(64, 0.03, 1) for _ in range(3)] + [E.non_bottleneck_1d(128, 0.3, 2) for _ in range(4)]
+    B = 64
+    torch.manual_seed(7)
+    masks = E.fused_dropout_masks(blocks, B, torch.device("cpu"))
+    torch.manual_seed(7)
+    again = E.fused_dropout_masks(blocks, B, torch.device("cpu"))
+    for b, m, m2 in zip(blocks, masks, again):
+        c, p = b.conv3x1_1.out_channels, b.dropout.p
+        assert m.shape == (B, c) and m.is_contiguous() and torch.equal(m, m2)
+        vals = set(torch.unique(m).tolist())
+        assert vals <= {0.0, float(torch.tensor(1.0 / (1.0 - p), dtype=torch.float32))}
+        keep = float((m > 0).float().mean())
+        assert abs(keep - (1 - p)) < 4 * (p * (1 - p) / (B * c)) ** 0.5 + 1e-3, (p, keep)
+        x = torch.zeros(B, 4, 4, c)                       # NHWC like the block sees it
+        b.train()
+        got = b._drop_mask(x)
+        assert got is m2                                   # the pending slice is handed out ...
+        fresh = b._drop_mask(x)
+        assert fresh is not m2 and fresh.shape == (B, c)   # ... exactly once; afterwards the block draws its own
