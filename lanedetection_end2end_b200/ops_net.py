@@ -936,7 +936,8 @@ class Nb1dFunction(torch.autograd.Function):
         # identically (the reference's autograd returns pure round-off there), so db2 = db4 = 0.
         # conv3x1_1 / conv3x1_2 feed a ReLU: db = column sums of the masked input gradient, which the
         # dgrad launch below accumulates in its epilogue (colsum=...).
-        db2, db4 = torch.zeros(C, device=x.device), torch.zeros(C, device=x.device)
+        zero2 = torch.zeros(2, C, device=x.device)           # one fill launch for both
+        db2, db4 = zero2[0], zero2[1]
         db1, db3 = _empty((C,), x), _empty((C,), x)
         # conv1x3_2 (dilated)
         dw4, _ = wgrad3(t4, d5, w4, False, dil, bias_grad="skip")
