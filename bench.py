@@ -461,8 +461,10 @@ def run_ours(a, cfg):
                 "clocks": clocks,
                 "algorithmic_tflops": (3 * gflop * imgs / 1e3) / (ms_dev * 1e-3) if gflop else None,
                 "roofline": roofline, "roofline_lsq": roofline_lsq, "cpu_baseline": cpu, "parity_mode": parity,
-                "accuracy": ("tf32 convs: beta within 5e-4 (order 2) / 2e-3 (order 3) norm-wise of the fp64 reference on the "
-                             "golden inputs (profiles/r01/tf32_accuracy_*.json); fp32 mode: 1e-6 (tests/test_net_gpu.py)")
+                "accuracy": ("tf32 convs: beta within 1.1e-3 (2 lanes, order 2) / 2.1e-3 (4 lanes, order 3) norm-wise of the fp64 "
+                             "reference on the golden inputs (profiles/r01/tf32_accuracy_*.json) -- the reference itself, with its "
+                             "convolutions in cuDNN's default TF32, deviates 7.5e-4 / 2.6e-3 (profiles/r01/"
+                             "tf32_reference_emulation_*.json); fp32 parity mode (parity_mode below): 1e-6 (tests/test_net_gpu.py)")
                 if a.conv_mode == "tf32" else "fp32 mode: beta within 1e-6 norm-wise of the fp64 reference (tests/test_net_gpu.py)"}
         print(json.dumps(line), flush=True)
     if world > 1:
