@@ -339,6 +339,21 @@ int lf_pack_gather(const LfPackJob* jobs_dev, int njobs, int blocks_per_job, lf_
 int lf_nhwc_to_nchw(const float* in, int N, int H, int W, int C, float* out, lf_stream_t stream);
 int lf_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out, lf_stream_t stream);
 
+/* Back-projection loss over all lanes, forward and gradient in one launch (replaces
+ * BP/Loss_crit.py:161-218 applied per lane and averaged as BP/main.py:297-305): float64 throughout.
+ *   Y56 [56][n], yprime [56], Minv [9] (row-major M^-1): HOST constants of the loss object (travel inside the launch);
+ *   beta [B][L][n], x_gt / valid [B][L][56]: DEVICE inputs;  lane_loss [L], loss [1]: DEVICE outputs,
+ *   loss = mean_l sum((x_gt - x_cal) valid)^2 / sum(valid)  (a lane with no valid sample contributes 0);
+ *   dbeta [B][L][n] = d loss / d beta (or NULL), xcal [B][L][56] = x_cal * valid (or NULL);
+ *   ticket: one zero-initialised device word (self-resetting).  No host synchronisation.
+ * lf_backproj_loss_host runs the SAME per-point code on host arrays: a test hook for the CPU suite, not a fallback. */
+int lf_backproj_loss(const double* Y56, const double* yprime, const double* Minv, const double* beta, const double* x_gt,
+                     const double* valid, int B, int L, int n, double* lane_loss, double* loss, double* dbeta, double* xcal,
+                     unsigned int* ticket, lf_stream_t stream);
+int lf_backproj_loss_host(const double* Y56, const double* yprime, const double* Minv, const double* beta, const double* x_gt,
+                          const double* valid, int B, int L, int n, double* lane_loss, double* loss, double* dbeta,
+                          double* xcal);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,22 @@ class backprojection_loss(nn.Module):
             self.y_prime, self.Y = self.y_prime.to(device), self.Y.to(device)
             self._dev = device
 
+    def _fused_host_constants(self):
+        """(Y56 [56, n], y' [56], M^-1 [9]) as contiguous float64 numpy arrays for lf_backproj_loss."""
+        c = self.__dict__.get("_fused_consts")
+        if c is None:
+            c = self.__dict__["_fused_consts"] = (
+                self.Y.detach().cpu().double().contiguous().numpy().copy(),
+                self.y_prime.detach().cpu().double().contiguous().numpy().copy(),
+                self.M_inv.detach().cpu().double().contiguous().numpy().reshape(-1).copy())
+        return c
+
+    def _fused_ticket(self, device):
+        t = self.__dict__.setdefault("_fused_tickets", {})
+        if device not in t:
+            t[device] = torch.zeros(1, dtype=torch.int32, device=device)
+        return t[device]
+
     def forward(self, params, x_gt, valid_samples):
         self._to(params.device)
         p = params.reshape(params.size(0), -1).double()
@@ -78,6 +94,46 @@ class backprojection_loss(nn.Module):
         # reference's host-side `if nvalid == 0` so the step has no sync and can live in a CUDA graph
         loss = torch.sum(x_err ** 2) / torch.where(nvalid == 0, torch.ones_like(nvalid), nvalid)
         return loss, x_cal * valid_samples
+
+
+class _FusedBackprojLoss(torch.autograd.Function):
+    """mean over lanes of backprojection_loss, forward + gradient in ONE launch (csrc/loss.cu: lf_backproj_loss)."""
+
+    @staticmethod
+    def forward(ctx, beta, x_gt, valid, crit):
+        import ctypes
+        if __package__:
+            from . import _capi
+        else:
+            import _capi
+        B, L, n = beta.shape
+        dev = beta.device
+        lane = torch.empty(L, dtype=torch.float64, device=dev)
+        loss = torch.empty(1, dtype=torch.float64, device=dev)
+        dbeta = torch.empty_like(beta)
+        xcal = torch.empty(B, L, 56, dtype=torch.float64, device=dev)
+        ticket = crit._fused_ticket(dev)
+        host = crit._fused_host_constants()
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _capi.call("lf_backproj_loss", host[0].ctypes.data, host[1].ctypes.data, host[2].ctypes.data, p(beta), p(x_gt), p(valid),
+                   B, L, n, p(lane), p(loss), p(dbeta), p(xcal), p(ticket), _capi.stream_ptr())
+        ctx.save_for_backward(dbeta)
+        ctx.mark_non_differentiable(xcal)
+        return loss.reshape(()), xcal
+
+    @staticmethod
+    def backward(ctx, g, _g_xcal):
+        (dbeta,) = ctx.saved_tensors
+        return dbeta * g, None, None, None
+
+
+def fused_backprojection_loss(crit, betas, x_gt, valid):
+    """``mean_l crit(betas[l], x_gt[:, l], valid[:, l])[0]`` (what BP/main.py:297-305 computes) in one launch.
+    betas: sequence of L tensors [B, order+1, 1] float64 (Net.forward's beta0..3); x_gt, valid: [B, >=L, 56] float64.
+    Returns (loss scalar, x_cal*valid [B, L, 56])."""
+    L = len(betas)
+    beta = torch.stack([b.reshape(b.shape[0], -1) for b in betas], 1).double().contiguous()      # [B, L, n]
+    return _FusedBackprojLoss.apply(beta, x_gt[:, :L].double().contiguous(), valid[:, :L].double().contiguous(), crit)
 
 
 class Area_Loss(nn.Module):

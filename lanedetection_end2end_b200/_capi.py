@@ -140,6 +140,8 @@ _NET_PROTOS = {
     "lf_nhwc_to_nchw": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "lf_nchw_to_nhwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "lf_pack_gather": (_i, [_p, _i, _i, _p]),
+    "lf_backproj_loss": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "lf_backproj_loss_host": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "lf_bn_bwd_finalize_masked": (_i, [_p, _i, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p]),
 }
 PROTOTYPES.update(_NET_PROTOS)

@@ -10,7 +10,13 @@ the LSQ status word are static outputs the caller reads when it wants to (no syn
 The graph only contains our C-ABI kernels, a handful of tiny float64 torch ops of the loss, torch's
 graph-safe Philox draws for the Dropout2d masks, and (optionally) the NCCL all-reduce.
 """
+import os
+
 import torch
+
+# lf_backproj_loss (one launch for the loss of all lanes + its gradient) is validated on the CPU only so far
+# (tests/test_boundary_cpu.py runs the kernel's per-point code on the host): opt-in until it has run on a GPU.
+FUSED_LOSS = os.environ.get("LANEFIT_FUSED_LOSS", "0") == "1"
 
 
 class GraphedTrainStep:
@@ -52,11 +58,15 @@ class GraphedTrainStep:
         else:
             torch._foreach_zero_(self.grads)
         out = self.model(self.x, self.gt_line, True)
-        loss = 0
-        for l in range(self.L):
-            ll, _ = self.crit(out[l], self.xgt[:, l], self.valid[:, l])
-            loss = loss + ll
-        loss = loss / self.L
+        if FUSED_LOSS and hasattr(self.crit, "_fused_host_constants"):
+            from .Loss_crit import fused_backprojection_loss
+            loss, _ = fused_backprojection_loss(self.crit, out[:self.L], self.xgt, self.valid)
+        else:
+            loss = 0
+            for l in range(self.L):
+                ll, _ = self.crit(out[l], self.xgt[:, l], self.valid[:, l])
+                loss = loss + ll
+            loss = loss / self.L
         loss.backward()
         if self.reducer is not None:
             self.reducer()

@@ -181,3 +181,48 @@ def test_fused_dropout_masks_statistics_and_layout():
         assert got is m2                                   # the pending slice is handed out ...
         fresh = b._drop_mask(x)
         assert fresh is not m2 and fresh.shape == (B, c)   # ... exactly once; afterwards the block draws its own
+
+
+def test_fused_backprojection_loss_math_on_host():
+    """csrc/loss.cu: the per-point code of the fused multi-lane back-projection loss kernel is __host__ __device__;
+    lf_backproj_loss_host runs it on the CPU.  Pin loss, x_cal and d loss / d beta against the per-lane torch module
+    (which the oracle tests pin against the reference) -- including a lane without any valid sample."""
+    import ctypes
+    import numpy as np
+    import torch
+    from lanedetection_end2end_b200 import _capi
+    from lanedetection_end2end_b200.Loss_crit import backprojection_loss
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    for order, L, B in ((2, 2, 5), (3, 4, 3), (1, 3, 2)):
+        args = define_args().parse_args(["--image_dir", "x", "--gt_dir", "y", "--no_cuda", "--order", str(order),
+                                         "--nclasses", "4" if L > 2 else "2"])
+        crit = backprojection_loss(args)
+        g = torch.Generator().manual_seed(order * 10 + L)
+        n = order + 1
+        beta = (torch.randn(B, L, n, generator=g, dtype=torch.float64) * torch.tensor([1e-3, 0.1, 100.0, 1.0][-n:])).requires_grad_(True)
+        x_gt = torch.rand(B, L, 56, generator=g, dtype=torch.float64) * 500
+        valid = (torch.rand(B, L, 56, generator=g) > 0.3).double()
+        valid[:, L - 1] = 0                                   # last lane: nothing valid -> contributes 0, finite gradient 0
+        total = 0
+        xcals = []
+        for l in range(L):
+            ll, xc = crit(beta[:, l].unsqueeze(-1), x_gt[:, l], valid[:, l])
+            total = total + ll
+            xcals.append(xc)
+        ref = total / L
+        ref.backward()
+        Y, yp, Mi = crit._fused_host_constants()
+        h = _capi.lib()
+        lane = np.zeros(L)
+        loss = np.zeros(1)
+        dbeta = np.zeros((B, L, n))
+        xcal = np.zeros((B, L, 56))
+        bt = np.ascontiguousarray(beta.detach().numpy())
+        P = lambda a: ctypes.c_void_p(a.ctypes.data)
+        rc = h.lf_backproj_loss_host(P(Y), P(yp), P(Mi), P(bt), P(np.ascontiguousarray(x_gt.numpy())),
+                                     P(np.ascontiguousarray(valid.numpy())), B, L, n, P(lane), P(loss), P(dbeta), P(xcal))
+        assert rc == 0
+        assert abs(loss[0] - float(ref.detach())) <= 1e-12 * abs(float(ref.detach()))
+        np.testing.assert_allclose(xcal, torch.stack(xcals, 1).detach().numpy(), rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(dbeta, beta.grad.numpy(), rtol=1e-9, atol=1e-12 * np.abs(beta.grad.numpy()).max())
+        assert lane[L - 1] == 0.0 and not np.any(dbeta[:, L - 1])

@@ -428,3 +428,33 @@ def test_weight_pack_cache_serves_current_weights(mode):
     finally:
         o.set_conv_mode(prev)
         o.ACTIVE_PACKS = None
+
+
+@pytest.mark.xfail(reason="lf_backproj_loss was validated on the CPU only in round 1 (no GPU budget left); first GPU run",
+                   strict=False)
+def test_fused_backprojection_loss_kernel():
+    """lf_backproj_loss (all lanes, forward + gradient, one launch) vs the per-lane torch module on the GPU."""
+    from lanedetection_end2end_b200.Loss_crit import backprojection_loss, fused_backprojection_loss
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    for order, L, B in ((2, 2, 32), (3, 4, 8)):
+        args = define_args().parse_args(["--image_dir", "x", "--gt_dir", "y", "--order", str(order), "--nclasses", str(L)])
+        crit = backprojection_loss(args)
+        g = torch.Generator().manual_seed(order + L)
+        n = order + 1
+        scale = torch.tensor([1e-3, 0.1, 100.0, 1.0][-n:], dtype=torch.float64)
+        betas = [(torch.randn(B, n, 1, generator=g, dtype=torch.float64) * scale.view(1, n, 1)).cuda().requires_grad_(True)
+                 for _ in range(L)]
+        x_gt = (torch.rand(B, 4, 56, generator=g, dtype=torch.float64) * 500).cuda()
+        valid = (torch.rand(B, 4, 56, generator=g) > 0.3).double().cuda()
+        valid[:, L - 1] = 0
+        ref = sum(crit(betas[l], x_gt[:, l], valid[:, l])[0] for l in range(L)) / L
+        gref = torch.autograd.grad(ref, betas)
+        loss, xcal = fused_backprojection_loss(crit, betas, x_gt, valid)
+        gours = torch.autograd.grad(loss, betas)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(ref)) <= 1e-12 * abs(float(ref))
+        for a, b in zip(gours, gref):
+            assert float((a - b).abs().max()) <= 1e-9 * max(float(b.abs().max()), 1e-30)
+        # second call: the ticket word reset itself
+        loss2, _ = fused_backprojection_loss(crit, betas, x_gt, valid)
+        assert float(loss2) == float(loss)
