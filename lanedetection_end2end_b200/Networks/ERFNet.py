@@ -125,6 +125,7 @@ class non_bottleneck_1d(nn.Module):
 
 
 _DROP_PLANS = {}
+_FUSE_DROPOUT = True
 
 
 def fused_dropout_masks(blocks, batch, device):
@@ -240,11 +241,17 @@ class Net(nn.Module):
                 packs = self.__dict__["_weight_packs"] = _ops.WeightPackCache(self)
             packs.refresh()
             _ops.ACTIVE_PACKS = packs
-        if self.training and input.is_cuda:
+        global _FUSE_DROPOUT
+        if _FUSE_DROPOUT and self.training and input.is_cuda:
             drops = [m for m in self.modules() if isinstance(m, non_bottleneck_1d) and m.dropout.p > 0
                      and m.drop_mask_override is None]
             if drops:
-                fused_dropout_masks(drops, input.shape[0], input.device)
+                try:
+                    fused_dropout_masks(drops, input.shape[0], input.device)
+                except Exception:                      # pragma: no cover -- the blocks then draw their own masks
+                    _FUSE_DROPOUT = False
+                    for m in drops:
+                        m.__dict__.pop("_pending_drop_mask", None)
         try:
             encoder_output = self.encoder(input)
             decoder_output, output_seg = self.decoder.forward(encoder_output, flag)
