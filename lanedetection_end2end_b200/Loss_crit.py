@@ -62,7 +62,28 @@ class backprojection_loss(nn.Module):
         if self._dev != device:
             self.M, self.M_inv = self.M.to(device), self.M_inv.to(device)
             self.y_prime, self.Y = self.y_prime.to(device), self.Y.to(device)
+            Mi, yp = self.M_inv, self.y_prime
+            # the parts of M^-1 [x', y', 1]^T that do not depend on the curve: computed once, not per call
+            self._c_num = Mi[0, 1] * yp + Mi[0, 2]
+            self._c_den = Mi[2, 1] * yp + Mi[2, 2]
             self._dev = device
+
+    def forward_lanes(self, betas, x_gt, valid_samples):
+        """``mean_l forward(betas[l], x_gt[:, l], valid[:, l])[0]`` -- the lane loop of BP/main.py:297-305 -- evaluated for
+        all lanes at once (same float64 arithmetic per element, a third of the launches).  betas: L tensors
+        [B, order+1, 1]; x_gt, valid_samples: [B, >=L, 56].  Returns (loss, x_cal * valid [B, L, 56])."""
+        L = len(betas)
+        self._to(betas[0].device)
+        p = torch.stack([b.reshape(b.size(0), -1) for b in betas], 1).double()     # [B, L, n]
+        x_prime = p @ self.Y.t()                                                    # [B, L, 56]
+        Mi = self.M_inv
+        x_cal = (Mi[0, 0] * x_prime + self._c_num) / (Mi[2, 0] * x_prime + self._c_den)
+        v = valid_samples[:, :L]
+        x_err = (x_gt[:, :L] - x_cal) * v
+        nvalid = v.sum(dim=(0, 2))                                                  # per lane, like the per-lane calls
+        sq = (x_err ** 2).sum(dim=(0, 2))
+        loss = (sq / torch.where(nvalid == 0, torch.ones_like(nvalid), nvalid)).mean()
+        return loss, x_cal * v
 
     def _fused_host_constants(self):
         """(Y56 [56, n], y' [56], M^-1 [9]) as contiguous float64 numpy arrays for lf_backproj_loss."""
@@ -84,9 +105,9 @@ class backprojection_loss(nn.Module):
         self._to(params.device)
         p = params.reshape(params.size(0), -1).double()
         x_prime = p @ self.Y.t()                                        # [B,56]   (:205)
-        Mi, yp = self.M_inv, self.y_prime
-        num = Mi[0, 0] * x_prime + (Mi[0, 1] * yp + Mi[0, 2])           # M^-1 [x', y', 1]^T  (:208-210)
-        den = Mi[2, 0] * x_prime + (Mi[2, 1] * yp + Mi[2, 2])
+        Mi = self.M_inv
+        num = Mi[0, 0] * x_prime + self._c_num                          # M^-1 [x', y', 1]^T  (:208-210)
+        den = Mi[2, 0] * x_prime + self._c_den
         x_cal = num / den
         x_err = (x_gt - x_cal) * valid_samples                          # (:214)
         nvalid = valid_samples.sum()

@@ -61,6 +61,8 @@ class GraphedTrainStep:
         if FUSED_LOSS and hasattr(self.crit, "_fused_host_constants"):
             from .Loss_crit import fused_backprojection_loss
             loss, _ = fused_backprojection_loss(self.crit, out[:self.L], self.xgt, self.valid)
+        elif hasattr(self.crit, "forward_lanes"):
+            loss, _ = self.crit.forward_lanes(out[:self.L], self.xgt, self.valid)    # all lanes in one pass
         else:
             loss = 0
             for l in range(self.L):

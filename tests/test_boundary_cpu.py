@@ -226,3 +226,29 @@ def test_fused_backprojection_loss_math_on_host():
         np.testing.assert_allclose(xcal, torch.stack(xcals, 1).detach().numpy(), rtol=1e-12, atol=1e-9)
         np.testing.assert_allclose(dbeta, beta.grad.numpy(), rtol=1e-9, atol=1e-12 * np.abs(beta.grad.numpy()).max())
         assert lane[L - 1] == 0.0 and not np.any(dbeta[:, L - 1])
+
+
+def test_backprojection_loss_all_lanes_at_once_equals_the_lane_loop():
+    """backprojection_loss.forward_lanes == the reference's per-lane loop (BP/main.py:297-305): value, x_cal, gradients."""
+    import torch
+    from lanedetection_end2end_b200.Loss_crit import backprojection_loss
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    for order, L, B in ((2, 2, 6), (3, 4, 3)):
+        args = define_args().parse_args(["--image_dir", "x", "--gt_dir", "y", "--no_cuda", "--order", str(order),
+                                         "--nclasses", str(L)])
+        crit = backprojection_loss(args)
+        g = torch.Generator().manual_seed(order)
+        n = order + 1
+        scale = torch.tensor([1e-3, 0.1, 100.0, 1.0][-n:], dtype=torch.float64).view(1, n, 1)
+        betas = [(torch.randn(B, n, 1, generator=g, dtype=torch.float64) * scale).requires_grad_(True) for _ in range(L)]
+        x_gt = torch.rand(B, 4, 56, generator=g, dtype=torch.float64) * 500
+        valid = (torch.rand(B, 4, 56, generator=g) > 0.3).double()
+        valid[:, 1] = 0
+        ref = sum(crit(betas[l], x_gt[:, l], valid[:, l])[0] for l in range(L)) / L
+        gref = torch.autograd.grad(ref, betas)
+        loss, xcal = crit.forward_lanes(betas, x_gt, valid)
+        gours = torch.autograd.grad(loss, betas)
+        assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-13 * abs(float(ref.detach()))
+        for l in range(L):
+            torch.testing.assert_close(xcal[:, l], crit(betas[l], x_gt[:, l], valid[:, l])[1], rtol=1e-13, atol=1e-10)
+            torch.testing.assert_close(gours[l], gref[l], rtol=1e-10, atol=1e-16)
