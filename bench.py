@@ -337,8 +337,10 @@ def run_ours(a, cfg):
         else:
             loss = step(hx.to(dev, non_blocking=True), hxgt.to(dev, non_blocking=True), hvalid.to(dev, non_blocking=True))
         v = float(loss.item())                    # D2H read of the step's result
-        if int(model.lsq_status.item()):
-            raise RuntimeError("singular normal matrix")
+        st = int(model.lsq_status.item())
+        if st:
+            raise RuntimeError("status word %d (1 singular / 2 non-finite / 4 not positive definite normal matrix, "
+                               "8 zero BatchNorm weight in the fused backward)" % st)
         return v
 
     sampler = ClockSampler(local) if rank == 0 else None
