@@ -353,13 +353,22 @@ def run_ours(a, cfg):
     # parity arm: the same step with every convolution on the fp32 CUDA-core kernels (the mode the 1e-4
     # parity gates run in), timed the same way, reported next to the headline
     parity = None
-    if a.conv_mode != "fp32" and a.parity_arm:
+    # (N=1 only: it is a single-GPU diagnostic, and a second graph capture with NCCL inside is not worth the risk of
+    # ranks diverging on a capture error)
+    if a.conv_mode != "fp32" and a.parity_arm and world == 1:
         ops_net.set_conv_mode("fp32")
         try:
             psteps = max(3, a.steps // 2)
+            pg = None
             if a.graph:
                 from lanedetection_end2end_b200.engine import GraphedTrainStep
-                pg = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, reducer)
+                try:
+                    pg = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, None)
+                except Exception as e:
+                    sys.stderr.write("parity arm: graph capture failed (%s: %s); timing eager launches\n" % (type(e).__name__, e))
+                    pg = None
+                    torch.cuda.synchronize()
+            if pg is not None:
                 for _ in range(3):
                     pg()
                 pms = timed(lambda: pg(), psteps)
