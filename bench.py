@@ -505,8 +505,10 @@ def main():
                     help="launch every kernel eagerly instead of replaying the whole step as one CUDA graph")
     ap.add_argument("--no-parity-arm", dest="parity_arm", action="store_false",
                     help="skip the extra fp32 (CUDA-core, 1e-4-parity) timing reported next to the tf32 headline")
-    ap.add_argument("--conv-mode", dest="conv_mode", default=os.environ.get("LANEFIT_CONV_MODE", "tf32"),
-                    choices=["fp32", "tf32"], help="fp32 = CUDA-core parity mode, tf32 = tcgen05 tensor cores")
+    ap.add_argument("--conv-mode", dest="conv_mode", default=os.environ.get("LANEFIT_CONV_MODE", "tf32x3"),
+                    choices=["fp32", "tf32", "tf32x3"],
+                    help="tf32x3 = tcgen05 with 3xTF32 operand splits (fp32-grade, default); tf32 = single-pass TF32 on tcgen05 "
+                         "(labelled extra, 1e-3 accuracy); fp32 = CUDA-core FFMA kernels")
     ap.add_argument("--max-seconds", dest="max_seconds", type=int, default=int(os.environ.get("LANEFIT_BENCH_MAX_SECONDS", "600")),
                     help="wall-clock watchdog: abort (exit 3, stacks on stderr) instead of hanging the box")
     a = ap.parse_args()

@@ -164,6 +164,14 @@ typedef struct LfConvTcArgs {
 } LfConvTcArgs;
 /* 0 = unsupported shape, else the number of CTA rows of colsum_partial */
 int lf_conv1d_tc_supported(int N, int H, int W, int C);
+/* 3xTF32 variant (csrc/conv_tc_x3.cu): same arguments and epilogue, but `wpack` is the pre-split operand
+ * [2][C][3*C] (TF32 hi parts, then lo parts: LF_PACK_TF32_HI / _LO) and every product is formed as
+ * a_hi*w_hi + (a_hi*w_lo + a_lo*w_hi) with fp32 accumulation -- results agree with lf_conv_f32 to fp32 round-off
+ * (the arithmetic the reference's fp32 Conv2d performs, BP/Networks/ERFNet.py:29-37) while running on tcgen05.
+ * lf_conv1d_tc_x3_rows: 0 if a call with taps {-dil,0,+dil} along y (vertical) or x is not served, else the number of
+ * rows of colsum_partial / stats_partial.  Unsupported shapes return LF_ERR_UNSUPPORTED (no fallback inside). */
+int lf_conv1d_tc_x3_rows(int N, int H, int W, int C, int vertical, int dil);
+int lf_conv1d_tc_x3(const LfConvTcArgs* args, lf_stream_t stream);
 int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream);
 /* 2 (default) = halo-slab kernel (one TMA slab per 32-channel chunk shared by the three taps);
  * 1 = first version (one TMA box per tap).  Same results; process-wide switch for A/B measurements. */
@@ -181,6 +189,12 @@ int lf_conv1d_tc_slab_ok(int N, int H, int W, int C, int vertical, int dil);
 int lf_wgrad3_tc_ctas(int N, int H, int W, int C);
 int lf_wgrad3_tc(const float* x, const float* dy, int N, int H, int W, int C, const int* tap_dy, const int* tap_dx,
                  float* partial, int nctas, lf_stream_t stream);
+/* 3xTF32 variant (csrc/wgrad_tc_x3.cu): same arguments and partial layout; both operands are split into TF32 hi / lo
+ * parts on the fly and every product is x_hi*g_hi + (x_hi*g_lo + x_lo*g_hi), fp32 accumulate -- results agree with
+ * lf_wgrad_f32 to fp32 round-off (the weight gradient the reference's autograd forms in fp32). */
+int lf_wgrad3_tc_x3_ctas(int N, int H, int W, int C);
+int lf_wgrad3_tc_x3(const float* x, const float* dy, int N, int H, int W, int C, const int* tap_dy, const int* tap_dx,
+                    float* partial, int nctas, lf_stream_t stream);
 
 /* Weight gradient as a split-K GEMM over pixels:
  *   partial[s][t][cp][cq] = sum_{(n,j,i) in split s} P[n, j*psy+pdy[t], i*psx+pdx[t], cp]
@@ -327,6 +341,12 @@ int lf_wgrad_tcg(const LfWgradTcgArgs* args, lf_stream_t stream);
  * weights as [Co,Ci,kh,kw] (Networks/ERFNet.py:18-55 builds them with nn.Conv2d); every kernel above wants a
  * GEMM layout.  Each job gathers dst[k] = idx[k] >= 0 ? src[idx[k]] : 0 for k < n; one launch runs all jobs.
  * jobs_dev: DEVICE array of njobs records. */
+/* Gather index flags: idx >= 0 selects src[idx & LF_PACK_INDEX_MASK]; with LF_PACK_TF32_HI / _LO the element written is
+ * the TF32 "hi" part of that value (round to nearest, low 13 mantissa bits cleared) or the TF32 rounding of the
+ * remainder value - hi: the pre-split weight operand of lf_conv1d_tc_x3 / lf_conv_tcg (precision 1). */
+#define LF_PACK_INDEX_MASK 0x1fffffff
+#define LF_PACK_TF32_HI 0x20000000
+#define LF_PACK_TF32_LO 0x40000000
 typedef struct LfPackJob {
     const float* src;   /* parameter in the reference layout (device) */
     float* dst;         /* packed operand (device) */

@@ -17,6 +17,7 @@ SOLVER_INVERSE, SOLVER_CHOLESKY = 0, 1
 STATUS_SINGULAR, STATUS_NONFINITE, STATUS_NOT_POSDEF = 1, 2, 4
 STATUS_BN_ZERO_WEIGHT = 8      # fused BatchNorm backward met weight == 0 (ops_net.FUSE_BN_BWD, lf_bn_bwd_finalize_masked)
 MAX_ORDER = 4
+PACK_INDEX_MASK, PACK_TF32_HI, PACK_TF32_LO = 0x1fffffff, 0x20000000, 0x40000000   # LfPackJob index flags
 
 _c_void_p = ctypes.c_void_p
 _c_int = ctypes.c_int
@@ -112,11 +113,15 @@ _NET_PROTOS = {
     "lf_wgrad_f32_nsplit": (_i, [ctypes.POINTER(LfWgradArgs)]),
     "lf_conv1d_tc": (_i, [ctypes.POINTER(LfConvTcArgs), _p]),
     "lf_conv1d_tc_supported": (_i, [_i, _i, _i, _i]),
+    "lf_conv1d_tc_x3": (_i, [ctypes.POINTER(LfConvTcArgs), _p]),
+    "lf_conv1d_tc_x3_rows": (_i, [_i, _i, _i, _i, _i, _i]),
     "lf_conv1d_tc_set_variant": (None, [_i]),
     "lf_conv1d_tc_set_debug": (None, [_i]),
     "lf_conv1d_tc_slab_ok": (_i, [_i, _i, _i, _i, _i, _i]),
     "lf_wgrad3_tc_ctas": (_i, [_i, _i, _i, _i]),
     "lf_wgrad3_tc": (_i, [_p, _p, _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), _p, _i, _p]),
+    "lf_wgrad3_tc_x3_ctas": (_i, [_i, _i, _i, _i]),
+    "lf_wgrad3_tc_x3": (_i, [_p, _p, _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), _p, _i, _p]),
     "lf_wgrad_reduce": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p]),
     "lf_vec_reduce": (_i, [_p, _i, _i, _i, _p, _p]),
     "lf_colsum_blocks": (_i, [ctypes.c_longlong]),

@@ -29,11 +29,7 @@
 //    straight from the pixel-row registers made every store instruction touch 32 different 512-byte-strided
 //    rows: ~8K L1 wavefronts per tile, 5x the MMA time -- measured in profiles/r01.)
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
-#include <cuda.h>
-
-#include "lf_common.cuh"
-#include "lf_net.h"
-#include "tc_ptx.cuh"
+#include "conv_tc_common.cuh"
 
 // variant 1 (conv_tc_v1.cu)
 int lf_conv1d_tc_supported_v1(int N, int H, int W, int C);
@@ -45,42 +41,8 @@ static int g_tc_variant = 2;  // 2 = halo slab (this file), 1 = one box per tap 
 static int g_tc_debug = 0;    // timing experiments only: bit0 = skip the epilogue body, bit1 = skip the TMA loads
 
 
-constexpr int TC_BM = 128;
-constexpr int TC_BN = 64;
-constexpr int TC_KCH = 32;                    // fp32 elements per 128-byte swizzle row
 constexpr int TC_B_ATOM_BYTES = TC_BN * 128;  // 8 KB
-constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_STG_LD = 32 + 4;                         // staging row stride in floats: a 32-channel half + bank spread
-constexpr int TC_STG_BYTES = TC_BM * TC_STG_LD * 4;       // 18 KB
-constexpr int TC_SMEM_LIMIT = 226 * 1024;  // 227 KB opt-in maximum minus the 1 KB static epilogue scratch
 
-struct TcArgs {
-    float* out;
-    const float* bias;
-    const float* mask_src;
-    const float* add_src;
-    const float* add_mask;
-    float* colsum_partial;  // [gridDim.x / n_halves][Ctot] per-CTA column sums of the output, or NULL
-    double* stats_partial;  // [gridDim.x / n_halves][2][Ctot] per-CTA sum and sum of squares (BatchNorm), or NULL
-    const float* stats_beta;  // non-NULL: second statistic = sum out*(mask - beta[c])  (BatchNorm backward)
-    int N, H, W, Ctot;
-    int vertical;           // conv axis: 1 = y (3x1), 0 = x (1x3)
-    int TA, TB;             // tile extent along / across the conv axis (TA*TB = 128)
-    int dil;                // tap spacing d
-    int tap_row[3];         // first slab row (128-byte rows) of the view used by weight slot t
-    int tiles_a, tiles_b;
-    int relu;
-    int n_halves;
-    int total_m_tiles;
-    int stages, stage_bytes;
-    int debug;              // timing experiments (lf_conv1d_tc_set_debug): results are garbage when != 0
-};
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
-// (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | SWIZZLE_128B(2) <<61)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
 // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 <<17, M>>4 <<24
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
 
@@ -215,194 +177,8 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (leader) umma_commit(&tfull[buf]);  // accumulator complete -> epilogue
         }
     } else {
-        // ================= epilogue (warps 2..) =================
-        constexpr int NH = Cfg::HALVES;
-        const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may access
-        const int m = lane_base + lane;         // phase 1: this thread's pixel row of the tile
-        const int grp = (threadIdx.x - 64) >> 7;  // epilogue group (0 when there is only one)
-        const int et = (threadIdx.x - 64) & 127;  // 0..127 inside the group
-        const int c4 = et & 7;                  // phase 2: float4 column inside a 32-channel half (fixed)
-        const int r0 = et >> 3;                 // phase 2: first of this thread's 8 rows (r0, r0+16, ...)
-        const int tb_shift = (a.TB == 8) ? 3 : 4;
-        const int h_first = (Cfg::EPI_GROUPS == 2) ? grp : 0;  // first (only) channel half of this group
-        float* stg_g = stg + grp * (TC_STG_BYTES / 4);
-        const int bar_id = 1 + grp;
-        const bool pre_mask = a.mask_src != nullptr;
-        const bool pre_add = (a.add_src != nullptr) && !pre_mask;  // both given: add_src is read in the loop
-        float4 csum[NH], csq[NH];               // running column sums / sums of squares, per channel half
-        float4 sbeta[NH];                       // BatchNorm bias of this thread's columns (stats_beta mode)
-#pragma unroll
-        for (int hh = 0; hh < NH; ++hh) {
-            csum[hh] = csq[hh] = sbeta[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.stats_beta)
-                sbeta[hh] = __ldg(reinterpret_cast<const float4*>(a.stats_beta + n_half * TC_BN + 32 * (h_first + hh) + 4 * c4));
-        }
-        float4 nxt_a[AHEAD ? 8 : 1], nxt_m[AHEAD ? 8 : 1];  // operands of the next tile in flight
-        int it = 0;
-        for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
-            const int buf = it & 1;
-            const uint32_t use_parity = (it >> 1) & 1;
-            const int ta = mt % a.tiles_a;
-            const int tb = (mt / a.tiles_a) % a.tiles_b;
-            const int n = mt / (a.tiles_a * a.tiles_b);
-            // global offsets of this thread's 8 phase-2 rows (channel 4*c4 of the group's first half)
-            size_t roff[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int r = r0 + 16 * j;
-                const int ap = r >> tb_shift, bp = r & (a.TB - 1);  // slab order: cross axis fastest
-                const int pa = ta * a.TA + ap, pb = tb * a.TB + bp;
-                const int y = a.vertical ? pa : pb, x = a.vertical ? pb : pa;
-                roff[j] = ((size_t)(n * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN + 32 * h_first + 4 * c4;
-            }
-            // Prefetch the ReLU mask (or the gated residual gradient).  One half per thread (C=64): ONE TILE AHEAD —
-            // the loads for tile i+1 are issued before tile i is processed, so their latency hides behind a whole
-            // tile of epilogue work (the epilogue, not the tensor pipe, bounds these layers).  Two halves per
-            // thread (C=128): no registers for that; prefetch this tile's operands before waiting on the accumulator.
-            float4 pre[NH][8];
-            if constexpr (NH == 1 && AHEAD) {
-                if (pre_mask || pre_add) {
-                    auto issue = [&](int mtn) {
-                        const int tan = mtn % a.tiles_a;
-                        const int tbn = (mtn / a.tiles_a) % a.tiles_b;
-                        const int nn = mtn / (a.tiles_a * a.tiles_b);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int r = r0 + 16 * j;
-                            const int ap = r >> tb_shift, bp = r & (a.TB - 1);
-                            const int pa = tan * a.TA + ap, pb = tbn * a.TB + bp;
-                            const int y = a.vertical ? pa : pb, x = a.vertical ? pb : pa;
-                            const size_t off = ((size_t)(nn * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN + 32 * h_first + 4 * c4;
-                            nxt_a[j] = __ldg(reinterpret_cast<const float4*>((pre_mask ? a.mask_src : a.add_src) + off));
-                            if (!pre_mask && a.add_mask) nxt_m[j] = __ldg(reinterpret_cast<const float4*>(a.add_mask + off));
-                        }
-                    };
-                    if (it == 0) issue(mt);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 v = nxt_a[j];
-                        if (!pre_mask && a.add_mask) {
-                            const float4 mk = nxt_m[j];
-                            v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
-                            v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
-                        }
-                        pre[0][j] = v;
-                    }
-                    if (mt + m_stride < a.total_m_tiles) issue(mt + m_stride);
-                }
-            } else if (pre_mask || pre_add) {
-#pragma unroll
-                for (int hh = 0; hh < NH; ++hh)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (pre_mask) {
-                            pre[hh][j] = __ldg(reinterpret_cast<const float4*>(a.mask_src + roff[j] + 32 * hh));
-                        } else {
-                            float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + roff[j] + 32 * hh));
-                            if (a.add_mask) {
-                                const float4 mk = __ldg(reinterpret_cast<const float4*>(a.add_mask + roff[j] + 32 * hh));
-                                ad.x = mk.x > 0.f ? ad.x : 0.f; ad.y = mk.y > 0.f ? ad.y : 0.f;
-                                ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
-                            }
-                            pre[hh][j] = ad;
-                        }
-                    }
-            }
-            mbar_wait(&tfull[buf], use_parity);
-            tc_fence_after();
-            if (a.debug & 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);
-                continue;
-            }
-#pragma unroll
-            for (int hh = 0; hh < NH; ++hh) {
-                const int h = h_first + hh;
-                // ---- phase 1: TMEM -> registers -> (+bias, ReLU) -> staging half-tile, one pixel row per thread
-#pragma unroll
-                for (int c0 = 0; c0 < 32; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + buf * TC_BN + 32 * h + c0, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                               __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                        if (a.bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n_half * TC_BN + 32 * h + c0 + 4 * q));
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                        }
-                        if (a.relu) {
-                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                        }
-                        *reinterpret_cast<float4*>(&stg_g[m * TC_STG_LD + c0 + 4 * q]) = o;
-                    }
-                }
-                if (hh == NH - 1) tc_fence_before();
-                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // staging complete (this group only)
-                if (hh == NH - 1 && lane == 0) mbar_arrive(&tempty[buf]);  // this warp's TMEM reads are done
-                // ---- phase 2: row-major walk, 8 consecutive threads = one pixel's 32 channels (128 B)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int r = r0 + 16 * j;
-                    const size_t off = roff[j] + 32 * hh;
-                    float4 o = *reinterpret_cast<const float4*>(&stg_g[r * TC_STG_LD + 4 * c4]);
-                    if (pre_mask) {
-                        const float4 mk = pre[hh][j];
-                        o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
-                        o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
-                    }
-                    if (pre_add) {
-                        o.x += pre[hh][j].x; o.y += pre[hh][j].y; o.z += pre[hh][j].z; o.w += pre[hh][j].w;
-                    } else if (a.add_src) {
-                        float4 ad = __ldg(reinterpret_cast<const float4*>(a.add_src + off));
-                        if (a.add_mask) {
-                            const float4 mk = __ldg(reinterpret_cast<const float4*>(a.add_mask + off));
-                            ad.x = mk.x > 0.f ? ad.x : 0.f; ad.y = mk.y > 0.f ? ad.y : 0.f;
-                            ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
-                        }
-                        o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
-                    }
-                    *reinterpret_cast<float4*>(a.out + off) = o;
-                    csum[hh].x += o.x; csum[hh].y += o.y; csum[hh].z += o.z; csum[hh].w += o.w;
-                    if (a.stats_beta) {   // pre_mask holds: pre[hh][j] is the mask operand relu(bn(x))
-                        const float4 mk = pre[hh][j];
-                        csq[hh].x = fmaf(o.x, mk.x - sbeta[hh].x, csq[hh].x); csq[hh].y = fmaf(o.y, mk.y - sbeta[hh].y, csq[hh].y);
-                        csq[hh].z = fmaf(o.z, mk.z - sbeta[hh].z, csq[hh].z); csq[hh].w = fmaf(o.w, mk.w - sbeta[hh].w, csq[hh].w);
-                    } else {
-                        csq[hh].x = fmaf(o.x, o.x, csq[hh].x); csq[hh].y = fmaf(o.y, o.y, csq[hh].y);
-                        csq[hh].z = fmaf(o.z, o.z, csq[hh].z); csq[hh].w = fmaf(o.w, o.w, csq[hh].w);
-                    }
-                }
-                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // staging half-tile may be overwritten
-            }
-        }
-        if (a.colsum_partial || a.stats_partial) {
-            // 16 threads share each (half, float4 column): combine them through the (now free) staging tile
-#pragma unroll
-            for (int hh = 0; hh < NH; ++hh) {
-                *reinterpret_cast<float4*>(&stg_g[(hh * 16 + r0) * TC_STG_LD + 4 * c4]) = csum[hh];
-                *reinterpret_cast<float4*>(&stg_g[(32 + hh * 16 + r0) * TC_STG_LD + 4 * c4]) = csq[hh];
-            }
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-            if (et < 32 * NH) {
-                const int hh = et >> 5, c = et & 31;
-                const int ch = n_half * TC_BN + 32 * (h_first + hh) + c;
-                double tot = 0.0, tsq = 0.0;
-#pragma unroll
-                for (int g = 0; g < 16; ++g) {
-                    tot += (double)stg_g[(hh * 16 + g) * TC_STG_LD + c];
-                    tsq += (double)stg_g[(32 + hh * 16 + g) * TC_STG_LD + c];
-                }
-                if (a.colsum_partial) a.colsum_partial[(size_t)cta_m * a.Ctot + ch] = (float)tot;
-                if (a.stats_partial) {
-                    double* sp = a.stats_partial + (size_t)cta_m * 2 * a.Ctot + ch;
-                    sp[0] = tot;
-                    sp[a.Ctot] = tsq;
-                }
-            }
-        }
+        // ================= epilogue (warps 2..): conv_tc_common.cuh =================
+        tc_epilogue<Cfg::EPI_GROUPS, AHEAD, 64, 2, TC_BN, false>(a, stg, tmem_base, tfull, tempty, n_half, cta_m, m_stride);
     }
     tc_fence_before();
     __syncthreads();
@@ -507,6 +283,8 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     LF_REQUIRE(!p.stats_beta || (p.mask_src && p.stats_partial));
     a.N = p.N; a.H = p.H; a.W = p.W; a.Ctot = p.C; a.relu = p.relu;
     a.vertical = pl.vertical; a.TA = pl.TA; a.TB = pl.TB; a.dil = pl.dil;
+    a.tb_shift = (pl.TB == 8) ? 3 : 4;
+    a.slab_rows = (pl.TA + 2 * pl.dil) * pl.TB;
     a.tiles_a = pl.tiles_a; a.tiles_b = pl.tiles_b;
     a.stages = pl.stages; a.stage_bytes = pl.stage_bytes;
     a.debug = g_tc_debug;

@@ -634,7 +634,14 @@ __global__ void __launch_bounds__(256) pack_gather_kernel(const PackJob* __restr
     const PackJob j = jobs[blockIdx.y];
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < j.n; k += (long long)gridDim.x * blockDim.x) {
         const int i = __ldg(j.idx + k);
-        j.dst[k] = i >= 0 ? __ldg(j.src + i) : 0.f;
+        float v = i >= 0 ? __ldg(j.src + (i & LF_PACK_INDEX_MASK)) : 0.f;
+        if (i >= 0 && (i & (LF_PACK_TF32_HI | LF_PACK_TF32_LO))) {
+            // 3xTF32 operand split (conv_tc_x3.cu): hi = TF32 round-to-nearest of v, lo = TF32 rounding of v - hi; both
+            // have their 13 low mantissa bits cleared, so the tensor core's own fp32 -> TF32 conversion is the identity
+            const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+            v = (i & LF_PACK_TF32_HI) ? hi : __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xffffe000u);
+        }
+        j.dst[k] = v;
     }
 }
 

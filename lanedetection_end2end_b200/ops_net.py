@@ -23,16 +23,40 @@ LfConvArgs, LfWgradArgs, LfConvTcArgs = _capi.LfConvArgs, _capi.LfWgradArgs, _ca
 
 # Convolution arithmetic for the dense 3-tap convolutions of non_bottleneck_1d (C in {64,128}):
 #   "fp32": CUDA-core FFMA implicit GEMM (parity mode, fp32-exact)
-#   "tf32": tcgen05 tensor cores, TF32 multiply / fp32 accumulate (what cuDNN does for the reference's
-#           fp32 convs on Ampere+ GPUs); every other layer shape stays on the fp32 kernel.
-CONV_MODE = os.environ.get("LANEFIT_CONV_MODE", "fp32")
+#   "tf32x3": tcgen05 tensor cores, every product formed from TF32 hi/lo splits of both operands
+#           (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi, fp32 accumulate): fp32-grade results at tensor-core speed -- the
+#           default, and the mode bench.py times (csrc/conv_tc_x3.cu);
+#   "tf32": tcgen05 tensor cores, single-pass TF32 multiply / fp32 accumulate (what cuDNN does for the reference's
+#           fp32 convs on Ampere+ GPUs; 1e-3 from fp32 on the curve coefficients -- a labelled extra);
+#   shapes a tensor-core kernel does not take stay on the fp32 kernel in every mode.
+CONV_MODES = ("fp32", "tf32", "tf32x3")
+CONV_MODE = os.environ.get("LANEFIT_CONV_MODE", "tf32x3")
 
 
 def set_conv_mode(mode):
     global CONV_MODE
-    if mode not in ("fp32", "tf32"):
+    if mode not in CONV_MODES:
         raise ValueError(mode)
     CONV_MODE = mode
+
+
+def tc_mode():
+    """True when the dense convolutions run on tcgen05 (either TF32 flavour)."""
+    return CONV_MODE in ("tf32", "tf32x3")
+
+
+def x3_mode():
+    return CONV_MODE == "tf32x3"
+
+
+def split_tf32(t):
+    """fp32 tensor -> stacked [2, ...] (hi, lo): hi = t rounded to TF32 (nearest, ties away; low 13 mantissa bits
+    cleared), lo = TF32 rounding of t - hi.  Bit-for-bit what lf_pack_gather writes for LF_PACK_TF32_HI / _LO."""
+    def rna(v):
+        return ((v.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    t = t.float()
+    hi = rna(t)
+    return torch.stack([hi, rna(t - hi)])
 
 ptr = _capi.ptr
 
@@ -303,18 +327,22 @@ class WeightPackCache:
     def _scan(self):
         self.by_ptr = {p.data_ptr(): p for p in self.module.parameters() if p.is_cuda}
 
-    def get(self, w, kind, fn):
+    def get(self, w, kind, fn, split=False):
         if not w.is_cuda:
             return None
         p = self.by_ptr.get(w.data_ptr())
         if p is None or p.shape != w.shape:
             return None
-        key = (w.data_ptr(), kind)
+        key = (w.data_ptr(), kind, split)
         e = self.entries.get(key)
         if e is None:
             if torch.cuda.is_current_stream_capturing():
                 return None
             idx = pack_gather_table(fn, p.shape)
+            if split:       # [2, ...]: TF32 hi parts, then lo parts (structural zeros stay negative)
+                assert p.numel() <= _capi.PACK_INDEX_MASK
+                idx = torch.stack([torch.where(idx >= 0, idx | _capi.PACK_TF32_HI, idx),
+                                   torch.where(idx >= 0, idx | _capi.PACK_TF32_LO, idx)])
             self.entries[key] = [p, idx.to(w.device), torch.empty(idx.shape, dtype=torch.float32, device=w.device), -1]
             self.dirty = True
             return None
@@ -346,14 +374,15 @@ class WeightPackCache:
 ACTIVE_PACKS = None
 
 
-def packed(w, kind, fn):
-    """The packed operand ``fn(w)``: from the active WeightPackCache when current, else computed now."""
+def packed(w, kind, fn, split=False):
+    """The packed operand ``fn(w)`` (``split``: its TF32 hi/lo pair, see split_tf32): from the active WeightPackCache
+    when current, else computed now."""
     c = ACTIVE_PACKS
     if c is not None:
-        t = c.get(w, kind, fn)
+        t = c.get(w, kind, fn, split)
         if t is not None:
             return t
-    return fn(w)
+    return split_tf32(fn(w)) if split else fn(w)
 
 
 # --------------------------------------------------------------------------------------
@@ -477,19 +506,39 @@ def unpack_wgrad_super(dw_super, vertical):
 
 def super_ok(x, dil):
     N, H, W, C = x.shape
-    if not (CONV_MODE == "tf32" and C == 16 and dil == 1 and W % SUPER == 0 and x.is_contiguous()):
+    if not (tc_mode() and C == 16 and dil == 1 and W % SUPER == 0 and x.is_contiguous()):
         return False
+    if x3_mode():
+        return min(int(_lib().lf_conv1d_tc_x3_rows(N, H, W // SUPER, SUPER * C, v, 1)) for v in (0, 1)) > 0
     return int(_lib().lf_conv1d_tc_supported(N, H, W // SUPER, SUPER * C)) > 0
 
 
-def tc_rows(x):
-    """0 if the tcgen05 kernel does not take this shape, else the row count of its colsum partials."""
+def tc_rows(x, vertical=None, dil=1, stats=False):
+    """0 if the active tcgen05 kernel does not take this call, else the row count of its colsum / stats partials.
+    tf32: any 3-tap pattern on a supported shape (the per-tap variant is the in-library fallback; `stats` needs the
+    slab kernel); tf32x3: per (axis, dilation) -- vertical=None asks for d=1 along both axes."""
     N, H, W, C = x.shape
-    return int(_lib().lf_conv1d_tc_supported(N, H, W, C))
+    if C not in (64, 128) or not tc_mode():
+        return 0
+    if x3_mode():
+        if vertical is None:
+            return min(int(_lib().lf_conv1d_tc_x3_rows(N, H, W, C, v, dil)) for v in (0, 1))
+        return int(_lib().lf_conv1d_tc_x3_rows(N, H, W, C, int(vertical), dil))
+    rows = int(_lib().lf_conv1d_tc_supported(N, H, W, C))
+    if rows and stats and not _lib().lf_conv1d_tc_slab_ok(N, H, W, C, int(bool(vertical)), dil):
+        return 0
+    return rows
 
 
-def tc_supported(x):
-    return tc_rows(x) > 0
+def tc_supported(x, vertical=None, dil=1):
+    return tc_rows(x, vertical, dil) > 0
+
+
+def _taps_axis(taps):
+    """(vertical, dilation) of a 3-tap list [(dy, dx)] * 3."""
+    vertical = taps[0][0] != 0 or taps[2][0] != 0
+    d = abs(taps[0][0] if vertical else taps[0][1])
+    return vertical, d
 
 
 def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_src=None, add_mask=None, colsum=None, stats_beta=None,
@@ -505,7 +554,7 @@ def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_s
     a.add_mask = add_mask.data_ptr() if add_mask is not None else None
     part = None
     if colsum is not None:
-        rows = tc_rows(x)
+        rows = tc_rows(x, *_taps_axis(taps))
         part = torch.empty(rows * C, dtype=torch.float32, device=x.device)
         a.colsum_partial = part.data_ptr()
     if stats_partial is not None:
@@ -517,7 +566,8 @@ def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_s
         a.dy[t], a.dx[t] = dy, dx
     a.relu = int(relu)
     n_operands = 2 + (mask_src is not None) + (add_src is not None) + (add_mask is not None)
-    _capi.call("lf_conv1d_tc", ctypes.byref(a), _stream(), flops=2 * N * H * W * 3 * C * C, nbytes=4 * n_operands * N * H * W * C)
+    _capi.call("lf_conv1d_tc_x3" if x3_mode() else "lf_conv1d_tc", ctypes.byref(a), _stream(), flops=2 * N * H * W * 3 * C * C,
+               nbytes=4 * n_operands * N * H * W * C)
     if part is not None:
         if _DEFERRED is not None:
             _reduce(part, rows, 1, 1, C, 1, C, colsum, 0, 0, 1)
@@ -549,7 +599,8 @@ def flush_deferred_reductions(jobs):
 
 
 def _super_conv_launch(taps, xs, w, vertical, transposed, out, N, H, W, C, cs, epi_s):
-    run_conv_tc(taps, xs, packed(w, "tc_super_%d%d" % (vertical, transposed), lambda t: pack_tc_super(t, vertical, transposed)),
+    run_conv_tc(taps, xs, packed(w, "tc_super_%d%d" % (vertical, transposed), lambda t: pack_tc_super(t, vertical, transposed),
+                                 split=x3_mode()),
                 out.view(N, H, W // SUPER, SUPER * C), colsum=cs, **epi_s)
 
 
@@ -576,10 +627,11 @@ def conv3(x, w, vertical, dil, transposed, colsum=None, **epi):
         if colsum is not None:
             colsum.copy_(cs.view(SUPER, C).sum(0))
         return out
-    if CONV_MODE == "tf32" and C in (64, 128) and tc_supported(x):
+    if tc_supported(x, vertical, dil):
         sgn = -1 if transposed else 1
         taps = [((sgn * (k - 1) * dil, 0) if vertical else (0, sgn * (k - 1) * dil)) for k in range(3)]
-        wp = packed(w, "tc_dgrad", pack_tc_dgrad) if transposed else packed(w, "tc_fwd", pack_tc_fwd)
+        wp = (packed(w, "tc_dgrad", pack_tc_dgrad, split=x3_mode()) if transposed
+              else packed(w, "tc_fwd", pack_tc_fwd, split=x3_mode()))
         return run_conv_tc(taps, x, wp, out, colsum=colsum, **epi)
     kh, kw = (3, 1) if vertical else (1, 3)
     ph, pw = (dil, 0) if vertical else (0, dil)
@@ -599,16 +651,17 @@ def wgrad3(x_in, d_out, w, vertical, dil, bias_grad="compute"):
     """Weight + bias gradient of one factorised 3-tap convolution -> (dw [Co,Ci,kh,kw], db [Co] or None).
     bias_grad: "compute" (column sums of d_out), or "skip" (the caller gets it elsewhere)."""
     N, H, W, C = x_in.shape
+    sfx = "_x3" if x3_mode() else ""          # which tcgen05 weight-gradient kernel
     if super_ok(x_in, dil) and d_out.is_contiguous():
         Cs, Ws = SUPER * C, W // SUPER
-        nctas = _lib().lf_wgrad3_tc_ctas(N, H, Ws, Cs)
+        nctas = getattr(_lib(), "lf_wgrad3_tc%s_ctas" % sfx)(N, H, Ws, Cs)
         if nctas > 0:
             tdy = (ctypes.c_int * 3)(*[((k - 1) if vertical else 0) for k in range(3)])
             tdx = (ctypes.c_int * 3)(*[(0 if vertical else (k - 1)) for k in range(3)])
             partial = torch.empty(nctas * 3 * Cs * Cs, dtype=torch.float32, device=x_in.device)
             dws = torch.empty(Cs, Cs, 3, dtype=torch.float32, device=x_in.device)
             st = _stream()
-            _capi.call("lf_wgrad3_tc", ptr(x_in), ptr(d_out), N, H, Ws, Cs, tdy, tdx, ptr(partial), nctas, st,
+            _capi.call("lf_wgrad3_tc" + sfx, ptr(x_in), ptr(d_out), N, H, Ws, Cs, tdy, tdx, ptr(partial), nctas, st,
                        flops=2 * N * H * W * 3 * C * C, nbytes=8 * N * H * W * C)
             _capi.call("lf_wgrad_reduce", ptr(partial), nctas, 3, Cs, Cs, Cs, Cs, ptr(dws), 1, 3, Cs * 3, st)
             dw = unpack_wgrad_super(dws, vertical).reshape(w.shape)
@@ -620,13 +673,13 @@ def wgrad3(x_in, d_out, w, vertical, dil, bias_grad="compute"):
     dw = torch.empty_like(w)
     db = torch.empty(C, dtype=torch.float32, device=x_in.device) if bias_grad == "compute" else None
     lay = (1, 3, C * 3)                                   # (tap, ci, co) strides of [Co,Ci,3] weights
-    nctas = _lib().lf_wgrad3_tc_ctas(N, H, W, C) if (CONV_MODE == "tf32" and C in (64, 128)) else 0
+    nctas = getattr(_lib(), "lf_wgrad3_tc%s_ctas" % sfx)(N, H, W, C) if (tc_mode() and C in (64, 128)) else 0
     if nctas > 0:
         tdy = (ctypes.c_int * 3)(*[((k - 1) * dil if vertical else 0) for k in range(3)])
         tdx = (ctypes.c_int * 3)(*[(0 if vertical else (k - 1) * dil) for k in range(3)])
         partial = torch.empty(nctas * 3 * C * C, dtype=torch.float32, device=x_in.device)
         st = _stream()
-        _capi.call("lf_wgrad3_tc", ptr(x_in), ptr(d_out), N, H, W, C, tdy, tdx, ptr(partial), nctas, st,
+        _capi.call("lf_wgrad3_tc" + sfx, ptr(x_in), ptr(d_out), N, H, W, C, tdy, tdx, ptr(partial), nctas, st,
                    flops=2 * N * H * W * 3 * C * C, nbytes=8 * N * H * W * C)
         _reduce(partial, nctas, 3, C, C, C, C, dw, lay[0], lay[1], lay[2])
         if db is not None:
@@ -739,12 +792,12 @@ def conv3_bn_stats(x, w, vertical, dil, bias, gamma, beta, running_mean, running
     """conv (forward) followed by the BatchNorm statistics of its output -> (out, BNState).  On the tcgen05 slab
     kernel the per-channel sums are accumulated in the conv epilogue, saving a full pass over `out`."""
     N, H, W, C = x.shape
-    if (training and CONV_MODE == "tf32" and C in (64, 128) and tc_supported(x)
-            and _lib().lf_conv1d_tc_slab_ok(N, H, W, C, int(vertical), dil)):
-        rows = tc_rows(x)
+    rows = tc_rows(x, vertical, dil, stats=True) if training else 0
+    if rows > 0:
         part = torch.empty(rows * 2 * C, dtype=torch.float64, device=x.device)
         taps = [(((k - 1) * dil, 0) if vertical else (0, (k - 1) * dil)) for k in range(3)]
-        out = run_conv_tc(taps, x, packed(w, "tc_fwd", pack_tc_fwd), torch.empty_like(x), bias=bias, stats_partial=part)
+        out = run_conv_tc(taps, x, packed(w, "tc_fwd", pack_tc_fwd, split=x3_mode()), torch.empty_like(x), bias=bias,
+                          stats_partial=part)
         return out, bn_finalize(part, rows, N * H * W, C, gamma, beta, running_mean, running_var)
     out = conv3(x, w, vertical, dil, False, bias=bias)
     return out, bn_forward_stats(out, gamma, beta, running_mean, running_var, training)
@@ -800,13 +853,12 @@ def dgrad_relu_bn_fused(d_out, w, vertical, dil, y, x, s, gamma, beta):
     """(dgrad of the 3-tap conv) * (y > 0) -> g, then BatchNorm backward of y = relu(bn(x)) -> (dx, dgamma, dbeta);
     returns None when the shapes are not served by the slab kernel (caller takes the two-pass route)."""
     N, H, W, C = d_out.shape
-    if not (FUSE_BN_BWD and CONV_MODE == "tf32" and C in (64, 128) and tc_supported(d_out)
-            and _lib().lf_conv1d_tc_slab_ok(N, H, W, C, int(vertical), dil)):
+    rows = tc_rows(d_out, vertical, dil, stats=True) if FUSE_BN_BWD else 0
+    if rows <= 0:
         return None
-    rows = tc_rows(d_out)
     part = torch.empty(rows * 2 * C, dtype=torch.float64, device=d_out.device)
     taps = [((-(k - 1) * dil, 0) if vertical else (0, -(k - 1) * dil)) for k in range(3)]
-    g = run_conv_tc(taps, d_out, packed(w, "tc_dgrad", pack_tc_dgrad), torch.empty_like(d_out), mask_src=y,
+    g = run_conv_tc(taps, d_out, packed(w, "tc_dgrad", pack_tc_dgrad, split=x3_mode()), torch.empty_like(d_out), mask_src=y,
                     stats_partial=part, stats_beta=beta)
     npix = N * H * W
     buf = torch.empty(4, C, dtype=torch.float32, device=d_out.device)

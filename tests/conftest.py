@@ -31,3 +31,16 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _restore_conv_mode():
+    """Tests switch ops_net.CONV_MODE; every test starts from (and leaves) the library default."""
+    try:
+        from lanedetection_end2end_b200 import ops_net
+    except Exception:
+        yield
+        return
+    default = ops_net.CONV_MODE
+    yield
+    ops_net.CONV_MODE = default

@@ -2,7 +2,7 @@
 and backward) through the reference-mirroring modules, against the torch-CPU oracle and the
 committed golden outputs of the reference itself.
 
-fp32 "parity mode" kernels (CUDA-core FFMA): block-level gate 1e-4 norm-wise (typically 1e-6).
+Both fp32-accurate modes (3xTF32 on tcgen05 = default; CUDA-core FFMA): block-level gate 1e-4 norm-wise (typically 1e-6).
 Whole-path gate vs the reference: |ours - fp64| <= |ref32 - fp64| * 4 + 1e-4.
 """
 import json
@@ -19,6 +19,15 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
+@pytest.fixture(autouse=True, params=["tf32x3", "fp32"])
+def conv_mode(request):
+    """Every parity test of this module runs in both fp32-accurate arithmetic modes: 3xTF32 on tcgen05 (the library
+    default and the mode bench.py times) and the CUDA-core FFMA kernels.  Same gates for both."""
+    from lanedetection_end2end_b200 import ops_net
+    ops_net.set_conv_mode(request.param)
+    yield request.param
+
+
 def load(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 
@@ -27,6 +36,19 @@ def rel(a, b):
     a = a.detach().double().cpu() if torch.is_tensor(a) else torch.as_tensor(a, dtype=torch.float64)
     b = b.detach().double().cpu() if torch.is_tensor(b) else torch.as_tensor(b, dtype=torch.float64)
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_up_to_relu_flips(a, b, tol=TOL, max_frac=2e-4):
+    """Norm-wise error of a gradient map, tolerant of isolated ReLU-mask flips: a pre-activation within fp32 round-off of
+    zero may land on the other side in fp32 (either kernel family) than in the fp64 oracle, which changes the gradient
+    entries downstream of that one pixel by O(1).  At most `max_frac` of the entries may be such outliers (a wrong tap,
+    stride or mask operand corrupts every entry); returns the max-norm error of all the others."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    sc = b.abs().max().clamp_min(1e-30)
+    bad = (a - b).abs() > tol * sc
+    assert int(bad.sum()) <= max(2, max_frac * bad.numel()), (int(bad.sum()), bad.numel())
+    assert float((a - b).norm() / b.norm()) <= 30 * tol
+    return float(((a - b) * ~bad).abs().max() / sc)
 
 
 def E():
@@ -122,7 +144,7 @@ def test_non_bottleneck_1d_block(C, dil, H, W, drop):
     yo = eo.non_bottleneck_1d(x64, P, prefix, dil, True, mask)
     yo.backward(gy.double())
     assert rel(y, yo) <= TOL
-    assert rel(gx, x64.grad) <= TOL
+    assert rel_up_to_relu_flips(gx, x64.grad) <= TOL
     check_grads(blk, P, prefix)
 
 
@@ -355,10 +377,11 @@ def test_full_path_tf32_mode_accuracy(name):
     # measured (profiles/r01/tf32_accuracy_*.json): beta 5e-4 (order 2) / 2e-3 (order 3) norm-wise; individual
     # decoder outputs of this random-weight, batch-2 network move by up to 17 % of the max (ReLU/BN chaos),
     # which the weighted fit averages out
-    assert rec["beta_normwise_err_tf32"] < 2e-2 and rec["loss_rel_err_tf32"] < 2e-2, rec
+    # gate = about 2x the measured error: an accuracy regression of the TF32 kernels must not pass
+    assert rec["beta_normwise_err_tf32"] < (2.5e-3 if order == 2 else 4.5e-3) and rec["loss_rel_err_tf32"] < 2e-2, rec
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3"])
 def test_weight_pack_cache_serves_current_weights(mode):
     """WeightPackCache: from the second Net.forward on every GEMM-layout weight operand comes from ONE
     lf_pack_gather launch.  Step 2 (served from the cache) must reproduce step 1 (packed directly) bit for bit,
@@ -406,11 +429,15 @@ def test_weight_pack_cache_serves_current_weights(mode):
             for p in model.parameters():
                 p.mul_(1.01)
         w = model.net.encoder.layers[1].conv3x1_1.weight
-        e = packs.entries[(w.data_ptr(), "tc_fwd" if mode == "tf32" else "conv_fwd")]
+        kind, split = ("conv_fwd" if mode == "fp32" else "tc_fwd"), mode == "tf32x3"
+        e = packs.entries[(w.data_ptr(), kind, split)]
         assert e[3] != w._version               # stale until the next refresh ...
-        assert packs.get(w, "tc_fwd" if mode == "tf32" else "conv_fwd", o.pack_tc_fwd) is None   # ... and not served
+        assert packs.get(w, kind, o.pack_tc_fwd, split) is None   # ... and not served
         b3, g3 = step()
-        ref_pack = o.pack_tc_fwd(w) if mode == "tf32" else o.pack_conv_fwd(w)
+        ref_pack = o.pack_conv_fwd(w) if mode == "fp32" else o.pack_tc_fwd(w)
+        if split:       # the kernel's TF32 hi / lo split is bit-identical to the torch restatement and loses < 2^-22
+            ref_pack = o.split_tf32(ref_pack)
+            assert float((ref_pack.sum(0) - o.pack_tc_fwd(w)).abs().max()) <= 2.0 ** -22 * float(w.abs().max())
         assert torch.equal(e[2], ref_pack)
         assert not torch.equal(b3, b2)
         # fresh model with the same updated weights, direct packing (first step) -> same numbers
@@ -430,8 +457,6 @@ def test_weight_pack_cache_serves_current_weights(mode):
         o.ACTIVE_PACKS = None
 
 
-@pytest.mark.xfail(reason="lf_backproj_loss was validated on the CPU only in round 1 (no GPU budget left); first GPU run",
-                   strict=False)
 def test_fused_backprojection_loss_kernel():
     """lf_backproj_loss (all lanes, forward + gradient, one launch) vs the per-lane torch module on the GPU."""
     from lanedetection_end2end_b200.Loss_crit import backprojection_loss, fused_backprojection_loss
