@@ -315,6 +315,8 @@ typedef struct LfConvTcgArgs {
     int N, Hs, Ws;
     int Kc, Ng, ntaps;
     int map[LF_TCG_MAX_TAPS], dy[LF_TCG_MAX_TAPS], dx[LF_TCG_MAX_TAPS];
+    int precision;          /* 0 = TF32 multiply; 1 = 3xTF32 (fp32-grade): wg is [2][Ng][ntaps*Kc], the TF32 hi parts then
+                               the lo parts (LF_PACK_TF32_HI / _LO), activations are split in shared memory */
 } LfConvTcgArgs;
 int lf_conv_tcg_supported(int N, int Hs, int Ws, int Kc, int Ng);
 int lf_conv_tcg(const LfConvTcgArgs* args, lf_stream_t stream);
@@ -333,8 +335,10 @@ typedef struct LfWgradTcgArgs {
     int Ka, Nn, nblocks;
     int map[LF_WGRAD_TCG_MAX_BLOCKS], dy[LF_WGRAD_TCG_MAX_BLOCKS], dx[LF_WGRAD_TCG_MAX_BLOCKS], cblk[LF_WGRAD_TCG_MAX_BLOCKS];
     int nctas;
+    int precision;          /* 0 = TF32 multiply; 1 = 3xTF32 (both operands split in shared memory, fp32-grade) */
 } LfWgradTcgArgs;
 int lf_wgrad_tcg_ctas(int N, int Hs, int Ws, int Ka, int Nn, int nblocks);
+int lf_wgrad_tcg_ctas_x3(int N, int Hs, int Ws, int Ka, int Nn, int nblocks);   /* same, for precision 1 */
 int lf_wgrad_tcg(const LfWgradTcgArgs* args, lf_stream_t stream);
 
 /* Batched weight packing (host side: ops_net.WeightPackCache).  The reference keeps Conv2d / ConvTranspose2d

@@ -30,8 +30,8 @@ def define_loss_crit(options):
     else:
         return NotImplementedError("The requested loss criterion is not implemented")
     weights = torch.Tensor([1] + [options.weight_seg] * options.nclasses)
-    if not getattr(options, "no_cuda", False) or torch.cuda.is_available():
-        weights = weights.cuda()       # the reference moves them unconditionally (:64)
+    if not getattr(options, "no_cuda", False) and torch.cuda.is_available():
+        weights = weights.cuda()       # the reference moves them unconditionally (:64); honour --no_cuda on a GPU box
     return loss_crit, nn.CrossEntropyLoss(weights)
 
 
@@ -87,13 +87,16 @@ class backprojection_loss(nn.Module):
 
     def _fused_host_constants(self):
         """(Y56 [56, n], y' [56], M^-1 [9]) as contiguous float64 numpy arrays for lf_backproj_loss."""
+        # keyed on the identity and in-place version of the tensors it was built from: reassigning or editing
+        # M_inv / Y / y_prime (e.g. a finetuned homography) rebuilds the host copies
+        key = tuple((id(t), t._version) for t in (self.Y, self.y_prime, self.M_inv))
         c = self.__dict__.get("_fused_consts")
-        if c is None:
-            c = self.__dict__["_fused_consts"] = (
+        if c is None or c[0] != key:
+            c = self.__dict__["_fused_consts"] = (key, (
                 self.Y.detach().cpu().double().contiguous().numpy().copy(),
                 self.y_prime.detach().cpu().double().contiguous().numpy().copy(),
-                self.M_inv.detach().cpu().double().contiguous().numpy().reshape(-1).copy())
-        return c
+                self.M_inv.detach().cpu().double().contiguous().numpy().reshape(-1).copy()))
+        return c[1]
 
     def _fused_ticket(self, device):
         t = self.__dict__.setdefault("_fused_tickets", {})

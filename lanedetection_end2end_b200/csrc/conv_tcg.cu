@@ -16,6 +16,11 @@
 // padding, mbarrier ring, warp-specialised, accumulators double-buffered in TMEM) except that the weight
 // chunk [Ng x 32] streams through the ring next to its activation box (the weight matrices of these
 // layers, up to 393 KB, do not fit in shared memory) and Ng is a run-time multiple of 16 (<= 128).
+//
+// precision 1 (3xTF32, template X3; see conv_tc_x3.cu for the arithmetic): the weight chunk is the pre-split pair
+// [W_hi rows | W_lo rows] (one TMA box of 2*Ng rows = ONE UMMA operand of N = 2*Ng), pass 1 = A_hi * [W_hi | W_lo]^T
+// into TMEM columns [0,Ng) | [Ng,2Ng); when it has completed two split warps rewrite the activation box in place with
+// A_lo, and pass 2 = A_lo * W_hi^T accumulates into [Ng,2Ng) one stage later.  The epilogue adds the two ranges.
 #include <cuda.h>
 
 #include "lf_common.cuh"
@@ -24,7 +29,8 @@
 
 namespace lf {
 
-constexpr int TG_THREADS = 192;
+constexpr int TG_THREADS = 192;       // producer, MMA issuer, 4 epilogue warps
+constexpr int TG_THREADS_X3 = 256;    // + 2 split warps (warps 2, 3)
 constexpr int TG_BM = 128;
 constexpr int TG_A_BYTES = TG_BM * 128;  // 16 KB
 constexpr int TG_MAX_STAGES = 8;
@@ -41,7 +47,8 @@ struct TgArgs {
     int kchunks, Ng, ntaps;
     int map[TG_MAXT], dy[TG_MAXT], dx[TG_MAXT];
     int stages, stage_bytes;
-    uint32_t idesc;
+    uint32_t idesc;       // pass 1: N = Ng (TF32) or 2*Ng (3xTF32)
+    uint32_t idesc_lo;    // 3xTF32 pass 2: N = Ng
     int total_tiles;
 };
 
@@ -49,7 +56,13 @@ __device__ __forceinline__ uint64_t tg_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-__global__ void __launch_bounds__(TG_THREADS, 1)
+__device__ __forceinline__ float tg_lo(float a) {   // tf32(a - trunc_tf32(a)), see conv_tc_x3.cu
+    const float r = a - __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+    return __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xffffe000u);
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(X3 ? TG_THREADS_X3 : TG_THREADS, 1)
 conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const TgArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -59,7 +72,11 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     uint64_t* empty = bars + TG_MAX_STAGES;      // [TG_MAX_STAGES]
     uint64_t* tfull = bars + 2 * TG_MAX_STAGES;  // [2]
     uint64_t* tempty = tfull + 2;                // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* hdone = tempty + 2;                // [TG_MAX_STAGES] X3: pass 1 done, the A box may be rewritten
+    uint64_t* lordy = hdone + TG_MAX_STAGES;     // [TG_MAX_STAGES] X3: A_lo written
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lordy + TG_MAX_STAGES);
+    constexpr int EPI_W0 = X3 ? 4 : 2;           // first epilogue warp
+    constexpr int BUF_COLS = X3 ? 256 : 128;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = a.Ws / a.bx, tiles_y = a.Hs / a.by;
@@ -71,6 +88,8 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int s = 0; s < a.stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
+            mbar_init(&hdone[s], 1);
+            mbar_init(&lordy[s], 2);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
@@ -78,7 +97,7 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BUF_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -102,7 +121,7 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         uint8_t* st = smem + (size_t)stage * a.stage_bytes;
                         mbar_arrive_expect_tx(&full[stage], a.stage_bytes);
                         tma_load_5d(tm, &full[stage], st, 0, cb, x0, y0, n);
-                        tma_load_2d(&tmB, &full[stage], st + TG_A_BYTES, (t * a.kchunks + cb) * 32, 0);
+                        tma_load_2d(&tmB, &full[stage], st + TG_A_BYTES, (t * a.kchunks + cb) * 32, 0);   // X3: 2*Ng rows (hi | lo)
                     }
                     if (++stage == a.stages) {
                         stage = 0;
@@ -118,12 +137,30 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
+        // X3: pass 2 (A_lo * W_hi) of the previous stage, issued one stage late
+        bool p_valid = false, p_last = false;
+        int p_stage = 0, p_buf = 0;
+        uint32_t p_phase = 0, p_dtmem = 0;
+        auto pass2 = [&]() {
+            mbar_wait(&lordy[p_stage], p_phase);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + (size_t)p_stage * a.stage_bytes);
+            const uint64_t adesc = tg_desc_sw128(st);
+            const uint64_t bdesc = tg_desc_sw128(st + TG_A_BYTES);
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8)
+                if (leader) umma_tf32(p_dtmem + a.Ng, adesc + 2 * k8, bdesc + 2 * k8, a.idesc_lo, 1u);
+            if (leader) {
+                umma_commit(&empty[p_stage]);
+                if (p_last) umma_commit(&tfull[p_buf]);
+            }
+        };
         for (int mt = blockIdx.x; mt < a.total_tiles; mt += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t use_parity = (it >> 1) & 1;
             mbar_wait(&tempty[buf], use_parity ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * 128;
+            const uint32_t d_tmem = tmem_base + buf * BUF_COLS;
             for (int ks = 0; ks < ksteps; ++ks) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
@@ -133,13 +170,48 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
                 for (int k8 = 0; k8 < 4; ++k8)  // 8 tf32 = 32 bytes per MMA
                     if (leader) umma_tf32(d_tmem, adesc + 2 * k8, bdesc + 2 * k8, a.idesc, (ks | k8) != 0 ? 1u : 0u);
-                if (leader) umma_commit(&empty[stage]);
+                if (X3) {
+                    if (leader) umma_commit(&hdone[stage]);
+                    if (p_valid) pass2();
+                    p_valid = true;
+                    p_stage = stage; p_phase = phase; p_buf = buf; p_dtmem = d_tmem;
+                    p_last = (ks == ksteps - 1);
+                } else {
+                    if (leader) umma_commit(&empty[stage]);
+                }
                 if (++stage == a.stages) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            if (leader) umma_commit(&tfull[buf]);
+            if (!X3 && leader) umma_commit(&tfull[buf]);
+        }
+        if (X3 && p_valid) pass2();
+    } else if (X3 && warp < EPI_W0) {
+        // ================= split warps (X3): A box <- A_lo in place once pass 1 has read it =================
+        const int tid = threadIdx.x - 64;
+        const int ksteps = a.ntaps * a.kchunks;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mt = blockIdx.x; mt < a.total_tiles; mt += gridDim.x) {
+            for (int ks = 0; ks < ksteps; ++ks) {
+                mbar_wait(&full[stage], phase);
+                mbar_wait(&hdone[stage], phase);
+                float4* p = reinterpret_cast<float4*>(smem + (size_t)stage * a.stage_bytes);
+#pragma unroll 4
+                for (int i = tid; i < TG_A_BYTES / 16; i += 64) {
+                    float4 v = p[i];
+                    v.x = tg_lo(v.x); v.y = tg_lo(v.y); v.z = tg_lo(v.z); v.w = tg_lo(v.w);
+                    p[i] = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&lordy[stage]);
+                if (++stage == a.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
         }
     } else {
         // ================= epilogue (warps 2..5): thread = pixel row of the tile =================
@@ -159,8 +231,17 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             tc_fence_after();
             for (int c0 = 0; c0 < a.Ng; c0 += 16) {
                 uint32_t v[16];
-                tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + buf * 128 + c0, v);
-                tmem_ld_wait();
+                const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + buf * BUF_COLS + c0;
+                tmem_ld16(taddr, v);
+                if (X3) {
+                    uint32_t sm[16];
+                    tmem_ld16(taddr + a.Ng, sm);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(sm[q]) + __uint_as_float(v[q]));
+                } else {
+                    tmem_ld_wait();
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
@@ -181,7 +262,7 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 2 * BUF_COLS);
     }
 }
 
@@ -240,22 +321,26 @@ extern "C" int lf_conv_tcg(const LfConvTcgArgs* args, lf_stream_t stream_) {
         two = two || p.map[t] == 1;
     }
     LF_REQUIRE(!two || p.a[1].ptr);
-    a.stage_bytes = TG_A_BYTES + p.Ng * 128;
+    LF_REQUIRE(p.precision == 0 || p.precision == 1);
+    const bool x3 = p.precision == 1;
+    const int nb = x3 ? 2 * p.Ng : p.Ng;   // rows of the weight chunk: W, or W_hi | W_lo
+    a.stage_bytes = TG_A_BYTES + nb * 128;
     int stages = (TG_SMEM_LIMIT - 1024 - 512) / a.stage_bytes;
     if (stages > TG_MAX_STAGES) stages = TG_MAX_STAGES;
     a.stages = stages;
-    a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Ng >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
+    a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nb >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
+    a.idesc_lo = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Ng >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
     a.total_tiles = p.N * (p.Hs / a.by) * (p.Ws / a.bx);
 
     CUtensorMap tmA0, tmA1, tmB;
     if (!tg_encode_view(enc, &tmA0, p.a[0], p.N, p.Kc, a.bx, a.by)) return LF_ERR_CUDA;
     if (!tg_encode_view(enc, &tmA1, two ? p.a[1] : p.a[0], p.N, p.Kc, a.bx, a.by)) return LF_ERR_CUDA;
     {
-        // weights [Ng][ntaps*Kc] (K contiguous)
+        // weights [Ng][ntaps*Kc] (K contiguous); 3xTF32: [2][Ng][ntaps*Kc] = hi rows, then lo rows, one box of 2*Ng rows
         const int K = p.ntaps * p.Kc;
-        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)p.Ng};
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)nb};
         cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-        cuuint32_t box[2] = {32, (cuuint32_t)p.Ng};
+        cuuint32_t box[2] = {32, (cuuint32_t)nb};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.wg), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -267,8 +352,10 @@ extern "C" int lf_conv_tcg(const LfConvTcgArgs* args, lf_stream_t stream_) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.total_tiles < sms ? a.total_tiles : sms;
     const int smem_bytes = 1024 + a.stages * a.stage_bytes + 512;
-    cudaError_t e = cudaFuncSetAttribute(conv_tcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_LIMIT);
+    cudaError_t e = x3 ? cudaFuncSetAttribute(conv_tcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_LIMIT)
+                       : cudaFuncSetAttribute(conv_tcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_LIMIT);
     if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-    conv_tcg_kernel<<<grid, TG_THREADS, smem_bytes, stream>>>(tmA0, tmA1, tmB, a);
+    if (x3) conv_tcg_kernel<true><<<grid, TG_THREADS_X3, smem_bytes, stream>>>(tmA0, tmA1, tmB, a);
+    else conv_tcg_kernel<false><<<grid, TG_THREADS, smem_bytes, stream>>>(tmA0, tmA1, tmB, a);
     return check_launch();
 }

@@ -12,6 +12,10 @@
 // lf_wgrad_reduce and gathered into the reference weight layout by lf_pack_gather (host: ops_net.wgrad_tcg_*).
 // These layers ran at 15-25 TFLOP/s on the fp32 split-K kernels (616 + ~470 us per step); here they are bound by the
 // L2 -> shared-memory fill (every tap re-reads its activation box), ~40 us per launch.
+//
+// precision 1 (3xTF32, template X3; scheme of wgrad_tc_x3.cu): the stage gets room for B_lo behind the B boxes, four
+// split warps write B_lo = tf32(B - trunc(B)) there, pass 1 = A_hi*B_hi then A_hi*B_lo on the raw A boxes; once it
+// has completed the split warps rewrite the A boxes in place with A_lo and pass 2 = A_lo*B_hi runs one stage later.
 #include <cuda.h>
 
 #include "lf_common.cuh"
@@ -21,6 +25,7 @@
 namespace lf {
 
 constexpr int WG_THREADS_TC = 192;
+constexpr int WG_THREADS_X3 = 320;          // + 4 split warps (warps 2..5), epilogue = warps 6..9
 constexpr int WG_KP = 32;                    // pixels per stage
 constexpr int WG_BOX = WG_KP * 128;          // one [32 px x 32 ch] box = 4 KB
 constexpr int WG_MAXB = LF_WGRAD_TCG_MAX_BLOCKS;
@@ -33,7 +38,8 @@ struct WgtArgs {
     int bx, by;
     int nblocks, nb_b, Nn;   // A blocks, B blocks (Nn/32), B channels
     int map[WG_MAXB], dy[WG_MAXB], dx[WG_MAXB], cblk[WG_MAXB];
-    int stages, stage_bytes, tmem_cols;
+    int stages, stage_bytes, load_bytes, tmem_cols;   // load_bytes: what TMA writes per stage
+    int a_box0;               // index of the first A box in a stage: nb_b (TF32) or 2*nb_b (3xTF32: B, B_lo, A)
     uint32_t idesc;
     int total_patches;
 };
@@ -44,7 +50,18 @@ __device__ __forceinline__ uint64_t wgt_desc_mn(uint32_t smem_addr, uint32_t lbo
            ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
-__global__ void __launch_bounds__(WG_THREADS_TC, 1)
+__device__ __forceinline__ float4 wgt_lo4(float4 v) {   // tf32(v - trunc_tf32(v)) per component, see conv_tc_x3.cu
+    float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float d = r[i] - __uint_as_float(__float_as_uint(r[i]) & 0xffffe000u);
+        r[i] = __uint_as_float((__float_as_uint(d) + 0x1000u) & 0xffffe000u);
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(X3 ? WG_THREADS_X3 : WG_THREADS_TC, 1)
 wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const WgtArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -54,7 +71,10 @@ wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint64_t* full = bars;
     uint64_t* empty = bars + WG_MAX_STAGES;
     uint64_t* done = bars + 2 * WG_MAX_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    uint64_t* glo = done + 1;                    // [S] X3: B_lo written
+    uint64_t* hdone = glo + WG_MAX_STAGES;       // [S] X3: pass 1 done, the A boxes may be rewritten
+    uint64_t* lordy = hdone + WG_MAX_STAGES;     // [S] X3: A_lo written
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lordy + WG_MAX_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (a.total_patches + gridDim.x - 1) / gridDim.x;
@@ -70,6 +90,9 @@ wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int s = 0; s < a.stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
+            mbar_init(&glo[s], 4);
+            mbar_init(&hdone[s], 1);
+            mbar_init(&lordy[s], 4);
         }
         mbar_init(done, 1);
         fence_barrier_init();
@@ -93,10 +116,10 @@ wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_wait(&empty[stage], phase ^ 1);
             if (leader) {
                 uint8_t* st = smem + (size_t)stage * a.stage_bytes;
-                mbar_arrive_expect_tx(&full[stage], a.stage_bytes);
+                mbar_arrive_expect_tx(&full[stage], a.load_bytes);
                 for (int cb = 0; cb < a.nb_b; ++cb) tma_load_5d(&tmB, &full[stage], st + cb * WG_BOX, 0, cb, x0, y0, n);
                 for (int b = 0; b < a.nblocks; ++b)
-                    tma_load_5d(a.map[b] ? &tmA1 : &tmA0, &full[stage], st + (a.nb_b + b) * WG_BOX, 0, a.cblk[b], x0 + a.dx[b],
+                    tma_load_5d(a.map[b] ? &tmA1 : &tmA0, &full[stage], st + (a.a_box0 + b) * WG_BOX, 0, a.cblk[b], x0 + a.dx[b],
                                 y0 + a.dy[b], n);
             }
             if (++stage == a.stages) {
@@ -109,29 +132,84 @@ wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const bool leader = elect_one();
         int stage = 0;
         uint32_t phase = 0;
-        bool first = true;
-        for (int p = p_begin; p < p_end; ++p) {
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
-            const uint32_t st = smem_u32(smem + (size_t)stage * a.stage_bytes);
+        bool first = true, p_valid = false;
+        int p_stage = 0;
+        uint32_t p_phase = 0;
+        // all groups x k8 steps of one stage against the B operand `b_box` boxes into the stage
+        auto pass = [&](int stg, int b_box, bool fresh) {
+            const uint32_t st = smem_u32(smem + (size_t)stg * a.stage_bytes);
 #pragma unroll
             for (int k8 = 0; k8 < WG_KP / 8; ++k8) {
                 const uint32_t koff = k8 * 1024;  // 8 pixel rows
-                const uint64_t bdesc = wgt_desc_mn(st + koff, WG_BOX);
-                const uint32_t acc = (first && k8 == 0) ? 0u : 1u;
+                const uint64_t bdesc = wgt_desc_mn(st + b_box * WG_BOX + koff, WG_BOX);
+                const uint32_t acc = (fresh && k8 == 0) ? 0u : 1u;
                 for (int g = 0; g < ngroups; ++g) {
-                    const uint64_t adesc = wgt_desc_mn(st + (a.nb_b + 4 * g) * WG_BOX + koff, WG_BOX);
+                    const uint64_t adesc = wgt_desc_mn(st + (a.a_box0 + 4 * g) * WG_BOX + koff, WG_BOX);
                     if (leader) umma_tf32(tmem_base + g * a.Nn, adesc, bdesc, a.idesc, acc);
                 }
             }
+        };
+        auto pass2 = [&]() {   // A_lo * B_hi of the previous stage
+            mbar_wait(&lordy[p_stage], p_phase);
+            tc_fence_after();
+            pass(p_stage, 0, false);
+            if (leader) umma_commit(&empty[p_stage]);
+        };
+        for (int p = p_begin; p < p_end; ++p) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            pass(stage, 0, first);                    // A * B   (X3: A_hi * B_hi)
             first = false;
-            if (leader) umma_commit(&empty[stage]);
+            if (X3) {
+                mbar_wait(&glo[stage], phase);
+                tc_fence_after();
+                pass(stage, a.nb_b, false);           // A_hi * B_lo
+                if (leader) umma_commit(&hdone[stage]);
+                if (p_valid) pass2();
+                p_valid = true;
+                p_stage = stage;
+                p_phase = phase;
+            } else {
+                if (leader) umma_commit(&empty[stage]);
+            }
             if (++stage == a.stages) {
                 stage = 0;
                 phase ^= 1;
             }
         }
+        if (X3 && p_valid) pass2();
         if (leader) umma_commit(done);
+    } else if (X3 && warp < 6) {
+        // split warps (X3): B_lo next to B; then A <- A_lo in place once pass 1 has read it
+        const int tid = threadIdx.x - 64;
+        int stage = 0;
+        uint32_t phase = 0;
+        const int bv = a.nb_b * WG_BOX / 16, av = a.nblocks * WG_BOX / 16;   // float4 counts
+        for (int p = p_begin; p < p_end; ++p) {
+            uint8_t* st = smem + (size_t)stage * a.stage_bytes;
+            mbar_wait(&full[stage], phase);
+            {
+                const float4* g = reinterpret_cast<const float4*>(st);
+                float4* gl = reinterpret_cast<float4*>(st + a.nb_b * WG_BOX);
+                for (int i = tid; i < bv; i += 128) gl[i] = wgt_lo4(g[i]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&glo[stage]);
+            mbar_wait(&hdone[stage], phase);
+            {
+                float4* x = reinterpret_cast<float4*>(st + a.a_box0 * WG_BOX);
+#pragma unroll 4
+                for (int i = tid; i < av; i += 128) x[i] = wgt_lo4(x[i]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&lordy[stage]);
+            if (++stage == a.stages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
     } else {
         // epilogue: TMEM lane = row of the group (block = row / 32)
         const int lane_base = (warp & 3) * 32;
@@ -198,13 +276,17 @@ static bool wgt_encode_view(TcEncodeTiledFn enc, CUtensorMap* tm, const LfTcgVie
 using namespace lf;
 
 // number of CTAs (= partial slices) lf_wgrad_tcg will use, 0 = unsupported
-extern "C" int lf_wgrad_tcg_ctas(int N, int Hs, int Ws, int Ka, int Nn, int nblocks) {
+static int wgt_ctas(int N, int Hs, int Ws, int Ka, int Nn, int nblocks, int precision);
+extern "C" int lf_wgrad_tcg_ctas(int N, int Hs, int Ws, int Ka, int Nn, int nblocks) { return wgt_ctas(N, Hs, Ws, Ka, Nn, nblocks, 0); }
+extern "C" int lf_wgrad_tcg_ctas_x3(int N, int Hs, int Ws, int Ka, int Nn, int nblocks) { return wgt_ctas(N, Hs, Ws, Ka, Nn, nblocks, 1); }
+
+static int wgt_ctas(int N, int Hs, int Ws, int Ka, int Nn, int nblocks, int precision) {
     int bx, by;
     if (N <= 0 || Ka % 32 != 0 || Ka < 32 || Nn % 32 != 0 || Nn < 32 || Nn > 128 || nblocks < 1 || nblocks > WG_MAXB) return 0;
     if (((nblocks + 3) / 4) * Nn > 512) return 0;
     if (!wgt_pick_patch(Hs, Ws, &bx, &by)) return 0;
     if (!tc_get_encode_fn()) return 0;
-    const int stage_bytes = (Nn / 32 + nblocks) * WG_BOX;
+    const int stage_bytes = ((precision ? 2 : 1) * (Nn / 32) + nblocks) * WG_BOX;
     if ((WG_SMEM_LIMIT - 1024 - 512 - 3 * WG_BOX) / stage_bytes < 2) return 0;
     const long long patches = (long long)N * (Hs / by) * (Ws / bx);
     int dev = 0, sms = 148;
@@ -221,7 +303,9 @@ extern "C" int lf_wgrad_tcg(const LfWgradTcgArgs* args, lf_stream_t stream_) {
     if (!args) return LF_ERR_INVALID_ARGUMENT;
     const LfWgradTcgArgs& p = *args;
     LF_REQUIRE(p.a[0].ptr && p.b.ptr && p.partial && p.nctas >= 1);
-    if (!lf_wgrad_tcg_ctas(p.N, p.Hs, p.Ws, p.Ka, p.Nn, p.nblocks)) return LF_ERR_UNSUPPORTED;
+    LF_REQUIRE(p.precision == 0 || p.precision == 1);
+    const bool x3 = p.precision == 1;
+    if (!wgt_ctas(p.N, p.Hs, p.Ws, p.Ka, p.Nn, p.nblocks, p.precision)) return LF_ERR_UNSUPPORTED;
     TcEncodeTiledFn enc = tc_get_encode_fn();
     WgtArgs a{};
     wgt_pick_patch(p.Hs, p.Ws, &a.bx, &a.by);
@@ -234,7 +318,9 @@ extern "C" int lf_wgrad_tcg(const LfWgradTcgArgs* args, lf_stream_t stream_) {
         two = two || p.map[b] == 1;
     }
     LF_REQUIRE(!two || p.a[1].ptr);
-    a.stage_bytes = (a.nb_b + a.nblocks) * WG_BOX;
+    a.a_box0 = x3 ? 2 * a.nb_b : a.nb_b;
+    a.stage_bytes = (a.a_box0 + a.nblocks) * WG_BOX;
+    a.load_bytes = (a.nb_b + a.nblocks) * WG_BOX;
     int stages = (WG_SMEM_LIMIT - 1024 - 512 - 3 * WG_BOX) / a.stage_bytes;
     if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
     a.stages = stages;
@@ -249,8 +335,10 @@ extern "C" int lf_wgrad_tcg(const LfWgradTcgArgs* args, lf_stream_t stream_) {
     if (!wgt_encode_view(enc, &tmA1, two ? p.a[1] : p.a[0], p.N, p.Ka, a.bx, a.by)) return LF_ERR_CUDA;
     if (!wgt_encode_view(enc, &tmB, p.b, p.N, p.Nn, a.bx, a.by)) return LF_ERR_CUDA;
     const int smem_bytes = 1024 + a.stages * a.stage_bytes + 3 * WG_BOX + 512;
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_LIMIT);
+    cudaError_t e = x3 ? cudaFuncSetAttribute(wgrad_tcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_LIMIT)
+                       : cudaFuncSetAttribute(wgrad_tcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_LIMIT);
     if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-    wgrad_tcg_kernel<<<p.nctas, WG_THREADS_TC, smem_bytes, stream>>>(tmA0, tmA1, tmB, a);
+    if (x3) wgrad_tcg_kernel<true><<<p.nctas, WG_THREADS_X3, smem_bytes, stream>>>(tmA0, tmA1, tmB, a);
+    else wgrad_tcg_kernel<false><<<p.nctas, WG_THREADS_TC, smem_bytes, stream>>>(tmA0, tmA1, tmB, a);
     return check_launch();
 }

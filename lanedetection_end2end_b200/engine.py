@@ -14,9 +14,10 @@ import os
 
 import torch
 
-# lf_backproj_loss (one launch for the loss of all lanes + its gradient) is validated on the CPU only so far
-# (tests/test_boundary_cpu.py runs the kernel's per-point code on the host): opt-in until it has run on a GPU.
-FUSED_LOSS = os.environ.get("LANEFIT_FUSED_LOSS", "0") == "1"
+# lf_backproj_loss: one launch for the loss of all lanes + its gradient instead of ~40 tiny float64 torch launches.
+# GPU-validated (tests/test_net_gpu.py::test_fused_backprojection_loss_kernel, profiles/r02): on by default;
+# LANEFIT_FUSED_LOSS=0 falls back to the torch ops of Loss_crit.backprojection_loss.forward_lanes.
+FUSED_LOSS = os.environ.get("LANEFIT_FUSED_LOSS", "1") != "0"
 
 
 class GraphedTrainStep:

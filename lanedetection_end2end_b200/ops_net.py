@@ -166,7 +166,7 @@ def _tcg_view(t, H, W, sn, sy, sx, offset=0):
 def tcg_s2conv_ok(x, C, O):
     """stride-2 conv of x[..., :C] (dense [N,H,W,C]) to O channels on lf_conv_tcg?"""
     N, H, W, cx = x.shape
-    return (CONV_MODE == "tf32" and cx == C and (2 * C) % 32 == 0 and H % 2 == 0 and W % 2 == 0 and x.is_contiguous()
+    return (tc_mode() and cx == C and (2 * C) % 32 == 0 and H % 2 == 0 and W % 2 == 0 and x.is_contiguous()
             and int(_lib().lf_conv_tcg_supported(N, H // 2, W // 2, 2 * C, plans.pad_to(O, 16))) > 0)
 
 
@@ -180,7 +180,8 @@ def run_tcg_s2conv(x, wg, O, out, bias=None):
     a.a[1] = _tcg_view(x, H // 2, W // 2, H * W * C, 2 * W * C, 2 * C, W * C)      # odd rows
     a.wg, a.bias, a.out = wg.data_ptr(), (bias.data_ptr() if bias is not None else None), out.data_ptr()
     a.osn, a.osy, a.osx, a.oy_mul, a.oy0 = Ho * Wo * cot, Wo * cot, cot, 1, 0
-    a.N, a.Hs, a.Ws, a.Kc, a.Ng, a.ntaps = N, Ho, Wo, 2 * C, wg.shape[0], 6
+    a.N, a.Hs, a.Ws, a.Kc, a.Ng, a.ntaps = N, Ho, Wo, 2 * C, wg.shape[-2], 6
+    a.precision = int(wg.dim() == 3)       # [2, Ng, K]: the TF32 hi / lo pair of the 3xTF32 mode
     for t, (m, dy, dx) in enumerate(TCG_S2CONV_TAPS):
         a.map[t], a.dy[t], a.dx[t] = m, dy, dx
     _capi.call("lf_conv_tcg", ctypes.byref(a), _stream(), flops=2 * N * Ho * Wo * 9 * C * O, nbytes=4 * N * (H * W * C + Ho * Wo * O))
@@ -191,7 +192,7 @@ def tcg_s2convT_ok(x, I, O):
     """stride-2 transposed conv of x[..., :I] ([N,H,W,cx], cx >= pad32(I)) to O channels on lf_conv_tcg?"""
     N, H, W, cx = x.shape
     kc = plans.pad_to(I, 32)
-    return (CONV_MODE == "tf32" and cx >= kc and cx % 4 == 0 and (2 * O) % 16 == 0 and 2 * O <= 128 and x.is_contiguous()
+    return (tc_mode() and cx >= kc and cx % 4 == 0 and (2 * O) % 16 == 0 and 2 * O <= 128 and x.is_contiguous()
             and int(_lib().lf_conv_tcg_supported(N, H, W, kc, 2 * O)) > 0)
 
 
@@ -207,6 +208,7 @@ def run_tcg_s2convT(x, I, wgs, O, out, bias2=None):
         a.wg, a.bias, a.out = wgs[par].data_ptr(), (bias2.data_ptr() if bias2 is not None else None), out.data_ptr()
         a.osn, a.osy, a.osx, a.oy_mul, a.oy0 = 4 * H * W * O, 2 * W * O, 2 * O, 2, par
         a.N, a.Hs, a.Ws, a.Kc, a.Ng, a.ntaps = N, H, W, kc, 2 * O, len(taps)
+        a.precision = int(wgs[par].dim() == 3)
         for t, (dy, dx, _ky) in enumerate(taps):
             a.map[t], a.dy[t], a.dx[t] = 0, dy, dx
         _capi.call("lf_conv_tcg", ctypes.byref(a), _stream(), flops=2 * N * H * W * len(taps) * I * 2 * O,
@@ -240,13 +242,27 @@ WGRAD_TCG = os.environ.get("LANEFIT_WGRAD_TCG", "1") != "0"
 def wgrad_tcg_ok(a_t, C, b_t, Nn):
     """A = dense [N,2Hs,2Ws,C] tensor (pair view 2C channels), B = [N,Hs,Ws,>=Nn] tensor."""
     N, H2, W2, ca = a_t.shape
-    if not (WGRAD_TCG and CONV_MODE == "tf32" and ca == C and (2 * C) % 32 == 0 and H2 % 2 == 0 and W2 % 2 == 0 and Nn % 32 == 0 and Nn <= 128
+    if not (WGRAD_TCG and tc_mode() and ca == C and (2 * C) % 32 == 0 and H2 % 2 == 0 and W2 % 2 == 0 and Nn % 32 == 0 and Nn <= 128
             and b_t.shape[-1] >= Nn and b_t.shape[1] == H2 // 2 and b_t.shape[2] == W2 // 2
             and a_t.is_contiguous() and b_t.is_contiguous()):
         return False
     per_tap = (2 * C) // 32
-    taps_per_launch = 6 if ((6 * per_tap + 3) // 4) * Nn <= 512 and 6 * per_tap <= _capi.WGRAD_TCG_MAX_BLOCKS else 3
-    return int(_lib().lf_wgrad_tcg_ctas(N, H2 // 2, W2 // 2, 2 * C, Nn, taps_per_launch * per_tap)) > 0
+    taps_per_launch = _wgrad_tcg_taps_per_launch(N, H2 // 2, W2 // 2, C, Nn)
+    return taps_per_launch > 0
+
+
+def _wgrad_tcg_ctas(*args):
+    return int((_lib().lf_wgrad_tcg_ctas_x3 if x3_mode() else _lib().lf_wgrad_tcg_ctas)(*args))
+
+
+def _wgrad_tcg_taps_per_launch(N, Hs, Ws, C, Nn):
+    """6, 3 or 2 taps per launch (TMEM columns, block table and shared-memory stages permitting), 0 = unsupported."""
+    per_tap = (2 * C) // 32
+    for tpl in (6, 3, 2):
+        nb = tpl * per_tap
+        if ((nb + 3) // 4) * Nn <= 512 and nb <= _capi.WGRAD_TCG_MAX_BLOCKS and _wgrad_tcg_ctas(N, Hs, Ws, 2 * C, Nn, nb) > 0:
+            return tpl
+    return 0
 
 
 def run_wgrad_tcg(a_t, C, b_t, Nn):
@@ -257,18 +273,19 @@ def run_wgrad_tcg(a_t, C, b_t, Nn):
     Ka = 2 * C
     per_tap = Ka // 32
     cb_tot = b_t.shape[-1]
-    taps_per_launch = 6 if ((6 * per_tap + 3) // 4) * Nn <= 512 and 6 * per_tap <= _capi.WGRAD_TCG_MAX_BLOCKS else 3
+    taps_per_launch = _wgrad_tcg_taps_per_launch(N, Hs, Ws, C, Nn)
     res = torch.empty(6 * Ka, Nn, dtype=torch.float32, device=a_t.device)
     st = _stream()
     for t0 in range(0, 6, taps_per_launch):
         nblocks = taps_per_launch * per_tap
-        nctas = int(_lib().lf_wgrad_tcg_ctas(N, Hs, Ws, Ka, Nn, nblocks))
+        nctas = _wgrad_tcg_ctas(N, Hs, Ws, Ka, Nn, nblocks)
         partial = torch.empty(nctas * nblocks * 32 * Nn, dtype=torch.float32, device=a_t.device)
         a = _capi.LfWgradTcgArgs()
         a.a[0] = _tcg_view(a_t, Hs, Ws, H2 * W2 * C, 2 * W2 * C, 2 * C)
         a.a[1] = _tcg_view(a_t, Hs, Ws, H2 * W2 * C, 2 * W2 * C, 2 * C, W2 * C)
         a.b = _tcg_view(b_t, Hs, Ws, Hs * Ws * cb_tot, Ws * cb_tot, cb_tot)
         a.partial, a.N, a.Hs, a.Ws, a.Ka, a.Nn, a.nblocks, a.nctas = partial.data_ptr(), N, Hs, Ws, Ka, Nn, nblocks, nctas
+        a.precision = int(x3_mode())
         for i in range(nblocks):
             m, dy, dx = TCG_S2CONV_TAPS[t0 + i // per_tap]
             a.map[i], a.dy[i], a.dx[i], a.cblk[i] = m, dy, dx, i % per_tap
@@ -894,7 +911,7 @@ class DownFunction(torch.autograd.Function):
         phases, (Ho, Wo) = plans.conv_fwd_plan(H, W, 3, 3, 2, 1, 1, 1, 1)
         cat = _empty((N, Ho, Wo, cout), x)
         if cc % 16 == 0 and tcg_s2conv_ok(x, cin, cc):
-            run_tcg_s2conv(x, packed(w, "tcg_s2conv", pack_tcg_s2conv), cc, cat, bias=b)
+            run_tcg_s2conv(x, packed(w, "tcg_s2conv", pack_tcg_s2conv, split=x3_mode()), cc, cat, bias=b)
         else:
             wmat = packed(w, "conv_fwd_%d" % cin_gemm, lambda t: pack_conv_fwd(t, cin_gemm))
             run_conv(phases, x, wmat, cin_gemm, cat, cc, 0, bias=b)
@@ -934,7 +951,7 @@ class DownFunction(torch.autograd.Function):
             dx = _empty((N, H, W, cx), x)
             if cx == cin and tcg_s2convT_ok(dcat, cc, cin):
                 kc = plans.pad_to(cc, 32)
-                wgs = tuple(packed(w, "tcg_s2convT%d_%d" % (par, kc), lambda t, par=par: pack_tcg_s2convT(t, par, kc))
+                wgs = tuple(packed(w, "tcg_s2convT%d_%d" % (par, kc), lambda t, par=par: pack_tcg_s2convT(t, par, kc), split=x3_mode())
                             for par in (0, 1))
                 run_tcg_s2convT(dcat, cc, wgs, cin, dx)
             else:
@@ -1029,7 +1046,7 @@ class UpFunction(torch.autograd.Function):
         co = w.shape[1]
         phases, (Ho, Wo) = plans.transposed_gather_plan(H, W, 2 * H, 2 * W, 3, 1)
         if tcg_s2convT_ok(x, ci, co):
-            wgs = tuple(packed(w, "tcg_s2convT%d_%d" % (par, ci), lambda t, par=par: pack_tcg_s2convT(t, par, ci))
+            wgs = tuple(packed(w, "tcg_s2convT%d_%d" % (par, ci), lambda t, par=par: pack_tcg_s2convT(t, par, ci), split=x3_mode())
                         for par in (0, 1))
             u = run_tcg_s2convT(x, ci, wgs, co, _empty((N, Ho, Wo, co), x), bias2=packed(b, "tile2", lambda t: t.repeat(2)))
         else:
@@ -1057,7 +1074,7 @@ class UpFunction(torch.autograd.Function):
             run_wgrad(plans.convT_wgrad_plan(H, W, 3, 1), x, ci, du, co, 0, N, dw, (1, co * 9, 9))
         run_colsum(du, co, 0, db)
         if ci % 16 == 0 and tcg_s2conv_ok(du, co, ci):
-            dx = run_tcg_s2conv(du, packed(w, "tcg_s2conv", pack_tcg_s2conv), ci, torch.empty_like(x))
+            dx = run_tcg_s2conv(du, packed(w, "tcg_s2conv", pack_tcg_s2conv, split=x3_mode()), ci, torch.empty_like(x))
         else:
             pd, _ = plans.convT_dgrad_plan(2 * H, 2 * W, H, W, 3, 1)
             dx = run_conv(pd, du, packed(w, "convT_dgrad", pack_convT_dgrad), co, torch.empty_like(x), ci)
