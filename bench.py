@@ -3,7 +3,7 @@
 ERFNet -> activation/mask -> weighted least squares -> backprojection loss.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels via the C ABI)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own modules on the host cores, rank 0 only
 
 Workload (BASELINE.json configs[1]): egolane 2-lane, order 2, batch 32 per GPU, 256x512, fp32 I/O,
 model.train() with dropout, `zero_grad -> forward -> loss -> backward` (optimizer excluded).
@@ -31,6 +31,20 @@ CONFIGS = {
     3: dict(name="tusimple_4lane_b64_256x512", nclasses=4, order=3, mask=0.2, resize=256, batch=64),
     4: dict(name="tusimple_4lane_b32pergpu_320x640", nclasses=4, order=3, mask=0.2, resize=320, batch=32),
 }
+MODE_DTYPE = {"tf32x3": "fp32 (storage fp32; products 3xTF32 on tcgen05 = fp32-grade; fp32 accumulate)",
+              "tf32": "tf32 (storage fp32; single-pass TF32 products on tcgen05; fp32 accumulate)",
+              "fp32": "fp32 (CUDA-core FFMA)"}
+MODE_TEXT = {"tf32x3": "3xTF32 on tcgen05 (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi, TMEM fp32 accumulators) for every convolution but the "
+                       "3->13 stem and the 16->L output ConvTranspose2d (fp32 FFMA): 3-tap convs conv_tc_x3.cu (C=16 as 4-pixel "
+                       "super-pixels), stride-2 layers conv_tcg.cu, weight gradients wgrad_tc_x3.cu / wgrad_tcg.cu",
+             "tf32": "single-pass TF32 on tcgen05 for the same layers (what cuDNN's default does for the reference's fp32 convs)",
+             "fp32": "every convolution on the CUDA-core FFMA kernels (conv_f32.cu, wgrad_f32.cu)"}
+MODE_ACCURACY = {"tf32x3": "meets the reference-fp32 gates: on the reference's golden inputs |ours - fp64| <= 4 |reference fp32 - fp64| + "
+                           "1e-4 for every block output, beta and the loss (tests/test_net_gpu.py, __graft_entry__.smoke(); measured "
+                           "numbers in profiles/r02/accuracy_*.json)",
+                 "tf32": "beta 1.1e-3 (2 lanes, order 2) / 2.1e-3 (4 lanes, order 3) norm-wise from fp64 on the golden inputs -- OUTSIDE "
+                         "the 1e-4 gate; labelled extra only (profiles/r01/tf32_accuracy_*.json)",
+                 "fp32": "meets the same gates as tf32x3 (tests/test_net_gpu.py)"}
 FWD_GFLOP_PER_IMG = {(2, 256): 13.231, (4, 256): 13.239, (4, 320): 20.686, (2, 320): 20.673}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
@@ -116,9 +130,86 @@ def host_batch(cfg, seed, pinned):
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle's CPU restatement of the reference path (kind "port";
-# the reference is Python and cannot travel to the GPU box)
+# reference arm / cpu_baseline: the reference's OWN modules (unmodified; /root/reference in the build container,
+# the verbatim copy under baseline/_ref/ on the GPU box -- oracle/reference_import.py) on the host cores, kind
+# "reference"; only if neither is present, the oracle's CPU restatement (kind "port").
 # ----------------------------------------------------------------------------------------------
+def _pick_threads(one_step_probe, cores):
+    """ "all the host threads it can use": the thread count that is actually fastest on this host (128 threads on
+    these small convolutions are far slower than 16-32), found on a 2-image probe."""
+    import torch
+    best_nt, best_t = cores, None
+    for nt in sorted({n for n in (8, 16, 32, 64, cores) if n <= cores}):
+        torch.set_num_threads(nt)
+        one_step_probe()
+        t0 = time.perf_counter()
+        one_step_probe()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best_nt, best_t = nt, dt
+    torch.set_num_threads(best_nt)
+    return best_nt
+
+
+def _time_cpu_steps(one_step, steps, warmup):
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        one_step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return statistics.median(times)
+
+
+def cpu_reference_run(cfg, steps, warmup, sample_images):
+    """The unmodified reference: Networks.LSQ_layer.Net + Loss_crit.backprojection_loss, model.train(),
+    zero_grad -> forward -> per-lane loss -> backward (BP/main.py:286-305,338-339), fp32, CPU."""
+    import contextlib
+    import io
+    import torch
+    from oracle import reference_import as ri
+    if cfg["resize"] != 256:
+        # the reference's own grid has +-inf in row 34 at --resize 320 and returns NaN (SURVEY.md 7.2 #10); it still
+        # executes the same work, so it is timed; its outputs are not used
+        pass
+    ns = ri.import_reference("Backprojection_Loss")
+    cores = os.cpu_count() or 1
+    L, order, R = cfg["nclasses"], cfg["order"], cfg["resize"]
+    Bs = max(1, min(cfg["batch"], sample_images))
+    args = ri.make_args(ns, ["--nclasses", str(L), "--order", str(order), "--batch_size", str(Bs), "--mask_percentage",
+                             str(cfg["mask"]), "--resize", str(R), "--loss_policy", "backproject", "--end_to_end", "True"])
+    torch.manual_seed(0)
+    model = ns.LSQ_layer.Net(args)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ns.utils.define_init_weights(model, "kaiming")
+    model.train()
+    crit = ns.Loss_crit.backprojection_loss(args)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(Bs, 3, R, 2 * R, generator=g)
+    xgt = torch.rand(Bs, 4, 56, generator=g, dtype=torch.float64) * 500.0
+    valid = torch.ones(Bs, 4, 56, dtype=torch.float64)
+    valid[:, :, :8] = 0
+    gt_line = torch.zeros(Bs, 4)
+
+    def one_step(n=Bs):
+        model.zero_grad()
+        out = model(x[:n], gt_line[:n], True)
+        loss = sum(crit(out[l], xgt[:n, l], valid[:n, l])[0] for l in range(L)) / L
+        loss.backward()
+
+    # the reference sizes its grid / constants for args.batch_size: the probe uses the full sample
+    cores_used = _pick_threads(one_step, cores)
+    med = _time_cpu_steps(one_step, steps, warmup)
+    ri.purge()
+    return {"value": Bs / med, "unit": "images/sec", "cores": cores_used, "kind": "reference",
+            "sample": "%d steps x %d images (of the %d-image batch), fwd+bwd fp32, the reference's own Networks.LSQ_layer.Net + "
+                      "Loss_crit.backprojection_loss (unmodified, from %s), torch %s CPU, %d threads (fastest of the tried "
+                      "counts; host has %d), median step %.3f s"
+                      % (steps, Bs, cfg["batch"], ri.REFERENCE_ROOT, torch.__version__, cores_used, cores, med),
+            "ms_per_step": med * 1e3, "images_per_step": Bs}
+
+
 def cpu_port_run(cfg, steps, warmup, sample_images):
     import torch
     from oracle import erfnet_oracle as eo, lsq_oracle as lo, inputs
@@ -149,27 +240,8 @@ def cpu_port_run(cfg, steps, warmup, sample_images):
                                      resize=R, skip_rows=zero_rows if R != 256 else 0)
         loss.backward()
 
-    # "all the host threads it can use": pick the thread count that is actually fastest on this host
-    # (128 threads on small convolutions are far slower than 16-32), on a 2-image probe
-    best_nt, best_t = cores, None
-    for nt in sorted({n for n in (8, 16, 32, 64, cores) if n <= cores}):
-        torch.set_num_threads(nt)
-        one_step(x[:2], xgt[:2], valid[:2])
-        t0 = time.perf_counter()
-        one_step(x[:2], xgt[:2], valid[:2])
-        dt = time.perf_counter() - t0
-        if best_t is None or dt < best_t:
-            best_nt, best_t = nt, dt
-    torch.set_num_threads(best_nt)
-    cores_used = best_nt
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        one_step(x, xgt, valid)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    med = statistics.median(times)
+    cores_used = _pick_threads(lambda: one_step(x[:2], xgt[:2], valid[:2]), cores)
+    med = _time_cpu_steps(lambda: one_step(x, xgt, valid), steps, warmup)
     return {"value": Bs / med, "unit": "images/sec", "cores": cores_used, "kind": "port",
             "sample": "%d steps x %d images (of the %d-image batch), fwd+bwd fp32, torch-CPU oracle port of the "
                       "reference modules, %d threads (fastest of the tried counts; host has %d), median step %.3f s"
@@ -177,11 +249,23 @@ def cpu_port_run(cfg, steps, warmup, sample_images):
             "ms_per_step": med * 1e3, "images_per_step": Bs}
 
 
+def cpu_baseline_run(cfg, steps, warmup, sample_images):
+    """Real reference if it is reachable (kind "reference"), else the oracle port (kind "port")."""
+    try:
+        from oracle import reference_import as ri
+        if ri.available():
+            return cpu_reference_run(cfg, steps, warmup, sample_images)
+    except Exception as e:      # missing dependency on this host, ...: say so and fall back
+        sys.stderr.write("reference arm: the reference modules could not be run (%s: %s); timing the oracle port\n"
+                         % (type(e).__name__, e))
+    return cpu_port_run(cfg, steps, warmup, sample_images)
+
+
 def run_reference_arm(a, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_port_run(cfg, a.steps, a.warmup, a.cpu_sample)
+    r = cpu_baseline_run(cfg, a.steps, a.warmup, a.cpu_sample)
     line = {"impl": "reference", "metric": "images/sec (fwd+bwd)", "value": r["value"], "unit": "images/sec",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
@@ -350,40 +434,43 @@ def run_ours(a, cfg):
     ms_e2e = timed(e2e_step, a.steps)
     clocks = sampler.stop() if sampler is not None else None
 
-    # parity arm: the same step with every convolution on the fp32 CUDA-core kernels (the mode the 1e-4
-    # parity gates run in), timed the same way, reported next to the headline
-    parity = None
-    # (N=1 only: it is a single-GPU diagnostic, and a second graph capture with NCCL inside is not worth the risk of
-    # ranks diverging on a capture error)
-    if a.conv_mode != "fp32" and a.parity_arm and world == 1:
-        ops_net.set_conv_mode("fp32")
-        try:
-            psteps = max(3, a.steps // 2)
-            pg = None
-            if a.graph:
-                from lanedetection_end2end_b200.engine import GraphedTrainStep
-                try:
-                    pg = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, None)
-                except Exception as e:
-                    sys.stderr.write("parity arm: graph capture failed (%s: %s); timing eager launches\n" % (type(e).__name__, e))
-                    pg = None
-                    torch.cuda.synchronize()
-            if pg is not None:
-                for _ in range(3):
-                    pg()
-                pms = timed(lambda: pg(), psteps)
-                del pg
-            else:
-                for _ in range(3):
-                    step(dx, dxgt, dvalid)
-                pms = timed(lambda: step(dx, dxgt, dvalid), psteps)
-            parity = {"dtype": "fp32", "conv_mode": "fp32 FFMA (parity mode)", "value": world * B * psteps / (pms * 1e-3),
-                      "unit": "images/sec", "ms_per_step": pms / psteps, "steps": psteps}
-        finally:
-            ops_net.set_conv_mode(a.conv_mode)
+    # extra arms (N=1 only: single-GPU diagnostics, and a second graph capture with NCCL inside is not worth the risk of
+    # ranks diverging on a capture error): the same step in the other two convolution modes, timed the same way and
+    # reported next to the headline as LABELLED extras -- never the headline
+    extras = {}
+    if a.parity_arm and world == 1:
+        for mode, label in (("fp32", "fp32_ffma_mode"), ("tf32", "tf32_single_pass_mode")):
+            if mode == a.conv_mode:
+                continue
+            ops_net.set_conv_mode(mode)
+            try:
+                psteps = max(3, a.steps // 2)
+                pg = None
+                if a.graph:
+                    from lanedetection_end2end_b200.engine import GraphedTrainStep
+                    try:
+                        pg = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, None)
+                    except Exception as e:
+                        sys.stderr.write("%s: graph capture failed (%s: %s); timing eager launches\n" % (label, type(e).__name__, e))
+                        pg = None
+                        torch.cuda.synchronize()
+                if pg is not None:
+                    for _ in range(3):
+                        pg()
+                    pms = timed(lambda: pg(), psteps)
+                    del pg
+                else:
+                    for _ in range(3):
+                        step(dx, dxgt, dvalid)
+                    pms = timed(lambda: step(dx, dxgt, dvalid), psteps)
+                extras[label] = {"dtype": MODE_DTYPE[mode], "conv_mode": MODE_TEXT[mode], "accuracy": MODE_ACCURACY[mode],
+                                 "value": world * B * psteps / (pms * 1e-3), "unit": "images/sec",
+                                 "ms_per_step": pms / psteps, "steps": psteps, "inputs": "resident in HBM"}
+            finally:
+                ops_net.set_conv_mode(a.conv_mode)
 
     # one traced step: CUDA events around every C-ABI launch on the launching stream
-    table, roofline, roofline_lsq = None, None, None
+    table, roofline, roofline_lsq, roofline_kernels = None, None, None, None
     peaks = load_peaks()
     # every rank runs the step (it contains the gradient all-reduce); only rank 0 records the events
     if rank == 0:
@@ -403,49 +490,64 @@ def run_ours(a, cfg):
         table = {k: dict(v, share=v["ms"] / tot if tot else 0.0) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
         dom = next(iter(table))
         d = table[dom]
-        # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture (if any)
-        traffic = None
-        try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_conv_tc_final.json")))
-            tr = [l["traffic_bytes"] for l in cap["launches"] if "conv1d_tc" in l["kernel"] and "traffic_bytes" in l]
-            if tr and dom == "lf_conv1d_tc":
-                traffic = sum(tr) / len(tr)
-        except (OSError, ValueError, KeyError):
-            pass
         hbm_peak = peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"])
-        tc_peak = peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
-        ach_b = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-        ach_f = d["flops"] / (d["ms"] * 1e-3) / 1e12
-        common = {"kernel": dom, "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
-                  "share_of_step": d["share"], "traffic": traffic,
-                  "traffic_source": "profiles/r01/ncu_conv_tc_final.json (dram__bytes_read.sum + dram__bytes_write.sum, mean over the 12 captured C=128 launches: 33.5 MB input read once, the 33.5 MB output stays in the 126 MB L2)" if traffic else None}
-        hbm = dict(common, bound="hbm", achieved=ach_b, peak=hbm_peak, unit="GB/s", frac=ach_b / hbm_peak,
-                   peak_source=peaks["_source"] + " (copy bandwidth)",
-                   algorithmic="input + output (+ mask / residual operands) tensors, 4 B per element, per launch")
-        tens = dict(common, bound="tensor", achieved=ach_f, peak=tc_peak, unit="TFLOP/s", frac=ach_f / tc_peak,
-                    peak_source=peaks["_source"] + " (sustained dense bf16; the kernel computes in tf32 = half that rate)",
-                    algorithmic="2*N*H*W*3*C*C per launch")
-        # the binding roof is the one the kernel sits closer to
-        if d["flops"] > 0 and tens["frac"] > hbm["frac"]:
-            roofline = dict(tens, other_roof={k: hbm[k] for k in ("bound", "achieved", "peak", "unit", "frac")})
-        else:
-            roofline = dict(hbm, other_roof=({k: tens[k] for k in ("bound", "achieved", "peak", "unit", "frac")}
-                                             if d["flops"] > 0 else None))
+        bf16_peak = peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
+        tf32_peak = bf16_peak / 2.0     # MEASURED_PEAKS.json has no TF32 entry: dense TF32 = half the dense bf16 rate
+        TENSOR_KERNELS = {"lf_conv1d_tc_x3": 3, "lf_conv1d_tc": 1, "lf_wgrad3_tc_x3": 3, "lf_wgrad3_tc": 1, "lf_conv_tcg": None,
+                          "lf_wgrad_tcg": None}
+
+        def kernel_roofline(name, dd):
+            """the conv / weight-gradient kernels are judged against the TENSOR roof (algorithmic FLOPs, i.e.
+            one multiply-add per product, over the TF32 dense rate), everything else against HBM; the other roof is kept
+            beside it."""
+            ach_b = dd["bytes"] / (dd["ms"] * 1e-3) / 1e9 if dd["bytes"] else None
+            ach_f = dd["flops"] / (dd["ms"] * 1e-3) / 1e12 if dd["flops"] else None
+            base = {"kernel": name, "launches_per_step": dd["launches"], "avg_launch_ms": dd["ms"] / dd["launches"],
+                    "share_of_step": dd["share"]}
+            hbm = None if ach_b is None else {"bound": "hbm", "achieved": ach_b, "peak": hbm_peak, "unit": "GB/s", "frac": ach_b / hbm_peak}
+            tens = None if ach_f is None else {"bound": "tensor", "achieved": ach_f, "peak": tf32_peak, "unit": "TFLOP/s",
+                                               "frac": ach_f / tf32_peak}
+            if name in TENSOR_KERNELS and tens is not None:
+                passes = TENSOR_KERNELS[name] or (3 if a.conv_mode == "tf32x3" else 1)
+                return dict(base, **tens, other_roof=hbm,
+                            peak_source=peaks["_source"] + ": 1/2 of the sustained dense bf16 rate (no TF32 entry in MEASURED_PEAKS.json)",
+                            algorithmic="2 * pixels * taps * Cin * Cout FLOPs per launch (one multiply-add per product)",
+                            tensor_passes_per_product=passes,
+                            tensor_pipe_work_frac=passes * tens["frac"])
+            if hbm is not None:
+                return dict(base, **hbm, other_roof=tens, peak_source=peaks["_source"] + " (copy bandwidth)",
+                            algorithmic="every input / output tensor of the launch once, 4 B per element")
+            return None
+
+        roofline = kernel_roofline(dom, d)
+        # DRAM traffic per launch of the dominant kernel: a STATIC figure from the committed `ncu --set full` capture of this
+        # kernel (profiles/r02), taken on this workload's shapes -- not measured in this run; null for other workloads
+        if roofline is not None:
+            roofline["traffic"], roofline["traffic_source"] = None, None
+            try:
+                cap = json.load(open(os.path.join(ROOT, "profiles", "r02", "ncu_%s.json" % dom)))
+                if cap.get("workload") == cfg["name"] and cap.get("batch") == B:
+                    roofline["traffic"] = cap["mean_traffic_bytes_per_launch"]
+                    roofline["traffic_source"] = "static: profiles/r02/ncu_%s.json (%s)" % (dom, cap.get("how", ""))
+            except (OSError, ValueError, KeyError):
+                pass
+        roofline_kernels = [r for r in (kernel_roofline(k, v) for k, v in list(table.items())[:10]) if r is not None]
         for k in ("lf_lsq_fwd", "lf_lsq_bwd"):
             if k in table:
                 dd = table[k]
                 ach = dd["bytes"] / (dd["ms"] * 1e-3) / 1e9
                 roofline_lsq = roofline_lsq or {}
-                roofline_lsq[k] = {"bound": "hbm", "achieved": ach, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                                   "frac": ach / peaks.get("hbm_gbs"), "avg_launch_ms": dd["ms"] / dd["launches"],
-                                   "note": "launch-latency regime at this size; see bench_lsq.py for the stress config"}
+                roofline_lsq[k] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": ach / hbm_peak, "avg_launch_ms": dd["ms"] / dd["launches"],
+                                   "note": "algorithmic bytes (SURVEY.md 8d: no credit for the masked rows the kernel skips); "
+                                           "launch-latency regime at this size; see tools/bench_lsq.py for the stress config"}
         outdir = os.path.join(ROOT, "gpurun_out")
         if os.path.isdir(outdir):
             json.dump(table, open(os.path.join(outdir, "kernel_table_%s_n%d.json" % (a.conv_mode, world)), "w"), indent=1)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu = cpu_port_run(cfg, 4, 1, a.cpu_sample)
+        cpu = cpu_baseline_run(cfg, 4, 1, a.cpu_sample)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -455,13 +557,12 @@ def run_ours(a, cfg):
         line = {"metric": "images/sec (fwd+bwd)", "value": imgs / (ms_dev * 1e-3), "unit": "images/sec",
                 "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "fp32" if a.conv_mode == "fp32" else "tf32 (fp32 storage and accumulate)", "data": "synthetic",
+                "dtype": MODE_DTYPE[a.conv_mode], "data": "synthetic",
                 "config": {"workload": cfg["name"], "per_gpu_batch": B, "global_batch": world * B,
                            "resolution": "%dx%d" % (cfg["resize"], 2 * cfg["resize"]), "nclasses": L,
                            "order": cfg["order"], "parallelism": "dp%d" % world,
                            "l2": "no flush needed: ~6 GB of activations per step >> 126 MB L2",
-                           "conv_mode": ("fp32 FFMA (parity mode)" if a.conv_mode == "fp32" else
-                                         "tcgen05 TF32 for the 3-tap convs of non_bottleneck_1d (C=64/128; C=16 as 4-pixel super-pixels), fp32 FFMA elsewhere"),
+                           "conv_mode": a.conv_mode + ": " + MODE_TEXT[a.conv_mode],
                            "init": "kaiming, torch.manual_seed(0)",
                            "launch": "one CUDA graph replay per step" if a.graph else "eager launches"},
                 "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
@@ -471,12 +572,8 @@ def run_ours(a, cfg):
                 "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches,
                 "clocks": clocks,
                 "algorithmic_tflops": (3 * gflop * imgs / 1e3) / (ms_dev * 1e-3) if gflop else None,
-                "roofline": roofline, "roofline_lsq": roofline_lsq, "cpu_baseline": cpu, "parity_mode": parity,
-                "accuracy": ("tf32 convs: beta within 1.1e-3 (2 lanes, order 2) / 2.1e-3 (4 lanes, order 3) norm-wise of the fp64 "
-                             "reference on the golden inputs (profiles/r01/tf32_accuracy_*.json) -- the reference itself, with its "
-                             "convolutions in cuDNN's default TF32, deviates 7.5e-4 / 2.6e-3 (profiles/r01/"
-                             "tf32_reference_emulation_*.json); fp32 parity mode (parity_mode below): 1e-6 (tests/test_net_gpu.py)")
-                if a.conv_mode == "tf32" else "fp32 mode: beta within 1e-6 norm-wise of the fp64 reference (tests/test_net_gpu.py)"}
+                "roofline": roofline, "roofline_kernels": roofline_kernels, "roofline_lsq": roofline_lsq, "cpu_baseline": cpu,
+                "extra_modes": extras or None, "accuracy": MODE_ACCURACY[a.conv_mode]}
         print(json.dumps(line), flush=True)
     if world > 1:
         # Leave without ProcessGroupNCCL's teardown: with a captured graph still referencing the communicator
@@ -499,12 +596,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
-    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=8, help="images per CPU-baseline step")
+    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=32,
+                    help="images per CPU-baseline / reference-arm step (default: the whole 32-image batch of config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every kernel eagerly instead of replaying the whole step as one CUDA graph")
-    ap.add_argument("--no-parity-arm", dest="parity_arm", action="store_false",
-                    help="skip the extra fp32 (CUDA-core, 1e-4-parity) timing reported next to the tf32 headline")
+    ap.add_argument("--no-parity-arm", "--no-extra-arms", dest="parity_arm", action="store_false",
+                    help="skip the two labelled extra timings (fp32 FFMA mode, single-pass TF32 mode) reported next to the headline")
     ap.add_argument("--conv-mode", dest="conv_mode", default=os.environ.get("LANEFIT_CONV_MODE", "tf32x3"),
                     choices=["fp32", "tf32", "tf32x3"],
                     help="tf32x3 = tcgen05 with 3xTF32 operand splits (fp32-grade, default); tf32 = single-pass TF32 on tcgen05 "

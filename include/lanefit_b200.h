@@ -172,6 +172,9 @@ int lf_conv1d_tc_supported(int N, int H, int W, int C);
  * rows of colsum_partial / stats_partial.  Unsupported shapes return LF_ERR_UNSUPPORTED (no fallback inside). */
 int lf_conv1d_tc_x3_rows(int N, int H, int W, int C, int vertical, int dil);
 int lf_conv1d_tc_x3(const LfConvTcArgs* args, lf_stream_t stream);
+/* timing experiments only (tools/x3_ablate.py): bit0 skips the epilogue body, bit2 the in-place a_lo rewrite, bit3 the
+ * lo MMAs; outputs are meaningless while bits are set.  0 = normal operation. */
+void lf_conv1d_tc_x3_set_debug(int bits);
 int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream);
 /* 2 (default) = halo-slab kernel (one TMA slab per 32-channel chunk shared by the three taps);
  * 1 = first version (one TMA box per tap).  Same results; process-wide switch for A/B measurements. */

@@ -116,6 +116,7 @@ _NET_PROTOS = {
     "lf_conv1d_tc_supported": (_i, [_i, _i, _i, _i]),
     "lf_conv1d_tc_x3": (_i, [ctypes.POINTER(LfConvTcArgs), _p]),
     "lf_conv1d_tc_x3_rows": (_i, [_i, _i, _i, _i, _i, _i]),
+    "lf_conv1d_tc_x3_set_debug": (None, [_i]),
     "lf_conv1d_tc_set_variant": (None, [_i]),
     "lf_conv1d_tc_set_debug": (None, [_i]),
     "lf_conv1d_tc_slab_ok": (_i, [_i, _i, _i, _i, _i, _i]),

@@ -192,7 +192,7 @@ conv1d_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint64_t bdesc = umma_desc_sw128(sB_u32 + p_slot * X3_B_SLOT_BYTES + t * X3_B_ATOM_BYTES);
 #pragma unroll
                 for (int k8 = 0; k8 < TC_KCH / 8; ++k8)
-                    if (leader) umma_tf32(p_dtmem + TC_BN, adesc + 2 * k8, bdesc + 2 * k8, X3_IDESC_N64, 1u);
+                    if (leader && !(a.debug & 8)) umma_tf32(p_dtmem + TC_BN, adesc + 2 * k8, bdesc + 2 * k8, X3_IDESC_N64, 1u);
             }
             if (leader) {
                 umma_commit(&empty[p_stage]);                       // slab free
@@ -254,7 +254,7 @@ conv1d_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(&full[stage], phase);    // TMA writes visible to this thread
             mbar_wait(&hdone[stage], phase);   // the tensor core has finished reading the fp32 values
             float4* p = reinterpret_cast<float4*>(sA + (size_t)stage * a.stage_bytes);
-            int i = tid;
+            int i = (a.debug & 4) ? nvec : tid;   // timing experiment: skip the rewrite
             for (; i + 3 * NT < nvec; i += 4 * NT) {
                 float4 v0 = p[i], v1 = p[i + NT], v2 = p[i + 2 * NT], v3 = p[i + 3 * NT];
                 v0.x = x3_lo(v0.x); v0.y = x3_lo(v0.y); v0.z = x3_lo(v0.z); v0.w = x3_lo(v0.w);
@@ -365,6 +365,11 @@ extern "C" int lf_conv1d_tc_x3_rows(int N, int H, int W, int C, int vertical, in
     return pl.m_ctas;
 }
 
+static int g_x3_debug = 0;
+// timing experiments only (tools/x3_ablate.py): bit0 skips the epilogue body, bit2 the a_lo rewrite, bit3 the lo MMAs;
+// outputs are meaningless while bits are set.  0 = normal operation.
+extern "C" void lf_conv1d_tc_x3_set_debug(int bits) { g_x3_debug = bits; }
+
 extern "C" int lf_conv1d_tc_x3(const LfConvTcArgs* args, lf_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!args) return LF_ERR_INVALID_ARGUMENT;
@@ -390,6 +395,7 @@ extern "C" int lf_conv1d_tc_x3(const LfConvTcArgs* args, lf_stream_t stream_) {
     a.tiles_a = pl.tiles_a; a.tiles_b = pl.tiles_b;
     a.stages = pl.stages; a.stage_bytes = pl.stage_bytes;
     a.slab_rows = (pl.TA + 2 * pl.dil) * pl.TB;
+    a.debug = g_x3_debug;
     for (int t = 0; t < 3; ++t) a.tap_row[t] = (pl.fwd_order ? t : 2 - t) * pl.dil * pl.TB;
     a.n_halves = p.C / TC_BN;
     a.total_m_tiles = p.N * pl.tiles_a * pl.tiles_b;

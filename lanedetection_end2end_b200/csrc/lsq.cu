@@ -290,6 +290,17 @@ __device__ __noinline__ void lsq_finalize(const LsqArgs& a, int b, int l0, int n
     if (t == 0) a.tickets[ticket_idx] = 0;  // leave the workspace reusable
 }
 
+// Rows of chunk c.  The unmasked rows [mask_rows, H) and the masked rows [0, mask_rows) are BOTH split evenly over the
+// chunks of a system: masked rows cost nothing (forward without `masked`) or a zero fill, so chunks of consecutive
+// rows would leave the CTAs of the top of the image idle (round 1: 25 % of the CTAs had no work, 0.5 of the HBM roof).
+__device__ __forceinline__ void lsq_chunk_rows(const LsqArgs& a, int chunk, int& m0, int& m1, int& r0, int& r1) {
+    const long long n = a.nchunks, ha = a.H - a.mask_rows;
+    m0 = (int)(chunk * (long long)a.mask_rows / n);
+    m1 = (int)((chunk + 1) * (long long)a.mask_rows / n);
+    r0 = a.mask_rows + (int)(chunk * ha / n);
+    r1 = a.mask_rows + (int)((chunk + 1) * ha / n);
+}
+
 // Block-level tail shared by both forward kernels: red[warp][l][k] holds per-warp
 // moment sums; write this chunk's partial, take a ticket, finalize if last.
 __device__ void lsq_chunk_tail(const LsqArgs& a, double (*red)[LSQ_MAXL][LSQ_MAXNM], double (*mom)[LSQ_MAXNM], int chunk,
@@ -345,19 +356,18 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const Ls
 #pragma unroll
     for (int l = 0; l < NL; ++l) acc[l] = 0.0;
 
-    const int r_end = min(a.H, (chunk + 1) * a.rows_per_cta);
-    for (int r = chunk * a.rows_per_cta + warp; r < r_end; r += LSQ_WARPS) {
-        const size_t rowoff = (size_t)r * a.W;
-        if (r < a.mask_rows) {
-            if (a.masked) {
-                for (int l = 0; l < nl; ++l) {
-                    float* m = a.masked + ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff;
-                    for (int c4 = lane; c4 < (a.W >> 2); c4 += 32)
-                        st_stream_f4(reinterpret_cast<float4*>(m) + c4, make_float4(0.f, 0.f, 0.f, 0.f));
-                }
+    int m_begin, m_end, r_begin, r_end;
+    lsq_chunk_rows(a, chunk, m_begin, m_end, r_begin, r_end);
+    if (a.masked) {
+        for (int r = m_begin + warp; r < m_end; r += LSQ_WARPS)
+            for (int l = 0; l < nl; ++l) {
+                float* m = a.masked + ((size_t)(b * a.L + l0 + l) * a.H + r) * a.W;
+                for (int c4 = lane; c4 < (a.W >> 2); c4 += 32)
+                    st_stream_f4(reinterpret_cast<float4*>(m) + c4, make_float4(0.f, 0.f, 0.f, 0.f));
             }
-            continue;
-        }
+    }
+    for (int r = r_begin + warp; r < r_end; r += LSQ_WARPS) {
+        const size_t rowoff = (size_t)r * a.W;
         float A[NL], Bx[NL];
 #pragma unroll
         for (int l = 0; l < NL; ++l) A[l] = Bx[l] = 0.f;
@@ -426,14 +436,12 @@ __global__ void __launch_bounds__(LSQ_THREADS) lsq_fwd_general_kernel(const LsqA
 #pragma unroll
     for (int k = 0; k <= LF_MAX_ORDER; ++k) T[k] = 0.0;
     const size_t map_off = ((size_t)(b * a.L + l) * a.H) * a.W;
-    const size_t p_begin = (size_t)chunk * a.rows_per_cta * a.W;
-    const size_t p_end = min((size_t)a.H, (size_t)(chunk + 1) * a.rows_per_cta) * a.W;
-    const size_t p_mask = (size_t)a.mask_rows * a.W;
+    int m_begin, m_end, r_begin, r_end;
+    lsq_chunk_rows(a, chunk, m_begin, m_end, r_begin, r_end);
+    if (a.masked)
+        for (size_t p = (size_t)m_begin * a.W + threadIdx.x; p < (size_t)m_end * a.W; p += LSQ_THREADS) a.masked[map_off + p] = 0.f;
+    const size_t p_begin = (size_t)r_begin * a.W, p_end = (size_t)r_end * a.W;
     for (size_t p = p_begin + threadIdx.x; p < p_end; p += LSQ_THREADS) {
-        if (p < p_mask) {
-            if (a.masked) a.masked[map_off + p] = 0.f;
-            continue;
-        }
         const float v = act_fn<ACT_T>(load_map1<BF16>(a.o, map_off + p), a.act);
         if (a.masked) a.masked[map_off + p] = v;
         const double w = (double)(v * v);
@@ -492,19 +500,19 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const Ls
     constexpr int V = MapVec<BF16>::V;
     const int WV = a.W / V;
     lsq_bwd_load_coeffs(a, b, l0, nl, bs, zs);
-    const int r_end = min(a.H, (chunk + 1) * a.rows_per_cta);
-    for (int r = chunk * a.rows_per_cta + warp; r < r_end; r += LSQ_WARPS) {
-        const size_t rowoff = (size_t)r * a.W;
-        if (r < a.mask_rows) {
-            float z[V];
+    int m_begin, m_end, r_begin, r_end;
+    lsq_chunk_rows(a, chunk, m_begin, m_end, r_begin, r_end);
+    for (int r = m_begin + warp; r < m_end; r += LSQ_WARPS) {   // masked rows: zero gradient
+        float z[V];
 #pragma unroll
-            for (int e = 0; e < V; ++e) z[e] = 0.f;
-            for (int l = 0; l < nl; ++l) {
-                const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff;
-                for (int cv = lane; cv < WV; cv += 32) store_mapv<BF16>(a.d_o, off + (size_t)V * cv, z);
-            }
-            continue;
+        for (int e = 0; e < V; ++e) z[e] = 0.f;
+        for (int l = 0; l < nl; ++l) {
+            const size_t off = ((size_t)(b * a.L + l0 + l) * a.H + r) * a.W;
+            for (int cv = lane; cv < WV; cv += 32) store_mapv<BF16>(a.d_o, off + (size_t)V * cv, z);
         }
+    }
+    for (int r = r_begin + warp; r < r_end; r += LSQ_WARPS) {
+        const size_t rowoff = (size_t)r * a.W;
         const double y = (double)__ldg(a.yrow + r);
         float qh[NL], ql[NL], sf[NL];
 #pragma unroll
@@ -547,34 +555,51 @@ __global__ void __launch_bounds__(LSQ_THREADS) lsq_bwd_general_kernel(const LsqA
     const int d = a.order;
     lsq_bwd_load_coeffs(a, b, l, 1, bs, zs);
     const size_t map_off = ((size_t)(b * a.L + l) * a.H) * a.W;
-    const size_t p_begin = (size_t)chunk * a.rows_per_cta * a.W;
-    const size_t p_end = min((size_t)a.H, (size_t)(chunk + 1) * a.rows_per_cta) * a.W;
-    const size_t p_mask = (size_t)a.mask_rows * a.W;
+    int m_begin, m_end, r_begin, r_end;
+    lsq_chunk_rows(a, chunk, m_begin, m_end, r_begin, r_end);
+    for (size_t p = (size_t)m_begin * a.W + threadIdx.x; p < (size_t)m_end * a.W; p += LSQ_THREADS)
+        store_map1<BF16>(a.d_o, map_off + p, 0.f);
+    const size_t p_begin = (size_t)r_begin * a.W, p_end = (size_t)r_end * a.W;
     for (size_t p = p_begin + threadIdx.x; p < p_end; p += LSQ_THREADS) {
-        float g = 0.f;
-        if (p >= p_mask) {
-            const float o = load_map1<BF16>(a.o, map_off + p);
-            const double y = (double)__ldg(a.ytab + p);
-            double q = bs[0][0], s = zs[0][0];
-            for (int i = 1; i <= d; ++i) {
-                q = fma(q, y, bs[0][i]);
-                s = fma(s, y, zs[0][i]);
-            }
-            g = (float)((double)dact_times_act<ACT_T>(o, a.act) * ((double)__ldg(a.xtab + p) - q) * s);
+        const float o = load_map1<BF16>(a.o, map_off + p);
+        const double y = (double)__ldg(a.ytab + p);
+        double q = bs[0][0], s = zs[0][0];
+        for (int i = 1; i <= d; ++i) {
+            q = fma(q, y, bs[0][i]);
+            s = fma(s, y, zs[0][i]);
         }
+        const float g = (float)((double)dact_times_act<ACT_T>(o, a.act) * ((double)__ldg(a.xtab + p) - q) * s);
         store_map1<BF16>(a.d_o, map_off + p, g);
     }
 }
 
-static int pick_rows_per_cta(int B, int groups, int H) {
-    // aim at ~2 waves of 4 resident CTAs per SM; every CTA pays a fixed tail (block reduction,
-    // fence, ticket), so rows per CTA grow with the problem instead of the CTA count
-    const long long target = 148LL * 4 * 2;
-    long long R = ((long long)B * groups * H + target - 1) / target;
-    R = ((R + LSQ_WARPS - 1) / LSQ_WARPS) * LSQ_WARPS;
-    if (R < LSQ_WARPS) R = LSQ_WARPS;
-    if (R > 64) R = 64;
-    return (int)R;
+// Chunks per system (image x lane group).  Every chunk gets an equal share of the unmasked rows (and of the masked
+// rows), so all CTAs carry the same work; the count is chosen so that the CTAs fill whole waves of 4 resident CTAs
+// per SM (the tail wave of a 1.7-wave grid cost 15 % in round 1), at least one row per warp and chunk, and few enough
+// chunks that the per-CTA tail (block reduction, fence, ticket) stays small.
+static int pick_nchunks(int B, int groups, int H, int mask_rows) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long slots = (long long)sms * 4, units = (long long)B * groups;
+    const int ha = H - mask_rows > 0 ? H - mask_rows : 1;
+    const int n_max = ha / LSQ_WARPS > 1 ? ha / LSQ_WARPS : 1;          // >= 8 unmasked rows per chunk
+    const int n_cap = (H + LSQ_WARPS - 1) / LSQ_WARPS;                  // what lf_lsq_workspace_bytes provides
+    int best = 1;
+    double best_score = -1.0;
+    for (int n = 1; n <= n_max && n <= n_cap; ++n) {
+        const long long ctas = units * n;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double fill = (double)ctas / (double)(waves * slots);      // how full the waves are
+        const double rows = (double)ha / n;
+        const double tail = rows / (rows + 6.0);                         // fixed per-CTA cost ~ 6 rows' worth
+        const double score = fill * tail;
+        if (score > best_score + 1e-9) {
+            best_score = score;
+            best = n;
+        }
+    }
+    return best;
 }
 
 static int validate(const LsqArgs& a, int o_dtype) {
@@ -671,8 +696,8 @@ extern "C" int lf_lsq_fwd(const void* o, int o_dtype, const float* xtab, const f
     if (!rowsep && !ytab) return LF_ERR_INVALID_ARGUMENT;
     int groups = L, nlg = 1;
     if (rowsep) lsq_lane_groups(L, &groups, &nlg);
-    a.rows_per_cta = pick_rows_per_cta(B, groups, H);
-    a.nchunks = (H + a.rows_per_cta - 1) / a.rows_per_cta;
+    a.nchunks = pick_nchunks(B, groups, H, mask_rows);
+    a.rows_per_cta = 0;
     a.tickets = reinterpret_cast<int*>(workspace);
     a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + LSQ_TICKET_BYTES);
     dim3 grid(a.nchunks, B, groups);
@@ -698,8 +723,8 @@ extern "C" int lf_lsq_bwd(const void* o, int o_dtype, const float* xtab, const f
     if (!rowsep && !ytab) return LF_ERR_INVALID_ARGUMENT;
     int groups = L, nlg = 1;
     if (rowsep) lsq_lane_groups(L, &groups, &nlg);
-    a.rows_per_cta = pick_rows_per_cta(B, groups, H);
-    a.nchunks = (H + a.rows_per_cta - 1) / a.rows_per_cta;
+    a.nchunks = pick_nchunks(B, groups, H, mask_rows);
+    a.rows_per_cta = 0;
     dim3 grid(a.nchunks, B, groups);
     if (rowsep)
         LSQ_DISPATCH_NL(lsq_bwd_rowsep_kernel, nlg, grid, a);

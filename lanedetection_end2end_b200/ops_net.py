@@ -797,7 +797,7 @@ def bn_forward_stats(x, gamma, beta, running_mean, running_var, training):
     if training:
         nblk = h.lf_bn_blocks(npix, C)
         part = torch.empty(nblk * 2 * C, dtype=torch.float64, device=x.device)
-        _capi.call("lf_bn_stats", ptr(x), npix, C, ptr(part), _stream())
+        _capi.call("lf_bn_stats", ptr(x), npix, C, ptr(part), _stream(), nbytes=4 * npix * C)
         return bn_finalize(part, nblk, npix, C, gamma, beta, running_mean, running_var)
     s = _bn_state(C, x.device)
     _capi.call("lf_bn_eval_prepare", C, ptr(gamma), ptr(beta), BN_EPS, ptr(running_mean), ptr(running_var),
@@ -827,7 +827,7 @@ def bn_apply(x, s, relu, drop=None, res=None):
     y = torch.empty_like(x)
     ppi = x.shape[1] * x.shape[2]
     _capi.call("lf_bn_apply", ptr(x), npix, C, ppi, ptr(s.scale), ptr(s.shift), ptr(drop), ptr(res), int(relu), ptr(y),
-                              _stream())
+                              _stream(), nbytes=4 * npix * C * (2 + (res is not None)))
     return y
 
 
@@ -841,13 +841,13 @@ def bn_backward(dy, ymask, drop, x, s, gamma):
     nblk = h.lf_bn_blocks(npix, C)
     part = torch.empty(nblk * 2 * C, dtype=torch.float64, device=x.device)
     _capi.call("lf_bn_bwd_reduce", ptr(dy), ptr(ymask), ptr(drop), ptr(x), npix, C, ppi, ptr(s.mean), ptr(s.invstd),
-                                   ptr(part), st)
+                                   ptr(part), st, nbytes=4 * npix * C * (2 + (ymask is not None)))
     buf = torch.empty(4, C, dtype=torch.float32, device=x.device)
     dgamma, dbeta, c1, c2 = buf[0], buf[1], buf[2], buf[3]
     _capi.call("lf_bn_bwd_finalize", ptr(part), nblk, npix, C, ptr(dgamma), ptr(dbeta), ptr(c1), ptr(c2), st)
     dx = torch.empty_like(x)
     _capi.call("lf_bn_bwd_apply", ptr(dy), ptr(ymask), ptr(drop), ptr(x), npix, C, ppi, ptr(s.mean), ptr(s.invstd),
-                                  ptr(gamma), ptr(c1), ptr(c2), ptr(dx), st)
+                                  ptr(gamma), ptr(c1), ptr(c2), ptr(dx), st, nbytes=4 * npix * C * (3 + (ymask is not None)))
     return dx, dgamma, dbeta
 
 
@@ -885,7 +885,7 @@ def dgrad_relu_bn_fused(d_out, w, vertical, dil, y, x, s, gamma, beta):
                ptr(bn_status_word(d_out.device)), _capi.STATUS_BN_ZERO_WEIGHT, st)
     dx = torch.empty_like(x)
     _capi.call("lf_bn_bwd_apply", ptr(g), None, None, ptr(x), npix, C, H * W, ptr(s.mean), ptr(s.invstd), ptr(gamma), ptr(c1),
-               ptr(c2), ptr(dx), st)
+               ptr(c2), ptr(dx), st, nbytes=4 * npix * C * 3)
     return dx, dgamma, dbeta
 
 

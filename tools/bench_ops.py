@@ -39,23 +39,49 @@ def main():
         b = torch.randn(C, device=dev)
         for mode in a.modes:
             o.set_conv_mode(mode)
+            # weight operands are packed outside the timed region (in the model one lf_pack_gather launch per step does it)
+            def taps(sgn):
+                return [((sgn * (k - 1) * dil, 0) if vertical else (0, sgn * (k - 1) * dil)) for k in range(3)]
+            if C == 16:
+                wf, wd = o.pack_tc_super(w, vertical, False), o.pack_tc_super(w, vertical, True)
+                tf, td = [((k - 1, 0) if vertical else (0, k - 1)) for k in range(3)], [((1 - k, 0) if vertical else (0, 1 - k)) for k in range(3)]
+                view = lambda t: t.view(N, H, W // 4, 64)
+                bb = b.repeat(4)
+            else:
+                wf, wd, tf, td, view, bb = o.pack_tc_fwd(w), o.pack_tc_dgrad(w), taps(1), taps(-1), (lambda t: t), b
+            if mode == "tf32x3":
+                wf, wd = o.split_tf32(wf), o.split_tf32(wd)
+            outs = [torch.empty_like(view(xs[0])) for _ in range(a.rot)]
             ops = {
-                "fwd_bias_relu": lambda i: o.conv3(xs[i], w, vertical, dil, False, bias=b, relu=True),
-                "dgrad_mask": lambda i: o.conv3(gs[i], w, vertical, dil, True, mask_src=xs[i]),
-                "dgrad_add": lambda i: o.conv3(gs[i], w, vertical, dil, True, add_src=xs[i], add_mask=xs[(i + 1) % a.rot]),
-                "wgrad": lambda i: o.wgrad3(xs[i], gs[i], w, vertical, dil, bias_grad="skip"),
+                "fwd_bias_relu": lambda i: o.run_conv_tc(tf, view(xs[i]), wf, outs[i], bias=bb, relu=True),
+                "dgrad_mask": lambda i: o.run_conv_tc(td, view(gs[i]), wd, outs[i], mask_src=view(xs[i])),
+                "dgrad_add": lambda i: o.run_conv_tc(td, view(gs[i]), wd, outs[i], add_src=view(xs[i]),
+                                                      add_mask=view(xs[(i + 1) % a.rot])),
+                "wgrad (+reduce)": lambda i: o.wgrad3(xs[i], gs[i], w, vertical, dil, bias_grad="skip"),
             }
             for name, fn in ops.items():
-                for i in range(3):
-                    fn(i % a.rot)
+                # a.iters launches (cycling through the input sets) captured into a CUDA graph: the replay time is GPU
+                # time, not ctypes launch overhead (~25 us per eager launch)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for i in range(a.rot):
+                        fn(i)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for i in range(a.iters):
+                        fn(i % a.rot)
+                g.replay()
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                for i in range(a.iters):
-                    fn(i % a.rot)
+                g.replay()
                 e1.record()
                 torch.cuda.synchronize()
                 us = e0.elapsed_time(e1) * 1e3 / a.iters
+                del g
                 flops = 2.0 * N * H * W * 3 * C * C
                 nbytes = 4.0 * N * H * W * C * (2 + (name != "fwd_bias_relu") + (name == "dgrad_add"))
                 print(json.dumps({"mode": mode, "op": name, "C": C, "H": H, "W": W, "vertical": vertical, "dil": dil, "batch": N,
