@@ -153,11 +153,13 @@ typedef struct LfConvTcArgs {
     double* stats_partial; /* NULL, or [lf_conv1d_tc_supported(...)][2][C]: per-CTA sum and sum of squares of `out`
                               = the `partial` input of lf_bn_finalize (replaces an lf_bn_stats pass over `out`);
                               LF_ERR_UNSUPPORTED when the launch has to use the per-tap variant */
-    const float* stats_beta; /* NULL, or [C] (needs mask_src and stats_partial): the second statistic becomes
-                              sum(out * (mask_src - stats_beta[c])) instead of sum(out^2).  With mask_src = relu(bn(x))
-                              and stats_beta = the BatchNorm bias, mask_src - beta == gamma * xhat wherever out != 0,
-                              so the launch that produces the gradient w.r.t. relu(bn(x)) also delivers BatchNorm
-                              backward's two reductions (lf_bn_bwd_finalize_masked) without a pass over x. */
+    const float* mask_scale; /* NULL, or [C] together with mask_shift [C] (needs mask_src and stats_partial): mask_src is then
+                              a PRE-activation x, the ReLU-backward mask bit is fma(x, mask_scale[c], mask_shift[c]) > 0
+                              (bit-identical to the forward's relu(bn(x)) when scale / shift are lf_bn_finalize's), and the
+                              second statistic becomes sum(out * x) instead of sum(out^2): the launch that produces the
+                              gradient w.r.t. relu(bn(x)) also delivers BatchNorm backward's two reductions
+                              (lf_bn_bwd_finalize_sx) without a pass over (g, x) -- and without reading relu(bn(x)). */
+    const float* mask_shift;
     int N, H, W, C;
     int dy[3], dx[3];
     int relu;
@@ -270,12 +272,12 @@ int lf_bn_bwd_reduce(const float* dy, const float* ymask, const float* drop, con
                      lf_stream_t stream);
 int lf_bn_bwd_finalize(const double* partial, int nblk, long long npix, int C, float* dgamma, float* dbeta,
                        float* c1, float* c2, lf_stream_t stream);
-/* Finalize for statistics gathered by lf_conv1d_tc with stats_beta: partial[nblk][2][C*fold] holds
- * sum g and sum g*(y - beta) = gamma * sum g*xhat per (folded) channel; fold > 1 sums `fold` consecutive groups of C
- * channels (super-pixel launches).  gamma[c] == 0 makes sum g*xhat unrecoverable: *status |= status_bit. */
-int lf_bn_bwd_finalize_masked(const double* partial, int nblk, long long npix, int C, int fold, const float* gamma,
-                              float* dgamma, float* dbeta, float* c1, float* c2, int* status, int status_bit,
-                              lf_stream_t stream);
+/* Finalize for statistics gathered by lf_conv1d_tc[_x3] with mask_scale: partial[nblk][2][C*fold] holds per-CTA
+ * s1 = sum g and s2 = sum g*x (g = the masked gradient, x = the BatchNorm input) of `fold` column groups that map to
+ * the same channel (fold > 1: super-pixel layers).  dbeta = s1, dgamma = invstd*(s2 - mean*s1) (fp64),
+ * c1 = dbeta/npix, c2 = dgamma/npix = the per-channel constants lf_bn_bwd_apply takes. */
+int lf_bn_bwd_finalize_sx(const double* partial, int nblk, long long npix, int C, int fold, const float* mean,
+                          const float* invstd, float* dgamma, float* dbeta, float* c1, float* c2, lf_stream_t stream);
 int lf_bn_bwd_apply(const float* dy, const float* ymask, const float* drop, const float* x, long long npix,
                     int C, int pix_per_image, const float* mean, const float* invstd, const float* gamma,
                     const float* c1, const float* c2, float* dx, lf_stream_t stream);

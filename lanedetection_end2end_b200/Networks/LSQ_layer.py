@@ -201,21 +201,6 @@ class Net(nn.Module):
 
     def forward(self, input, gt_line, end_to_end, early_return=False, gt=None):
         line, horizon = None, None
-        if input.is_cuda:
-            # status word of the fused BatchNorm backward (ops_net.dgrad_relu_bn_fused): deferred mode shares
-            # self.lsq_status; otherwise the previous backward's word is checked here (this mode syncs anyway)
-            if self.defer_status_check:
-                if self.lsq_status is None or self.lsq_status.device != input.device:
-                    self.lsq_status = torch.zeros(1, dtype=torch.int32, device=input.device)
-                _ops_net.BN_STATUS[input.device] = self.lsq_status
-            else:
-                word = _ops_net.bn_status_word(input.device)
-                if word is self.lsq_status:
-                    word = _ops_net.BN_STATUS[input.device] = torch.zeros(1, dtype=torch.int32, device=input.device)
-                if _ops_net.FUSE_BN_BWD and int(word.item()):
-                    word.zero_()
-                    raise RuntimeError("a BatchNorm2d weight is exactly 0: the fused BatchNorm backward cannot recover its "
-                                       "gradient (set LANEFIT_FUSE_BN_BWD=0)")
         shared_encoder, output, output_seg = self.net(input, end_to_end * self.pretrained)
         if early_return:
             return output

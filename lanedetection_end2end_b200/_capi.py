@@ -15,7 +15,6 @@ LF_F32, LF_BF16 = 0, 1
 ACT_IDS = {"none": 0, "square": 1, "abs": 2, "relu": 3, "sigmoid": 4, "softplus": 5}
 SOLVER_INVERSE, SOLVER_CHOLESKY = 0, 1
 STATUS_SINGULAR, STATUS_NONFINITE, STATUS_NOT_POSDEF = 1, 2, 4
-STATUS_BN_ZERO_WEIGHT = 8      # fused BatchNorm backward met weight == 0 (ops_net.FUSE_BN_BWD, lf_bn_bwd_finalize_masked)
 MAX_ORDER = 4
 PACK_INDEX_MASK, PACK_TF32_HI, PACK_TF32_LO = 0x1fffffff, 0x20000000, 0x40000000   # LfPackJob index flags
 
@@ -57,7 +56,7 @@ class LfConvArgs(ctypes.Structure):
 
 class LfConvTcArgs(ctypes.Structure):
     _fields_ = [("inp", _p), ("wpack", _p), ("bias", _p), ("out", _p), ("mask_src", _p), ("add_src", _p),
-                ("add_mask", _p), ("colsum_partial", _p), ("stats_partial", _p), ("stats_beta", _p), ("N", _i), ("H", _i), ("W", _i), ("C", _i), ("dy", _i * 3),
+                ("add_mask", _p), ("colsum_partial", _p), ("stats_partial", _p), ("mask_scale", _p), ("mask_shift", _p), ("N", _i), ("H", _i), ("W", _i), ("C", _i), ("dy", _i * 3),
                 ("dx", _i * 3), ("relu", _i)]
 
 
@@ -149,7 +148,7 @@ _NET_PROTOS = {
     "lf_pack_gather": (_i, [_p, _i, _i, _p]),
     "lf_backproj_loss": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "lf_backproj_loss_host": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
-    "lf_bn_bwd_finalize_masked": (_i, [_p, _i, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p]),
+    "lf_bn_bwd_finalize_sx": (_i, [_p, _i, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
 }
 PROTOTYPES.update(_NET_PROTOS)
 

@@ -279,8 +279,9 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     a.out = p.out; a.bias = p.bias; a.mask_src = p.mask_src; a.add_src = p.add_src; a.add_mask = p.add_mask;
     a.colsum_partial = p.colsum_partial;
     a.stats_partial = p.stats_partial;
-    a.stats_beta = p.stats_beta;
-    LF_REQUIRE(!p.stats_beta || (p.mask_src && p.stats_partial));
+    a.mask_scale = p.mask_scale;
+    a.mask_shift = p.mask_shift;
+    LF_REQUIRE(!p.mask_scale || (p.mask_shift && p.mask_src && p.stats_partial));
     a.N = p.N; a.H = p.H; a.W = p.W; a.Ctot = p.C; a.relu = p.relu;
     a.vertical = pl.vertical; a.TA = pl.TA; a.TB = pl.TB; a.dil = pl.dil;
     a.tb_shift = (pl.TB == 8) ? 3 : 4;

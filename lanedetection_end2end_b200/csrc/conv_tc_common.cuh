@@ -26,7 +26,8 @@ struct TcArgs {
     const float* add_mask;
     float* colsum_partial;  // [gridDim.x / n_halves][Ctot] per-CTA column sums of the output, or NULL
     double* stats_partial;  // [gridDim.x / n_halves][2][Ctot] per-CTA sum and sum of squares (BatchNorm), or NULL
-    const float* stats_beta;  // non-NULL: second statistic = sum out*(mask - beta[c])  (BatchNorm backward)
+    const float* mask_scale;  // non-NULL (with mask_shift): mask_src is a PRE-activation x; the ReLU mask bit is
+    const float* mask_shift;  // fma(x, scale[c], shift[c]) > 0 and the second statistic = sum out*x  (BatchNorm backward)
     int N, H, W, Ctot;
     int vertical;           // conv axis: 1 = y (3x1), 0 = x (1x3)
     int TA, TB;             // tile extent along / across the conv axis (TA*TB = 128)
@@ -76,12 +77,15 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
     const bool pre_mask = a.mask_src != nullptr;
     const bool pre_add = (a.add_src != nullptr) && !pre_mask;  // both given: add_src is read in the loop
     float4 csum[NH], csq[NH];               // running column sums / sums of squares, per channel half
-    float4 sbeta[NH];                       // BatchNorm bias of this thread's columns (stats_beta mode)
+    float4 msc[NH], msh[NH];                // BatchNorm scale / shift of this thread's columns (mask_scale mode)
+    const bool affine_mask = a.mask_scale != nullptr;
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh) {
-        csum[hh] = csq[hh] = sbeta[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.stats_beta)
-            sbeta[hh] = __ldg(reinterpret_cast<const float4*>(a.stats_beta + n_half * TC_BN + 32 * (h_first + hh) + 4 * c4));
+        csum[hh] = csq[hh] = msc[hh] = msh[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (affine_mask) {
+            msc[hh] = __ldg(reinterpret_cast<const float4*>(a.mask_scale + n_half * TC_BN + 32 * (h_first + hh) + 4 * c4));
+            msh[hh] = __ldg(reinterpret_cast<const float4*>(a.mask_shift + n_half * TC_BN + 32 * (h_first + hh) + 4 * c4));
+        }
     }
     float4 nxt_a[AHEAD ? 8 : 1], nxt_m[AHEAD ? 8 : 1];  // operands of the next tile in flight
     int it = 0;
@@ -204,7 +208,11 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
                 const size_t off = roff[j] + 32 * hh;
                 float4 o = *reinterpret_cast<const float4*>(&stg_g[r * TC_STG_LD + 4 * c4]);
                 if (pre_mask) {
-                    const float4 mk = pre[hh][j];
+                    float4 mk = pre[hh][j];
+                    if (affine_mask) {   // the same fma the forward BatchNorm-apply performed before its ReLU: bit-identical mask
+                        mk.x = fmaf(mk.x, msc[hh].x, msh[hh].x); mk.y = fmaf(mk.y, msc[hh].y, msh[hh].y);
+                        mk.z = fmaf(mk.z, msc[hh].z, msh[hh].z); mk.w = fmaf(mk.w, msc[hh].w, msh[hh].w);
+                    }
                     o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
                     o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
                 }
@@ -221,10 +229,10 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
                 }
                 *reinterpret_cast<float4*>(a.out + off) = o;
                 csum[hh].x += o.x; csum[hh].y += o.y; csum[hh].z += o.z; csum[hh].w += o.w;
-                if (a.stats_beta) {   // pre_mask holds: pre[hh][j] is the mask operand relu(bn(x))
+                if (affine_mask) {   // pre_mask holds: pre[hh][j] is the BatchNorm input x
                     const float4 mk = pre[hh][j];
-                    csq[hh].x = fmaf(o.x, mk.x - sbeta[hh].x, csq[hh].x); csq[hh].y = fmaf(o.y, mk.y - sbeta[hh].y, csq[hh].y);
-                    csq[hh].z = fmaf(o.z, mk.z - sbeta[hh].z, csq[hh].z); csq[hh].w = fmaf(o.w, mk.w - sbeta[hh].w, csq[hh].w);
+                    csq[hh].x = fmaf(o.x, mk.x, csq[hh].x); csq[hh].y = fmaf(o.y, mk.y, csq[hh].y);
+                    csq[hh].z = fmaf(o.z, mk.z, csq[hh].z); csq[hh].w = fmaf(o.w, mk.w, csq[hh].w);
                 } else {
                     csq[hh].x = fmaf(o.x, o.x, csq[hh].x); csq[hh].y = fmaf(o.y, o.y, csq[hh].y);
                     csq[hh].z = fmaf(o.z, o.z, csq[hh].z); csq[hh].w = fmaf(o.w, o.w, csq[hh].w);

@@ -25,7 +25,7 @@
 //    block-major over them (block 0 of tiles 0..3, block 1 of tiles 0..3, ...), so a slot is refilled a whole
 //    sub-phase (4 slabs) before it is needed again and is re-read from L2 once per 4 tiles.
 // Warp roles: 0 = TMA producer (activation slabs + weight slot refills), 1 = MMA issuer (+TMEM alloc), 2.. = split warps,
-// then 4 or 8 epilogue warps; 10 or 12 warps in all (<= 3 per SM sub-partition keeps the register cap at 168).
+// then 8 epilogue warps; 12 warps in all (3 per SM sub-partition keeps the register cap at 168).
 #include "conv_tc_common.cuh"
 
 namespace lf {
@@ -49,8 +49,11 @@ __device__ __forceinline__ float x3_lo(float a) { return x3_rna_tf32(a - x3_hw_t
 template <int C, bool AHEAD = false>
 struct X3Cfg {
     static constexpr int NCB = C / TC_KCH;          // 32-channel blocks = slabs per tile
-    static constexpr int EPI_GROUPS = (C == 64 || AHEAD) ? 2 : 1;   // see conv_tc.cu
-    static constexpr int SPLIT_WARPS = (EPI_GROUPS == 2) ? 2 : 4;
+    // Two epilogue groups (one 32-channel half each) for every shape: at C = 128 the tiles of a group complete in a burst
+    // (block-major walk) and the next group needs their TMEM buffers back at once -- a single group (5k cycles per
+    // tile) stalled the MMA issuer for ~9 us per launch (tools/x3_ablate.py, profiles/r02).
+    static constexpr int EPI_GROUPS = 2;
+    static constexpr int SPLIT_WARPS = 2;
     static constexpr int EPI_T0 = 32 * (2 + SPLIT_WARPS);
     static constexpr int THREADS = EPI_T0 + 128 * EPI_GROUPS;
     static constexpr int STG_BYTES = EPI_GROUPS * TC_STG_BYTES;
@@ -178,26 +181,33 @@ conv1d_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t sB_u32 = smem_u32(sB);
         int stage = 0;
         uint32_t phase = 0;
-        // the lo MMAs of the previous slab, issued one step late
-        bool p_valid = false, p_last_of_tile = false, p_release_b = false;
-        int p_stage = 0, p_buf = 0, p_slot = 0;
-        uint32_t p_phase = 0, p_dtmem = 0;
-        auto issue_lo = [&]() {
-            mbar_wait(&lordy[p_stage], p_phase);
+        // The lo MMAs of a slab are issued LAG slabs late (2 when the ring has >= 4 stages, else 1): by then its hi MMAs have
+        // long completed and the split warps have rewritten it, so the issuer never blocks on `lordy` with an empty
+        // tensor-pipe queue (with LAG = 1 the pipe was 50 % active: ncu profiles/r02).
+        struct Pend {
+            int stage, buf, slot;
+            uint32_t phase, dtmem;
+            bool last_of_tile, release_b;
+        };
+        Pend older{}, newer{};
+        int npend = 0;
+        const int LAG = a.stages >= 4 ? 2 : 1;
+        auto issue_lo = [&](const Pend& p) {
+            mbar_wait(&lordy[p.stage], p.phase);
             tc_fence_after();
-            const uint32_t slab = smem_u32(sA + (size_t)p_stage * a.stage_bytes);
+            const uint32_t slab = smem_u32(sA + (size_t)p.stage * a.stage_bytes);
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
                 const uint64_t adesc = umma_desc_sw128(slab + a.tap_row[t] * 128);
-                const uint64_t bdesc = umma_desc_sw128(sB_u32 + p_slot * X3_B_SLOT_BYTES + t * X3_B_ATOM_BYTES);
+                const uint64_t bdesc = umma_desc_sw128(sB_u32 + p.slot * X3_B_SLOT_BYTES + t * X3_B_ATOM_BYTES);
 #pragma unroll
                 for (int k8 = 0; k8 < TC_KCH / 8; ++k8)
-                    if (leader && !(a.debug & 8)) umma_tf32(p_dtmem + TC_BN, adesc + 2 * k8, bdesc + 2 * k8, X3_IDESC_N64, 1u);
+                    if (leader && !(a.debug & 8)) umma_tf32(p.dtmem + TC_BN, adesc + 2 * k8, bdesc + 2 * k8, X3_IDESC_N64, 1u);
             }
             if (leader) {
-                umma_commit(&empty[p_stage]);                       // slab free
-                if (p_release_b) umma_commit(&bempty[p_slot]);      // last use of this weight block in the group
-                if (p_last_of_tile) umma_commit(&tfull[p_buf]);     // accumulator complete -> epilogue
+                umma_commit(&empty[p.stage]);                       // slab free
+                if (p.release_b) umma_commit(&bempty[p.slot]);      // last use of this weight block in the group
+                if (p.last_of_tile) umma_commit(&tfull[p.buf]);     // accumulator complete -> epilogue
             }
         };
         for (int g0 = 0; g0 < my_tiles; g0 += X3_NBUF) {
@@ -230,18 +240,22 @@ conv1d_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (leader) umma_tf32(d_tmem, adesc + 2 * k8, bdesc + 2 * k8, X3_IDESC_N128, (cb | t | k8) != 0 ? 1u : 0u);
                 }
                 if (leader) umma_commit(&hdone[stage]);   // the split warps may now rewrite the slab with a_lo
-                if (p_valid) issue_lo();
-                p_valid = true;
-                p_stage = stage; p_phase = phase; p_buf = buf; p_slot = slot; p_dtmem = d_tmem;
-                p_last_of_tile = (cb == NCB - 1);
-                p_release_b = Cfg::BLOCK_MAJOR && (j == gn - 1);
+                if (npend == LAG) {
+                    issue_lo(older);
+                    older = newer;
+                    --npend;
+                }
+                const Pend cur{stage, buf, slot, phase, d_tmem, cb == NCB - 1, Cfg::BLOCK_MAJOR && (j == gn - 1)};
+                if (npend == 0) older = cur; else newer = cur;
+                ++npend;
                 if (++stage == a.stages) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
         }
-        if (p_valid) issue_lo();
+        if (npend >= 1) issue_lo(older);
+        if (npend == 2) issue_lo(newer);
     } else if (warp < 2 + Cfg::SPLIT_WARPS) {
         // ================= split warps: slab <- a_lo, in place, once its hi MMAs have completed =================
         const int tid = threadIdx.x - 64;
@@ -361,7 +375,7 @@ extern "C" int lf_conv1d_tc_x3_rows(int N, int H, int W, int C, int vertical, in
     if (dil < 1) return 0;
     X3Plan pl;
     const int zero[3] = {0, 0, 0}, off[3] = {-dil, 0, dil};
-    if (!x3_make_plan(N, H, W, C, vertical ? off : zero, vertical ? zero : off, (C == 64) ? 2 : 1, &pl)) return 0;
+    if (!x3_make_plan(N, H, W, C, vertical ? off : zero, vertical ? zero : off, 2, &pl)) return 0;
     return pl.m_ctas;
 }
 
@@ -376,20 +390,17 @@ extern "C" int lf_conv1d_tc_x3(const LfConvTcArgs* args, lf_stream_t stream_) {
     const LfConvTcArgs& p = *args;
     LF_REQUIRE(p.in && p.wpack && p.out);
     X3Plan pl;
-    if (!x3_make_plan(p.N, p.H, p.W, p.C, p.dy, p.dx, (p.C == 64) ? 2 : 1, &pl)) return LF_ERR_UNSUPPORTED;
-    // residual-add launches: operands one tile ahead + two epilogue groups (if the extra staging tile leaves 3 stages at C=128)
-    bool ahead = p.add_src && !p.mask_src;
-    if (ahead && p.C == 128) {
-        X3Plan pl2;
-        if (x3_make_plan(p.N, p.H, p.W, p.C, p.dy, p.dx, 2, &pl2)) pl = pl2; else ahead = false;
-    }
+    if (!x3_make_plan(p.N, p.H, p.W, p.C, p.dy, p.dx, 2, &pl)) return LF_ERR_UNSUPPORTED;
+    // residual-add launches: operands one tile ahead
+    const bool ahead = p.add_src && !p.mask_src;
     TcEncodeTiledFn enc = tc_get_encode_fn();
     TcArgs a{};
     a.out = p.out; a.bias = p.bias; a.mask_src = p.mask_src; a.add_src = p.add_src; a.add_mask = p.add_mask;
     a.colsum_partial = p.colsum_partial;
     a.stats_partial = p.stats_partial;
-    a.stats_beta = p.stats_beta;
-    LF_REQUIRE(!p.stats_beta || (p.mask_src && p.stats_partial));
+    a.mask_scale = p.mask_scale;
+    a.mask_shift = p.mask_shift;
+    LF_REQUIRE(!p.mask_scale || (p.mask_shift && p.mask_src && p.stats_partial));
     a.N = p.N; a.H = p.H; a.W = p.W; a.Ctot = p.C; a.relu = p.relu;
     a.vertical = pl.vertical; a.TA = pl.TA; a.TB = pl.TB; a.tb_shift = pl.tb_shift; a.dil = pl.dil;
     a.tiles_a = pl.tiles_a; a.tiles_b = pl.tiles_b;

@@ -290,6 +290,12 @@ __device__ __noinline__ void lsq_finalize(const LsqArgs& a, int b, int l0, int n
     if (t == 0) a.tickets[ticket_idx] = 0;  // leave the workspace reusable
 }
 
+// Resident CTAs per SM the row-separable kernels are compiled for (register cap 128 / 64 per thread): the forward keeps
+// NL * RU * UNR 16-byte loads per thread in flight and needs the registers; memory-level parallelism comes from the
+// batched loads, not from occupancy.
+constexpr int LSQ_FWD_CTAS_PER_SM = 2;
+constexpr int LSQ_BWD_CTAS_PER_SM = 4;
+
 // Rows of chunk c.  The unmasked rows [mask_rows, H) and the masked rows [0, mask_rows) are BOTH split evenly over the
 // chunks of a system: masked rows cost nothing (forward without `masked`) or a zero fill, so chunks of consecutive
 // rows would leave the CTAs of the top of the image idle (round 1: 25 % of the CTAs had no work, 0.5 of the HBM roof).
@@ -337,7 +343,7 @@ __device__ void lsq_chunk_tail(const LsqArgs& a, double (*red)[LSQ_MAXL][LSQ_MAX
 // NL = lanes per CTA (compile time, so the loads of all lanes and column steps of a row are in flight
 // together: the kernel is latency-bound otherwise -- ncu: long_scoreboard stalls, profiles/r01).
 template <int ACT_T, bool BF16, int NL>
-__global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const LsqArgs a) {
+__global__ void __launch_bounds__(LSQ_THREADS, LSQ_FWD_CTAS_PER_SM) lsq_fwd_rowsep_kernel(const LsqArgs a) {
     __shared__ double red[LSQ_WARPS][LSQ_MAXL][LSQ_MAXNM];
     __shared__ double mom[LSQ_MAXL][LSQ_MAXNM];
     const int chunk = blockIdx.x, b = blockIdx.y, lg = blockIdx.z;
@@ -366,19 +372,35 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const Ls
                     st_stream_f4(reinterpret_cast<float4*>(m) + c4, make_float4(0.f, 0.f, 0.f, 0.f));
             }
     }
-    for (int r = r_begin + warp; r < r_end; r += LSQ_WARPS) {
-        const size_t rowoff = (size_t)r * a.W;
-        float A[NL], Bx[NL];
+    // Hot loop.  No run-time lane-count test around the loads: a partial lane group re-reads its last lane (map_base is
+    // clamped) and simply drops the duplicates afterwards -- with `if (l < nl)` around each load the compiler kept the
+    // loads of a row in separate basic blocks and every one of them was waited for on its own (ncu r01: 65 % of the
+    // stall samples on the first use of each float4, 30 % of the DRAM roof).  RU rows per warp iteration (2 for bf16
+    // maps, whose rows are only two 16-byte loads per lane) put NL * RU * UNR loads in flight per thread.
+    constexpr int RU = BF16 ? 2 : 1;
+    size_t map_base[NL];
 #pragma unroll
-        for (int l = 0; l < NL; ++l) A[l] = Bx[l] = 0.f;
+    for (int l = 0; l < NL; ++l) map_base[l] = ((size_t)(b * a.L + min(l0 + l, a.L - 1)) * a.H) * a.W;
+    for (int r = r_begin + warp * RU; r < r_end; r += LSQ_WARPS * RU) {
+        float A[RU][NL], Bx[RU][NL];
+        size_t rowoff[RU];
+        bool rvalid[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            rvalid[u] = r + u < r_end;
+            rowoff[u] = (size_t)(rvalid[u] ? r + u : r) * a.W;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) A[u][l] = Bx[u][l] = 0.f;
+        }
 #pragma unroll UNR
         for (int cv = lane; cv < WV; cv += 32) {
-            float x[V];
-            load_xv<V>(a.xtab + rowoff, cv, x);
 #pragma unroll
-            for (int l = 0; l < NL; ++l) {
-                if (l < nl) {
-                    const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff + (size_t)V * cv;
+            for (int u = 0; u < RU; ++u) {
+                float x[V];
+                load_xv<V>(a.xtab + rowoff[u], cv, x);
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    const size_t off = map_base[l] + rowoff[u] + (size_t)V * cv;
                     float o[V];
                     load_mapv<BF16>(a.o, off, o);
                     float sa = 0.f, sb = 0.f;
@@ -389,25 +411,27 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_fwd_rowsep_kernel(const Ls
                         sa += w;
                         sb = fmaf(w, x[e], sb);
                     }
-                    if (a.masked) {
+                    if (a.masked && l < nl && rvalid[u]) {
 #pragma unroll
                         for (int q = 0; q < V / 4; ++q)
                             st_stream_f4(reinterpret_cast<float4*>(a.masked + off) + q,
                                          make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
                     }
-                    A[l] += sa;
-                    Bx[l] += sb;
+                    A[u][l] += sa;
+                    Bx[u][l] += sb;
                 }
             }
         }
-        const double y = (double)__ldg(a.yrow + r);
-        double pw = 1.0;
-        for (int i = 0; i < ek && i < 2 * LF_MAX_ORDER; ++i) pw *= y;
 #pragma unroll
-        for (int l = 0; l < NL; ++l) {
-            if (l < nl) {
-                const double As = warp_sum((double)A[l]);
-                const double Bs = warp_sum((double)Bx[l]);
+        for (int u = 0; u < RU; ++u) {
+            if (!rvalid[u]) continue;                 // warp-uniform
+            const double y = (double)__ldg(a.yrow + r + u);
+            double pw = 1.0;
+            for (int i = 0; i < ek && i < 2 * LF_MAX_ORDER; ++i) pw *= y;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                const double As = warp_sum((double)A[u][l]);
+                const double Bs = warp_sum((double)Bx[u][l]);
                 acc[l] = fma(pw, useB ? Bs : As, acc[l]);
             }
         }
@@ -517,6 +541,7 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const Ls
         float qh[NL], ql[NL], sf[NL];
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
+            qh[l] = ql[l] = sf[l] = 0.f;
             if (l < nl) {
                 double q = bs[l][0], s = zs[l][0];
                 for (int i = 1; i <= d; ++i) {
@@ -534,15 +559,14 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const Ls
             load_xv<V>(a.xtab + rowoff, cv, x);
 #pragma unroll
             for (int l = 0; l < NL; ++l) {
-                if (l < nl) {
-                    const size_t off = ((size_t)(b * a.L + l0 + l) * a.H) * a.W + rowoff + (size_t)V * cv;
-                    float o[V], g[V];
-                    load_mapv<BF16>(a.o, off, o);
+                // unconditional load from a clamped lane (see the forward kernel); only the store is predicated
+                const size_t off = ((size_t)(b * a.L + min(l0 + l, a.L - 1)) * a.H) * a.W + rowoff + (size_t)V * cv;
+                float o[V], g[V];
+                load_mapv<BF16>(a.o, off, o);
 #pragma unroll
-                    for (int e = 0; e < V; ++e)
-                        g[e] = dact_times_act<ACT_T>(o[e], a.act) * (((x[e] - qh[l]) - ql[l]) * sf[l]);
-                    store_mapv<BF16>(a.d_o, off, g);
-                }
+                for (int e = 0; e < V; ++e)
+                    g[e] = dact_times_act<ACT_T>(o[e], a.act) * (((x[e] - qh[l]) - ql[l]) * sf[l]);
+                if (l < nl) store_mapv<BF16>(a.d_o, off, g);
             }
         }
     }
@@ -574,14 +598,14 @@ __global__ void __launch_bounds__(LSQ_THREADS) lsq_bwd_general_kernel(const LsqA
 }
 
 // Chunks per system (image x lane group).  Every chunk gets an equal share of the unmasked rows (and of the masked
-// rows), so all CTAs carry the same work; the count is chosen so that the CTAs fill whole waves of 4 resident CTAs
+// rows), so all CTAs carry the same work; the count is chosen so that the CTAs fill whole waves of the resident CTAs
 // per SM (the tail wave of a 1.7-wave grid cost 15 % in round 1), at least one row per warp and chunk, and few enough
 // chunks that the per-CTA tail (block reduction, fence, ticket) stays small.
-static int pick_nchunks(int B, int groups, int H, int mask_rows) {
+static int pick_nchunks(int B, int groups, int H, int mask_rows, int ctas_per_sm) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long slots = (long long)sms * 4, units = (long long)B * groups;
+    const long long slots = (long long)sms * ctas_per_sm, units = (long long)B * groups;
     const int ha = H - mask_rows > 0 ? H - mask_rows : 1;
     const int n_max = ha / LSQ_WARPS > 1 ? ha / LSQ_WARPS : 1;          // >= 8 unmasked rows per chunk
     const int n_cap = (H + LSQ_WARPS - 1) / LSQ_WARPS;                  // what lf_lsq_workspace_bytes provides
@@ -696,7 +720,7 @@ extern "C" int lf_lsq_fwd(const void* o, int o_dtype, const float* xtab, const f
     if (!rowsep && !ytab) return LF_ERR_INVALID_ARGUMENT;
     int groups = L, nlg = 1;
     if (rowsep) lsq_lane_groups(L, &groups, &nlg);
-    a.nchunks = pick_nchunks(B, groups, H, mask_rows);
+    a.nchunks = pick_nchunks(B, groups, H, mask_rows, rowsep ? LSQ_FWD_CTAS_PER_SM : 4);
     a.rows_per_cta = 0;
     a.tickets = reinterpret_cast<int*>(workspace);
     a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + LSQ_TICKET_BYTES);
@@ -723,7 +747,7 @@ extern "C" int lf_lsq_bwd(const void* o, int o_dtype, const float* xtab, const f
     if (!rowsep && !ytab) return LF_ERR_INVALID_ARGUMENT;
     int groups = L, nlg = 1;
     if (rowsep) lsq_lane_groups(L, &groups, &nlg);
-    a.nchunks = pick_nchunks(B, groups, H, mask_rows);
+    a.nchunks = pick_nchunks(B, groups, H, mask_rows, LSQ_BWD_CTAS_PER_SM);
     a.rows_per_cta = 0;
     dim3 grid(a.nchunks, B, groups);
     if (rowsep)

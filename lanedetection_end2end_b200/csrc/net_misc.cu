@@ -145,10 +145,11 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int n
     c2[c] = (float)(s2 / (double)npix);
 }
 
-// Statistics from the conv epilogue (lf_conv1d_tc with stats_beta): [0] = sum g, [1] = sum g*(y-beta) = gamma*sum g*xhat
-__global__ void bn_bwd_finalize_masked_kernel(const double* __restrict__ partial, int nblk, long long npix, int C, int fold,
-                                              const float* __restrict__ gamma, float* dgamma, float* dbeta, float* c1,
-                                              float* c2, int* status, int status_bit) {
+// Statistics from the conv epilogue (lf_conv1d_tc[_x3] with mask_scale): [0] = sum g, [1] = sum g*x  ->  sum g*xhat =
+// invstd*(sum g*x - mean*sum g), in fp64 (no division by the BatchNorm weight: exact for any gamma, including 0)
+__global__ void bn_bwd_finalize_sx_kernel(const double* __restrict__ partial, int nblk, long long npix, int C, int fold,
+                                          const float* __restrict__ mean, const float* __restrict__ invstd, float* dgamma,
+                                          float* dbeta, float* c1, float* c2) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per channel
     if (c >= C) return;
     double s1 = 0.0, s2 = 0.0;
@@ -159,17 +160,11 @@ __global__ void bn_bwd_finalize_masked_kernel(const double* __restrict__ partial
         s2 += b;
     }
     if ((threadIdx.x & 31) != 0) return;
-    const float gm = gamma[c];
-    if (gm == 0.f) {
-        if (status) atomicOr(status, status_bit);
-        s2 = 0.0;
-    } else {
-        s2 /= (double)gm;
-    }
+    const double dg = (double)invstd[c] * (s2 - (double)mean[c] * s1);
     dbeta[c] = (float)s1;
-    dgamma[c] = (float)s2;
+    dgamma[c] = (float)dg;
     c1[c] = (float)(s1 / (double)npix);
-    c2[c] = (float)(s2 / (double)npix);
+    c2[c] = (float)(dg / (double)npix);
 }
 
 // y = relu?( (x*scale+shift) * drop? + res? )
@@ -544,13 +539,12 @@ extern "C" int lf_bn_bwd_finalize(const double* partial, int nblk, long long npi
     return check_launch();
 }
 
-extern "C" int lf_bn_bwd_finalize_masked(const double* partial, int nblk, long long npix, int C, int fold, const float* gamma,
-                                         float* dgamma, float* dbeta, float* c1, float* c2, int* status, int status_bit,
-                                         lf_stream_t stream_) {
+extern "C" int lf_bn_bwd_finalize_sx(const double* partial, int nblk, long long npix, int C, int fold, const float* mean,
+                                     const float* invstd, float* dgamma, float* dbeta, float* c1, float* c2, lf_stream_t stream_) {
     STREAM;
-    LF_REQUIRE(partial && gamma && dgamma && dbeta && c1 && c2 && nblk >= 1 && fold >= 1 && C >= 1);
-    bn_bwd_finalize_masked_kernel<<<(C * 32 + 255) / 256, 256, 0, stream>>>(partial, nblk, npix, C, fold, gamma, dgamma, dbeta,
-                                                                           c1, c2, status, status_bit);
+    LF_REQUIRE(partial && mean && invstd && dgamma && dbeta && c1 && c2 && nblk >= 1 && fold >= 1 && C >= 1);
+    bn_bwd_finalize_sx_kernel<<<(C * 32 + 255) / 256, 256, 0, stream>>>(partial, nblk, npix, C, fold, mean, invstd, dgamma, dbeta,
+                                                                       c1, c2);
     return check_launch();
 }
 

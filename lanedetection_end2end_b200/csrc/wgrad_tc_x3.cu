@@ -195,23 +195,29 @@ wgrad_tc_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (p_valid) pass2();
         if (leader) umma_commit(done);
     } else if (warp < 6) {
-        // split warps
+        // split warps.  dY_lo of stage p+1 is produced BEFORE waiting for pass 1 of stage p (its TMA landed long ago), so
+        // the MMA issuer never waits for it behind the X rewrite of the previous stage.
         const int tid = threadIdx.x - 64;
         int stage = 0;
         uint32_t phase = 0;
         constexpr int GV = CB * BOX / 16, XV = 3 * CB * BOX / 16;   // float4 counts
-        for (int p = p_begin; p < p_end; ++p) {
-            uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-            mbar_wait(&full[stage], phase);
-            {
-                const float4* g = reinterpret_cast<const float4*>(st);
-                float4* gl = reinterpret_cast<float4*>(st + CB * BOX);
+        auto make_glo = [&](int stg, uint32_t ph) {
+            uint8_t* st = smem + stg * Cfg::STAGE_BYTES;
+            mbar_wait(&full[stg], ph);
+            const float4* g = reinterpret_cast<const float4*>(st);
+            float4* gl = reinterpret_cast<float4*>(st + CB * BOX);
 #pragma unroll
-                for (int i = tid; i < GV; i += 128) gl[i] = wx_lo4(g[i]);
-            }
+            for (int i = tid; i < GV; i += 128) gl[i] = wx_lo4(g[i]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&glo[stage]);
+            if (lane == 0) mbar_arrive(&glo[stg]);
+        };
+        if (p_begin < p_end) make_glo(0, 0);
+        for (int p = p_begin; p < p_end; ++p) {
+            const int nstage = (stage + 1 == S) ? 0 : stage + 1;
+            const uint32_t nphase = (stage + 1 == S) ? phase ^ 1 : phase;
+            if (p + 1 < p_end) make_glo(nstage, nphase);
+            uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
             mbar_wait(&hdone[stage], phase);
             {
                 float4* x = reinterpret_cast<float4*>(st + 2 * CB * BOX);
@@ -221,10 +227,8 @@ wgrad_tc_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&lordy[stage]);
-            if (++stage == S) {
-                stage = 0;
-                phase ^= 1;
-            }
+            stage = nstage;
+            phase = nphase;
         }
     } else {
         // epilogue: TMEM lane = GEMM row

@@ -180,22 +180,28 @@ wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         if (X3 && p_valid) pass2();
         if (leader) umma_commit(done);
     } else if (X3 && warp < 6) {
-        // split warps (X3): B_lo next to B; then A <- A_lo in place once pass 1 has read it
+        // split warps (X3): B_lo next to B; then A <- A_lo in place once pass 1 has read it.  B_lo of stage p+1 is
+        // produced before waiting for pass 1 of stage p, so the MMA issuer never waits for it behind an A rewrite.
         const int tid = threadIdx.x - 64;
         int stage = 0;
         uint32_t phase = 0;
         const int bv = a.nb_b * WG_BOX / 16, av = a.nblocks * WG_BOX / 16;   // float4 counts
-        for (int p = p_begin; p < p_end; ++p) {
-            uint8_t* st = smem + (size_t)stage * a.stage_bytes;
-            mbar_wait(&full[stage], phase);
-            {
-                const float4* g = reinterpret_cast<const float4*>(st);
-                float4* gl = reinterpret_cast<float4*>(st + a.nb_b * WG_BOX);
-                for (int i = tid; i < bv; i += 128) gl[i] = wgt_lo4(g[i]);
-            }
+        auto make_blo = [&](int stg, uint32_t ph) {
+            uint8_t* st = smem + (size_t)stg * a.stage_bytes;
+            mbar_wait(&full[stg], ph);
+            const float4* g = reinterpret_cast<const float4*>(st);
+            float4* gl = reinterpret_cast<float4*>(st + a.nb_b * WG_BOX);
+            for (int i = tid; i < bv; i += 128) gl[i] = wgt_lo4(g[i]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&glo[stage]);
+            if (lane == 0) mbar_arrive(&glo[stg]);
+        };
+        if (p_begin < p_end) make_blo(0, 0);
+        for (int p = p_begin; p < p_end; ++p) {
+            const int nstage = (stage + 1 == a.stages) ? 0 : stage + 1;
+            const uint32_t nphase = (stage + 1 == a.stages) ? phase ^ 1 : phase;
+            if (p + 1 < p_end) make_blo(nstage, nphase);
+            uint8_t* st = smem + (size_t)stage * a.stage_bytes;
             mbar_wait(&hdone[stage], phase);
             {
                 float4* x = reinterpret_cast<float4*>(st + a.a_box0 * WG_BOX);
@@ -205,10 +211,8 @@ wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&lordy[stage]);
-            if (++stage == a.stages) {
-                stage = 0;
-                phase ^= 1;
-            }
+            stage = nstage;
+            phase = nphase;
         }
     } else {
         // epilogue: TMEM lane = row of the group (block = row / 32)

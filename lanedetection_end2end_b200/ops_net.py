@@ -558,8 +558,8 @@ def _taps_axis(taps):
     return vertical, d
 
 
-def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_src=None, add_mask=None, colsum=None, stats_beta=None,
-                stats_partial=None):
+def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_src=None, add_mask=None, colsum=None,
+                mask_affine=None, stats_partial=None):
     """3-tap convolution on tcgen05.  taps: [(dy, dx)] * 3 in weight-slot order.  colsum: optional [C]
     tensor receiving the column sums of `out` (bias gradient), accumulated in the kernel's epilogue."""
     N, H, W, C = x.shape
@@ -576,8 +576,8 @@ def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_s
         a.colsum_partial = part.data_ptr()
     if stats_partial is not None:
         a.stats_partial = stats_partial.data_ptr()
-    if stats_beta is not None:
-        a.stats_beta = stats_beta.data_ptr()
+    if mask_affine is not None:        # (scale, shift): mask_src is a BatchNorm INPUT, the mask bit is fma(x, scale, shift) > 0
+        a.mask_scale, a.mask_shift = mask_affine[0].data_ptr(), mask_affine[1].data_ptr()
     a.N, a.H, a.W, a.C = N, H, W, C
     for t, (dy, dx) in enumerate(taps):
         a.dy[t], a.dx[t] = dy, dx
@@ -852,37 +852,31 @@ def bn_backward(dy, ymask, drop, x, s, gamma):
 
 
 # Fused BatchNorm backward for relu(bn(x)) feeding a 3-tap conv (BN1 of non_bottleneck_1d): the conv's input-gradient
-# launch (mask = relu(bn(x))) also accumulates sum g and sum g*(y - beta) = gamma * sum g*xhat, so the separate
-# reduction pass over (g, x) disappears.  Needs gamma != 0 (else sum g*xhat cannot be recovered from y): the finalize
-# kernel then raises a bit in BN_STATUS, which Net.forward turns into an error.
+# launch takes the BatchNorm INPUT x as its mask operand, rebuilds the ReLU mask bit with the forward's own
+# fma(x, scale, shift) > 0, and accumulates sum g and sum g*x in its epilogue, from which sum g*xhat = invstd*(sum g*x -
+# mean*sum g) -- so the separate reduction pass over (g, x) disappears, relu(bn(x)) is not read, and no division by the
+# BatchNorm weight is involved (round 1 recovered xhat from (y - beta)/gamma, undefined at gamma = 0: ADVICE r1).
 FUSE_BN_BWD = os.environ.get("LANEFIT_FUSE_BN_BWD", "1") != "0"
-BN_STATUS = {}
 
 
-def bn_status_word(device):
-    w = BN_STATUS.get(device)
-    if w is None:
-        w = BN_STATUS[device] = torch.zeros(1, dtype=torch.int32, device=device)
-    return w
-
-
-def dgrad_relu_bn_fused(d_out, w, vertical, dil, y, x, s, gamma, beta):
-    """(dgrad of the 3-tap conv) * (y > 0) -> g, then BatchNorm backward of y = relu(bn(x)) -> (dx, dgamma, dbeta);
-    returns None when the shapes are not served by the slab kernel (caller takes the two-pass route)."""
+def dgrad_relu_bn_fused(d_out, w, vertical, dil, x, s, gamma):
+    """(dgrad of the 3-tap conv) * (relu(bn(x)) > 0) -> g, then BatchNorm backward -> (dx, dgamma, dbeta); s carries the
+    forward's (mean, invstd, scale, shift).  Returns None when the shapes are not served by the slab kernel (caller takes
+    the two-pass route)."""
     N, H, W, C = d_out.shape
     rows = tc_rows(d_out, vertical, dil, stats=True) if FUSE_BN_BWD else 0
     if rows <= 0:
         return None
     part = torch.empty(rows * 2 * C, dtype=torch.float64, device=d_out.device)
     taps = [((-(k - 1) * dil, 0) if vertical else (0, -(k - 1) * dil)) for k in range(3)]
-    g = run_conv_tc(taps, d_out, packed(w, "tc_dgrad", pack_tc_dgrad, split=x3_mode()), torch.empty_like(d_out), mask_src=y,
-                    stats_partial=part, stats_beta=beta)
+    g = run_conv_tc(taps, d_out, packed(w, "tc_dgrad", pack_tc_dgrad, split=x3_mode()), torch.empty_like(d_out), mask_src=x,
+                    stats_partial=part, mask_affine=(s.scale, s.shift))
     npix = N * H * W
     buf = torch.empty(4, C, dtype=torch.float32, device=d_out.device)
     dgamma, dbeta, c1, c2 = buf[0], buf[1], buf[2], buf[3]
     st = _stream()
-    _capi.call("lf_bn_bwd_finalize_masked", ptr(part), rows, npix, C, 1, ptr(gamma), ptr(dgamma), ptr(dbeta), ptr(c1), ptr(c2),
-               ptr(bn_status_word(d_out.device)), _capi.STATUS_BN_ZERO_WEIGHT, st)
+    _capi.call("lf_bn_bwd_finalize_sx", ptr(part), rows, npix, C, 1, ptr(s.mean), ptr(s.invstd), ptr(dgamma), ptr(dbeta), ptr(c1),
+               ptr(c2), st)
     dx = torch.empty_like(x)
     _capi.call("lf_bn_bwd_apply", ptr(g), None, None, ptr(x), npix, C, H * W, ptr(s.mean), ptr(s.invstd), ptr(gamma), ptr(c1),
                ptr(c2), ptr(dx), st, nbytes=4 * npix * C * 3)
@@ -977,13 +971,13 @@ class Nb1dFunction(torch.autograd.Function):
         t5, s2 = conv3_bn_stats(t4, w4, False, dil, b4, g2, be2, rm2, rv2, training)
         y = bn_apply(t5, s2, relu=True, drop=drop, res=x)
         ctx.save_for_backward(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1.mean, s1.invstd, s2.mean, s2.invstd,
-                              drop if drop is not None else x.new_empty(0), be1)
+                              drop if drop is not None else x.new_empty(0), s1.scale, s1.shift)
         ctx.cfg = (dil, training, drop is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, m1, is1, m2, is2, drop, be1) = ctx.saved_tensors
+        (x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, m1, is1, m2, is2, drop, sc1, sh1) = ctx.saved_tensors
         dil, training, has_drop = ctx.cfg
         _require_training_for_backward(training)
         drop = drop if has_drop else None
@@ -991,16 +985,17 @@ class Nb1dFunction(torch.autograd.Function):
         N, H, W, C = x.shape
         s1, s2 = BNState(), BNState()
         s1.mean, s1.invstd, s2.mean, s2.invstd = m1, is1, m2, is2
+        s1.scale, s1.shift = sc1, sh1
 
         global _DEFERRED
         _DEFERRED = jobs = []
         try:
-            return Nb1dFunction._backward_body(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1, s2, drop, dil, dy, jobs, be1)
+            return Nb1dFunction._backward_body(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1, s2, drop, dil, dy, jobs)
         finally:
             _DEFERRED = None
 
     @staticmethod
-    def _backward_body(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1, s2, drop, dil, dy, jobs, be1):
+    def _backward_body(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1, s2, drop, dil, dy, jobs):
         N, H, W, C = x.shape
         # y = relu(bn2(t5)*drop + x)
         d5, dg2, dbe2 = bn_backward(dy, y, drop, t5, s2, g2)
@@ -1016,7 +1011,7 @@ class Nb1dFunction(torch.autograd.Function):
         d4 = conv3(d5, w4, False, dil, True, colsum=db3, mask_src=t4)
         # conv3x1_2 (dilated)
         dw3, _ = wgrad3(t3, d4, w3, True, dil, bias_grad="skip")
-        fused = dgrad_relu_bn_fused(d4, w3, True, dil, t3, t2, s1, g1, be1)
+        fused = dgrad_relu_bn_fused(d4, w3, True, dil, t2, s1, g1)
         if fused is not None:
             d2, dg1, dbe1 = fused          # dgrad + relu mask + BatchNorm reductions in one launch, then apply
         else:
