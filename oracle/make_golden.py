@@ -209,10 +209,61 @@ def run_homography():
     return "homography", out
 
 
+# ---------------------------------------------------------------------------
+# Area_Loss goldens (A12).  The reference's forward ends in ``torch.masked_select(loss_fit, mask.byte())``
+# (BP/Loss_crit.py:140-141 == BEV/Loss_crit.py:131-132), which torch >= 2 rejects (uint8 masks were removed).  The
+# reference targets torch 1.1 where a byte mask IS a boolean mask, so the run below shims exactly that dispatch
+# (masked_select accepts uint8 by viewing it as bool) and executes every other line of the reference unmodified.
+# ---------------------------------------------------------------------------
+AREA_CASES = [(2, "none"), (2, "linear"), (2, "quadratic"), (1, "none")]
+
+
+def run_area_loss():
+    out = {}
+    orig = torch.masked_select
+
+    def masked_select_torch11(x, mask):
+        return orig(x, mask.bool() if mask.dtype == torch.uint8 else mask)
+
+    rng = np.random.default_rng(1234)
+    B = 6
+    params = rng.normal(size=(B, 3, 1)) * np.array([1e-3, 0.2, 0.5]).reshape(1, 3, 1)
+    gt = rng.normal(size=(B, 3)) * np.array([1e-3, 0.2, 0.5])
+    gt[2] = 0.0                    # absent lane: all-zero ground truth -> excluded from the mean
+    gt[4, 1] = 0.0                 # one zero entry also excludes the lane (prod(gt != 0))
+    out["params"], out["gt"] = params, gt
+    torch.masked_select = masked_select_torch11
+    try:
+        for variant in ("Backprojection_Loss", "Birds_Eye_View_Loss"):
+            ns = ri.import_reference(variant)
+            for order, wf in AREA_CASES:
+                for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+                    p = torch.from_numpy(params).to(dt).requires_grad_(True)
+                    loss = ns.Loss_crit.Area_Loss(order, wf)(p, torch.from_numpy(gt).to(dt))
+                    loss.backward()
+                    key = "%s/o%d_%s_%s" % (variant[:2], order, wf, tag)
+                    out[key + "/loss"] = np.array(float(loss))
+                    out[key + "/grad"] = p.grad.double().numpy()
+            # every lane absent -> the reference returns the python int 0
+            z = ns.Loss_crit.Area_Loss(2, "none")(torch.from_numpy(params).float(), torch.zeros(B, 3))
+            out["%s/all_absent" % variant[:2]] = np.array(float(z))
+    finally:
+        torch.masked_select = orig
+        ri.purge()
+    return "area_loss", out
+
+
 def main():
+    if "--only-area" in sys.argv:      # add the A12 fixture without touching the (bit-identical) existing ones
+        os.makedirs(GOLDEN_DIR, exist_ok=True)
+        name, out = run_area_loss()
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes")
+        return 0
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    jobs = [run_homography()]
+    jobs = [run_homography(), run_area_loss()]
     for i, c in enumerate(LSQ_CASES):
         name, out = run_lsq_case(c)
         if c[0] not in ("bp_l2_d2", "bev_l2_d2"):

@@ -184,3 +184,24 @@ def test_c_abi_rejects_bad_arguments():
     assert rc == -1
     assert h.lf_lsq_workspace_bytes(1, 1, 8, 8, 9) == 0
     assert b"invalid" in h.lf_error_string(-1)
+
+
+@pytest.mark.parametrize("act", ["none", "abs", "relu", "sigmoid", "softplus"])
+def test_lsq_every_activation_vs_fp64_autograd(act):
+    """A5: every activation_layer kind of the reference (BP/Networks/LSQ_layer.py:27-47) fused into lf_lsq_fwd / lf_lsq_bwd,
+    forward and backward, against the fp64 oracle differentiated by autograd (inputs of both signs)."""
+    B, L, H, W, order, zero_rows = 2, 2, 256, 512, 2, 77
+    o_np = ((inputs.make_lane_maps(B, L, H, W, seed=31) - 0.3) * 4.0).astype(np.float32)
+    g_np = inputs.make_grad_beta(B, L, order, seed=7)
+    grid_np = load("lsq_bp_l2_d2")["grid0"]
+    o = torch.from_numpy(o_np).cuda().requires_grad_(True)
+    beta, masked = ops().lsq(o, torch.from_numpy(grid_np).cuda().unsqueeze(0), order, 255.0, zero_rows, act, want_masked=True)
+    (beta * torch.from_numpy(g_np).cuda()).sum().backward()
+    o64 = torch.from_numpy(o_np).double().requires_grad_(True)
+    m64 = lo.activate_and_mask(o64, act, zero_rows)
+    b_ref, _ = lo.wls_forward(m64, torch.from_numpy(grid_np), order, 255.0)
+    (b_ref * torch.from_numpy(g_np)).sum().backward()
+    assert normwise(beta.detach().cpu().numpy(), b_ref.detach().numpy()) <= 1e-5
+    np.testing.assert_allclose(masked.cpu().numpy(), m64.detach().float().numpy(), rtol=3e-6, atol=1e-7)
+    want = o64.grad.numpy()
+    assert np.abs(o.grad.cpu().numpy() - want).max() <= 2e-4 * np.abs(want).max()

@@ -413,3 +413,34 @@ def test_fused_backprojection_loss_kernel():
         # second call: the ticket word reset itself
         loss2, _ = fused_backprojection_loss(crit, betas, x_gt, valid)
         assert float(loss2) == float(loss)
+
+
+def test_projections_compute_coordinates_matches_reference_formulas():
+    """inference.Projections (one lf_backproj_loss launch for all lanes) vs a literal torch restatement of the
+    reference's Projections.compute_coordinates (BP/test.py:172-186) in float64."""
+    from lanedetection_end2end_b200.inference import Projections, lanes_from_predictions
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    B, L, order = 3, 4, 3
+    args = define_args().parse_args(["--image_dir", "x", "--gt_dir", "y", "--nclasses", str(L), "--order", str(order),
+                                     "--batch_size", str(B)])
+    proj = Projections(args)
+    g = torch.Generator().manual_seed(4)
+    betas = [(torch.randn(B, order + 1, 1, generator=g, dtype=torch.float64) * torch.tensor([1e-5, 1e-3, 0.3, 250.0]).view(1, -1, 1)).cuda()
+             for _ in range(L)]
+    got = proj.compute_all(betas)
+    M, Mi = proj.M.cpu(), proj.M_inv.cpu()
+    y_d = (torch.arange(160, 720, 10) - 80).double() / 2.5
+    y_prime = (M[1, 1] * y_d + M[1, 2]) / (M[2, 1] * y_d + M[2, 2])
+    y_eval = 255 - y_prime
+    Y = torch.stack([y_eval ** k for k in range(order, 0, -1)] + [torch.ones_like(y_eval)], 1)     # [56, n]
+    for l in range(L):
+        x_prime = Y @ betas[l].cpu().squeeze(-1).t()                                                # [56, B]
+        coords = torch.stack([x_prime, y_prime[:, None].expand_as(x_prime), torch.ones_like(x_prime)], 0)   # [3, 56, B]
+        trans = torch.einsum("ij,jkb->ikb", Mi, coords)
+        want = (trans[0] / trans[2]).t() * 2.5
+        assert float((got[:, l].cpu() - want).abs().max()) <= 1e-9 * float(want.abs().max())
+        assert torch.equal(proj.compute_coordinates(betas[l]), got[:, l])
+    lanes = lanes_from_predictions(got, torch.tensor([[1., 1, 0, 1]] * B).cuda(), torch.tensor([200, 240, 300]).cuda())
+    assert len(lanes) == B and len(lanes[0]) == 4 and len(lanes[0][0]) == 56
+    assert all(v == -2 for v in lanes[0][1])            # line_pred[:, [1, 2, 0, 3]] = [1, 0, 1, 1]: lane 1 is switched off
+    assert all(v == -2 for v in lanes[1][0][:8])        # horizon 240 -> the first (240 - 160) / 10 samples are cut

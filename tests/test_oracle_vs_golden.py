@@ -123,3 +123,26 @@ def test_full_path_oracle_matches_reference(case):
             for n, (mean, var_unb) in stats.items():
                 np.testing.assert_allclose(0.1 * mean.numpy(), g["buf_f64/net.%s.running_mean" % n], rtol=1e-9, atol=1e-12)
                 np.testing.assert_allclose(0.9 + 0.1 * var_unb.numpy(), g["buf_f64/net.%s.running_var" % n], rtol=1e-9)
+
+
+@pytest.mark.parametrize("order,wf", [(2, "none"), (2, "linear"), (2, "quadratic"), (1, "none")])
+def test_area_loss_matches_reference_golden(order, wf):
+    """A12: the oracle's bool-mask restatement AND the product's Area_Loss (pure torch ops, any device) against the golden
+    outputs of the reference's own Area_Loss (BP/Loss_crit.py:87-143 == BEV/Loss_crit.py:78-134, run with the torch-1.1
+    byte-mask dispatch shimmed: oracle/make_golden.py run_area_loss) -- value and gradient, fp64 to 1e-12, fp32 to 1e-6."""
+    import numpy as np
+    from lanedetection_end2end_b200.Loss_crit import Area_Loss
+    g = np.load(os.path.join(GOLDEN, "area_loss.npz"))
+    for variant in ("Ba", "Bi"):
+        for tag, dt, tol in (("f64", torch.float64, 1e-12), ("f32", torch.float32, 2e-6)):
+            key = "%s/o%d_%s_%s" % (variant, order, wf, tag)
+            want, wgrad = float(g[key + "/loss"]), g[key + "/grad"]
+            for impl in ("oracle", "product"):
+                p = torch.from_numpy(g["params"]).to(dt).requires_grad_(True)
+                gt = torch.from_numpy(g["gt"]).to(dt)
+                loss = lo.area_loss(p, gt, order, wf) if impl == "oracle" else Area_Loss(order, wf)(p, gt)
+                loss.backward()
+                assert abs(float(loss.detach()) - want) <= tol * abs(want), (impl, key)
+                assert np.abs(p.grad.double().numpy() - wgrad).max() <= tol * np.abs(wgrad).max(), (impl, key)
+        z = Area_Loss(2, "none")(torch.from_numpy(g["params"]).float(), torch.zeros(6, 3))
+        assert float(z) == float(g[variant + "/all_absent"]) == 0.0
