@@ -219,6 +219,15 @@ conv1d_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int slot = cb & 1;
                 if (Cfg::BLOCK_MAJOR ? (j == 0) : (g0 == 0 && j == 0)) {   // first use of a (re)filled weight slot
                     const int q = Cfg::BLOCK_MAJOR ? (g0 / X3_NBUF) * NCB + cb : cb;   // fill number (see the producer)
+                    // Fill q >= 2 is released by the lo MMAs of the last slab of sub-phase q - 2.  In a group of fewer than
+                    // LAG tiles those are still pending here (they would be issued AFTER this step's hi MMAs, which wait for
+                    // the fill: a cycle -- the B=2 test shapes trapped on it): issue them first.
+                    while (npend > 0 && ((older.release_b && older.slot == slot) ||
+                                         (npend == 2 && newer.release_b && newer.slot == slot))) {
+                        issue_lo(older);
+                        older = newer;
+                        --npend;
+                    }
                     mbar_wait(&bfull[slot], (q >> 1) & 1);
                     tc_fence_after();
                 }
