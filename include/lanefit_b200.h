@@ -61,6 +61,10 @@ typedef struct CUstream_st* lf_stream_t; /* == cudaStream_t */
 #define LF_MAX_ORDER 4
 
 int lf_version(void);
+/* Programmatic dependent launch of the library's kernels (default on; LANEFIT_PDL=0 disables): each kernel may be
+ * scheduled while its predecessor in the stream drains and waits (griddepcontrol.wait) before touching global memory. */
+void lf_set_pdl(int on);
+int lf_get_pdl(void);
 const char* lf_error_string(int code);
 /* last CUDA error string seen by the library on this thread (host pointer) */
 const char* lf_last_cuda_error(void);
@@ -304,7 +308,7 @@ int lf_nchw_to_nhwc_pad(const float* in, int N, int C, int H, int W, int Cpad, f
  * for (n, oy, ox) in [N]x[Hs]x[Ws], c < Ng; A_i(n,y,x,k) = a[i].ptr[n*sn + y*sy + x*sx + k], zero outside
  * [0,H)x[0,W).  Kc: multiple of 32 (<= 256); Ng: multiple of 16 (<= 128); all strides multiples of 4 elements.
  * ops_net.py (tcg_* packers) maps the four layer forms onto this through pair-pixel / row-parity views. */
-#define LF_TCG_MAX_TAPS 6
+#define LF_TCG_MAX_TAPS 9   /* 6 for the stride-2 layers; 9 = a dense 3x3 stride-1 conv (Classification heads) */
 typedef struct LfTcgView {
     const float* ptr;
     int H, W;
@@ -382,6 +386,23 @@ int lf_backproj_loss(const double* Y56, const double* yprime, const double* Minv
 int lf_backproj_loss_host(const double* Y56, const double* yprime, const double* Minv, const double* beta, const double* x_gt,
                           const double* valid, int B, int L, int n, double* lane_loss, double* loss, double* dbeta,
                           double* xcal);
+
+/* Fully connected layers of the Classification heads (csrc/linear.cu; replaces nn.Linear at
+ * BP/Networks/LSQ_layer.py:188-192,203-206): y[b][o] = bias[o] + sum_k x[b][k] W[o][k], W in nn.Linear's [O][K] layout,
+ * fp32, deterministic.  partial: caller-owned scratch of lf_linear_chunks(K)*B*O floats.  relu: apply ReLU to y.
+ * Backward: g = dy, or dy * (relu_out > 0) when relu_out (the forward's ReLU output) is given;
+ *   lf_linear_bwd_data:   dx[b][k] = sum_o g[b][o] W[o][k]
+ *   lf_linear_bwd_weight: dW[o][k] = sum_b g[b][o] x[b][k],  db[o] = sum_b g[b][o]  (db may be NULL). */
+int lf_linear_chunks(int K);
+/* AvgPool2d((1,W)) of the horizon head on an NHWC map, flattened as the reference's NCHW view does:
+ * out[b][c*H + h] = mean_w x[b][h][w][c] (C <= 256); and its gradient dx[b][h][w][c] = dout[b][c*H + h] / W. */
+int lf_rowmean_fwd(const float* x, int B, int H, int W, int C, float* out, lf_stream_t stream);
+int lf_rowmean_bwd(const float* dout, int B, int H, int W, int C, float* dx, lf_stream_t stream);
+int lf_linear_fwd(const float* x, const float* W, const float* bias, int B, int K, int O, int relu, float* partial, float* y,
+                  lf_stream_t stream);
+int lf_linear_bwd_data(const float* dy, const float* relu_out, const float* W, int B, int K, int O, float* dx, lf_stream_t stream);
+int lf_linear_bwd_weight(const float* dy, const float* relu_out, const float* x, int B, int K, int O, float* dW, float* db,
+                         lf_stream_t stream);
 
 #ifdef __cplusplus
 }

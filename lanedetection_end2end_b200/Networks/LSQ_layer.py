@@ -6,7 +6,7 @@ the fused sm_100a kernels in csrc/lsq.cu through the C ABI.
   activation_layer        BP/Networks/LSQ_layer.py:27-47
   ProjectiveGridGenerator :50-68
   Weighted_least_squares  :72-154
-  Classification          :157-207   ("next" scope, SURVEY.md 8f-2: torch modules for now)
+  Classification          :157-207   (on the library's kernels through ops_heads.py)
   Net                     :210-315
 """
 from math import ceil
@@ -124,9 +124,11 @@ class Weighted_least_squares(nn.Module):
 
 
 class Classification(nn.Module):
-    """Line-type / horizon heads on the encoder output (BP/Networks/LSQ_layer.py:157-207).
-    Not part of the B200-native hot path yet: plain torch modules
-    with the reference's parameter names so ``--clas 1`` checkpoints round-trip."""
+    """Line-type / horizon heads on the encoder output (BP/Networks/LSQ_layer.py:157-207; SURVEY.md 8f rank 2).
+    The torch modules below only hold the parameters / buffers under the reference's names (``--clas 1`` checkpoints
+    round-trip); ``forward`` runs every stage on the library's kernels through ``ops_heads`` (tcgen05 gather-GEMM
+    convolutions, the ERFNet BatchNorm kernels with eps 1e-5, max / row-mean pooling, HBM-bound fully connected
+    layers) -- forward and backward, no torch operator on a feature map."""
 
     def __init__(self, class_type, size, channels_in, resize):
         super().__init__()
@@ -140,6 +142,7 @@ class Classification(nn.Module):
         self.conv4 = nn.Conv2d(64, 64, 3, padding=1)
         self.conv4_bn = nn.BatchNorm2d(64)
         rows, cols = size
+        self.size = (rows, cols)
         self.avgpool = nn.AvgPool2d((1, cols))
         self.maxpool = nn.MaxPool2d((2, 2), stride=2)
         if class_type == "line":
@@ -149,14 +152,21 @@ class Classification(nn.Module):
             self.fully_connected_horizon = nn.Linear(64 * rows, resize)
 
     def forward(self, x):
+        _heads, _net = submodule("ops_heads"), _ops_net
+        from .ERFNet import _track
+        h = _net.as_nhwc(x)
+        _capi.require_cuda(h)
+        if tuple(h.shape[1:3]) != self.size:
+            raise ValueError("Classification head built for a %dx%d encoder map, got %dx%d" % (self.size + tuple(h.shape[1:3])))
         for conv, bn in ((self.conv1, self.conv1_bn), (self.conv2, self.conv2_bn),
                          (self.conv3, self.conv3_bn), (self.conv4, self.conv4_bn)):
-            x = F.relu(bn(conv(x)))
-        x = self.maxpool(x) if self.class_type == "line" else self.avgpool(x)
-        x = x.reshape(x.size(0), -1)
+            h = _heads.conv_bn_relu(h, conv, bn, self.training, _track)
         if self.class_type == "line":
-            return self.fully_connected_line1(F.relu(self.fully_connected1(x)))
-        return self.fully_connected_horizon(x)
+            f = _heads.MaxPool2FlatFunction.apply(h)
+            f = _heads.LinearFunction.apply(f, self.fully_connected1.weight, self.fully_connected1.bias, True)
+            return _heads.LinearFunction.apply(f, self.fully_connected_line1.weight, self.fully_connected_line1.bias, False)
+        f = _heads.RowMeanFlatFunction.apply(h)
+        return _heads.LinearFunction.apply(f, self.fully_connected_horizon.weight, self.fully_connected_horizon.bias, False)
 
 
 class Net(nn.Module):

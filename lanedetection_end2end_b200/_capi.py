@@ -27,6 +27,8 @@ _c_size_t = ctypes.c_size_t
 # name -> (restype, argtypes); every symbol include/lanefit_b200.h declares
 PROTOTYPES = {
     "lf_version": (_c_int, []),
+    "lf_set_pdl": (None, [_c_int]),
+    "lf_get_pdl": (_c_int, []),
     "lf_error_string": (ctypes.c_char_p, [_c_int]),
     "lf_last_cuda_error": (ctypes.c_char_p, []),
     "lf_lsq_workspace_bytes": (_c_size_t, [_c_int] * 5),
@@ -70,7 +72,7 @@ class LfWgradArgs(ctypes.Structure):
                 ("CpPad", _i), ("CqPad", _i), ("nsplit", _i)]
 
 
-TCG_MAX_TAPS = 6
+TCG_MAX_TAPS = 9
 _ll = ctypes.c_longlong
 
 
@@ -148,6 +150,12 @@ _NET_PROTOS = {
     "lf_pack_gather": (_i, [_p, _i, _i, _p]),
     "lf_backproj_loss": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "lf_backproj_loss_host": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "lf_linear_chunks": (_i, [_i]),
+    "lf_rowmean_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "lf_rowmean_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "lf_linear_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "lf_linear_bwd_data": (_i, [_p, _p, _p, _i, _i, _i, _p, _p]),
+    "lf_linear_bwd_weight": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "lf_bn_bwd_finalize_sx": (_i, [_p, _i, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
 }
 PROTOTYPES.update(_NET_PROTOS)

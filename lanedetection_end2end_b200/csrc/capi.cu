@@ -1,10 +1,23 @@
 // Library-level entry points of the lanefit_b200 C ABI (include/lanefit_b200.h).
+#include <stdlib.h>
+
 #include "lf_common.cuh"
 
 namespace lf {
 static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
+static int g_pdl = -1;   // -1: not decided yet (LANEFIT_PDL, default on)
+bool pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("LANEFIT_PDL");
+        g_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_pdl != 0;
+}
 }  // namespace lf
+
+extern "C" void lf_set_pdl(int on) { lf::g_pdl = on ? 1 : 0; }
+extern "C" int lf_get_pdl(void) { return lf::pdl_enabled() ? 1 : 0; }
 
 extern "C" int lf_version(void) { return 100; }
 

@@ -39,6 +39,7 @@ struct ConvTile {
 
 template <int BN>
 __global__ void __launch_bounds__(CONV_THREADS) conv_igemm_f32_kernel(const ConvArgs a) {
+    pdl_entry();
     using T = ConvTile<BN>;
     constexpr int TM = T::TM, TN = T::TN;
     constexpr int BM = T::BM, AH = T::AH;
@@ -245,10 +246,10 @@ extern "C" int lf_conv_f32(const LfConvArgs* args, lf_stream_t stream_) {
     const int BMsel = (BN == 16) ? 256 : CONV_BM;
     dim3 grid((unsigned)((M + BMsel - 1) / BMsel), a.CoutPad / BN);
     switch (BN) {
-        case 128: conv_igemm_f32_kernel<128><<<grid, CONV_THREADS, 0, stream>>>(a); break;
-        case 64: conv_igemm_f32_kernel<64><<<grid, CONV_THREADS, 0, stream>>>(a); break;
-        case 32: conv_igemm_f32_kernel<32><<<grid, CONV_THREADS, 0, stream>>>(a); break;
-        default: conv_igemm_f32_kernel<16><<<grid, CONV_THREADS, 0, stream>>>(a); break;
+        case 128: lf_launch(conv_igemm_f32_kernel<128>, grid, CONV_THREADS, 0, stream, a); break;
+        case 64: lf_launch(conv_igemm_f32_kernel<64>, grid, CONV_THREADS, 0, stream, a); break;
+        case 32: lf_launch(conv_igemm_f32_kernel<32>, grid, CONV_THREADS, 0, stream, a); break;
+        default: lf_launch(conv_igemm_f32_kernel<16>, grid, CONV_THREADS, 0, stream, a); break;
     }
     return check_launch();
 }

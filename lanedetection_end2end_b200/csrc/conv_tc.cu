@@ -68,6 +68,7 @@ struct TcCfg {
 template <int C, bool AHEAD>
 __global__ void __launch_bounds__(TcCfg<C, AHEAD>::THREADS, 1)
 conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    pdl_trigger();
     using Cfg = TcCfg<C, AHEAD>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -106,6 +107,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0) {
         // ================= TMA producer (whole warp converged, one elected lane issues) =================
@@ -323,19 +325,19 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     if (p.C == 128 && ahead) {
         e = cudaFuncSetAttribute(conv1d_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_kernel<128, true><<<grid, TcCfg<128, true>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
+        lf_launch(conv1d_tc_kernel<128, true>, grid, TcCfg<128, true>::THREADS, pl.smem_bytes, stream, tmA, tmB, a);
     } else if (p.C == 128) {
         e = cudaFuncSetAttribute(conv1d_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_kernel<128, false><<<grid, TcCfg<128>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
+        lf_launch(conv1d_tc_kernel<128, false>, grid, TcCfg<128>::THREADS, pl.smem_bytes, stream, tmA, tmB, a);
     } else if (ahead) {
         e = cudaFuncSetAttribute(conv1d_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_kernel<64, true><<<grid, TcCfg<64, true>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
+        lf_launch(conv1d_tc_kernel<64, true>, grid, TcCfg<64, true>::THREADS, pl.smem_bytes, stream, tmA, tmB, a);
     } else {
         e = cudaFuncSetAttribute(conv1d_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_kernel<64, false><<<grid, TcCfg<64>::THREADS, pl.smem_bytes, stream>>>(tmA, tmB, a);
+        lf_launch(conv1d_tc_kernel<64, false>, grid, TcCfg<64>::THREADS, pl.smem_bytes, stream, tmA, tmB, a);
     }
     return check_launch();
 }

@@ -69,6 +69,7 @@ struct TcCfgV1 {
 template <int C>
 __global__ void __launch_bounds__(TC_THREADS_V1, 1)
 conv1d_tc_v1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgsV1 a) {
+    pdl_trigger();
     using Cfg = TcCfgV1<C>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -107,6 +108,7 @@ conv1d_tc_v1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0) {
         // ================= TMA producer (whole warp converged, one elected lane issues) =================
@@ -324,11 +326,11 @@ int lf_conv1d_tc_v1(const LfConvTcArgs* args, lf_stream_t stream_) {
     if (p.C == 128) {
         e = cudaFuncSetAttribute(conv1d_tc_v1_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgV1<128>::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_v1_kernel<128><<<grid, TC_THREADS_V1, TcCfgV1<128>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+        lf_launch(conv1d_tc_v1_kernel<128>, grid, TC_THREADS_V1, TcCfgV1<128>::SMEM_BYTES, stream, tmA, tmB, a);
     } else {
         e = cudaFuncSetAttribute(conv1d_tc_v1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgV1<64>::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        conv1d_tc_v1_kernel<64><<<grid, TC_THREADS_V1, TcCfgV1<64>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+        lf_launch(conv1d_tc_v1_kernel<64>, grid, TC_THREADS_V1, TcCfgV1<64>::SMEM_BYTES, stream, tmA, tmB, a);
     }
     return check_launch();
 }

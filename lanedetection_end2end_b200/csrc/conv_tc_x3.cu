@@ -63,6 +63,7 @@ struct X3Cfg {
 template <int C, bool AHEAD>
 __global__ void __launch_bounds__(X3Cfg<C, AHEAD>::THREADS, 1)
 conv1d_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    pdl_trigger();
     using Cfg = X3Cfg<C, AHEAD>;
     constexpr int NCB = Cfg::NCB;
     extern __shared__ uint8_t smem_raw[];
@@ -111,6 +112,7 @@ conv1d_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     // Step s of a group of gn <= X3_NBUF tiles touches (tile j of the group, 32-channel block cb):
     // tile-major when the weights are resident (C = 64), block-major when they stream through the two slots.
@@ -371,7 +373,7 @@ static cudaError_t x3_launch(int grid, int smem_bytes, cudaStream_t stream, cons
                              const TcArgs& a) {
     cudaError_t e = cudaFuncSetAttribute(conv1d_tc_x3_kernel<C, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
-    conv1d_tc_x3_kernel<C, AHEAD><<<grid, X3Cfg<C, AHEAD>::THREADS, smem_bytes, stream>>>(tmA, tmB, a);
+    lf_launch(conv1d_tc_x3_kernel<C, AHEAD>, grid, X3Cfg<C, AHEAD>::THREADS, smem_bytes, stream, tmA, tmB, a);
     return cudaSuccess;
 }
 

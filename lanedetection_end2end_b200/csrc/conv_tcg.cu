@@ -65,6 +65,7 @@ template <bool X3>
 __global__ void __launch_bounds__(X3 ? TG_THREADS_X3 : TG_THREADS, 1)
 conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const TgArgs a) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * a.stage_bytes);
@@ -102,6 +103,7 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0) {
         // ================= TMA producer (converged warp, elected lane issues) =================
@@ -355,7 +357,7 @@ extern "C" int lf_conv_tcg(const LfConvTcgArgs* args, lf_stream_t stream_) {
     cudaError_t e = x3 ? cudaFuncSetAttribute(conv_tcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_LIMIT)
                        : cudaFuncSetAttribute(conv_tcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_LIMIT);
     if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-    if (x3) conv_tcg_kernel<true><<<grid, TG_THREADS_X3, smem_bytes, stream>>>(tmA0, tmA1, tmB, a);
-    else conv_tcg_kernel<false><<<grid, TG_THREADS, smem_bytes, stream>>>(tmA0, tmA1, tmB, a);
+    if (x3) lf_launch(conv_tcg_kernel<true>, grid, TG_THREADS_X3, smem_bytes, stream, tmA0, tmA1, tmB, a);
+    else lf_launch(conv_tcg_kernel<false>, grid, TG_THREADS, smem_bytes, stream, tmA0, tmA1, tmB, a);
     return check_launch();
 }

@@ -18,6 +18,43 @@ inline int check_launch() {
     return LF_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library is launched through lf_launch(); with the switch on
+// (lf_set_pdl / LANEFIT_PDL, default on) the launch carries cudaLaunchAttributeProgrammaticStreamSerialization, so the
+// grid may be scheduled while its predecessor in the stream is still draining: its launch latency and on-chip prologue
+// (barrier init, TMEM allocation, descriptor prefetch) overlap the predecessor's tail instead of following it.  The
+// contract every kernel keeps: pdl_trigger() first (dependents may be scheduled once ALL CTAs of this grid are
+// resident -- so a waiting dependent can never starve CTAs of this grid that have not started), and pdl_wait() before
+// the first global-memory access (reads of the predecessor's results AND writes: the allocator may hand a buffer the
+// predecessor still reads to this kernel as output).  griddepcontrol.wait returns when the prerequisite grid has
+// COMPLETED and flushed, so completion stays transitive along the stream exactly as without PDL.  Both instructions are
+// no-ops for a launch without the attribute.  A step of ~470 launches of 10-60 us each has ~2-3 us of launch gap per
+// kernel otherwise (CUDA graph replay included).
+// ---------------------------------------------------------------------------------
+bool pdl_enabled();
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() {
+    pdl_trigger();
+    pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t lf_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define LF_REQUIRE(cond)                            \
     do {                                            \
         if (!(cond)) return LF_ERR_INVALID_ARGUMENT; \
@@ -40,6 +77,11 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                  : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream_f1(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void st_stream_f4(float4* p, float4 v) {

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(BP_THREADS) backproj_loss_kernel(const BpConst
                                                                     double* __restrict__ lane_loss, double* __restrict__ dbeta,
                                                                     double* __restrict__ xcal, unsigned int* ticket,
                                                                     double* __restrict__ loss) {
+    pdl_entry();
     __shared__ double red_sq[BP_THREADS], red_nv[BP_THREADS];
     __shared__ double s_scale;
     const int l = blockIdx.x;
@@ -141,7 +142,7 @@ extern "C" int lf_backproj_loss(const double* Y56, const double* yprime, const d
     BpConst c;
     int rc = bp_fill_const(Y56, yprime, Minv, n, &c);
     if (rc) return rc;
-    backproj_loss_kernel<<<L, BP_THREADS, 0, stream>>>(c, beta, x_gt, valid, B, L, n, lane_loss, dbeta, xcal, ticket, loss);
+    lf_launch(backproj_loss_kernel, L, BP_THREADS, 0, stream, c, beta, x_gt, valid, B, L, n, lane_loss, dbeta, xcal, ticket, loss);
     return check_launch();
 }
 

@@ -344,6 +344,7 @@ __device__ void lsq_chunk_tail(const LsqArgs& a, double (*red)[LSQ_MAXL][LSQ_MAX
 // together: the kernel is latency-bound otherwise -- ncu: long_scoreboard stalls, profiles/r01).
 template <int ACT_T, bool BF16, int NL>
 __global__ void __launch_bounds__(LSQ_THREADS, LSQ_FWD_CTAS_PER_SM) lsq_fwd_rowsep_kernel(const LsqArgs a) {
+    pdl_entry();
     __shared__ double red[LSQ_WARPS][LSQ_MAXL][LSQ_MAXNM];
     __shared__ double mom[LSQ_MAXL][LSQ_MAXNM];
     const int chunk = blockIdx.x, b = blockIdx.y, lg = blockIdx.z;
@@ -449,6 +450,7 @@ __global__ void __launch_bounds__(LSQ_THREADS, LSQ_FWD_CTAS_PER_SM) lsq_fwd_rows
 // ---------------------------------------------------------------------------------
 template <int ACT_T, bool BF16>
 __global__ void __launch_bounds__(LSQ_THREADS) lsq_fwd_general_kernel(const LsqArgs a) {
+    pdl_entry();
     __shared__ double red[LSQ_WARPS][LSQ_MAXL][LSQ_MAXNM];
     __shared__ double mom[LSQ_MAXL][LSQ_MAXNM];
     const int chunk = blockIdx.x, b = blockIdx.y, l = blockIdx.z;
@@ -514,6 +516,7 @@ __device__ __forceinline__ void lsq_bwd_load_coeffs(const LsqArgs& a, int b, int
 
 template <int ACT_T, bool BF16, int NL>
 __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const LsqArgs a) {
+    pdl_entry();
     __shared__ double bs[LSQ_MAXL][LF_MAX_ORDER + 1], zs[LSQ_MAXL][LF_MAX_ORDER + 1];
     const int chunk = blockIdx.x, b = blockIdx.y, lg = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -574,6 +577,7 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const Ls
 
 template <int ACT_T, bool BF16>
 __global__ void __launch_bounds__(LSQ_THREADS) lsq_bwd_general_kernel(const LsqArgs a) {
+    pdl_entry();
     __shared__ double bs[LSQ_MAXL][LF_MAX_ORDER + 1], zs[LSQ_MAXL][LF_MAX_ORDER + 1];
     const int chunk = blockIdx.x, b = blockIdx.y, l = blockIdx.z;
     const int d = a.order;
@@ -658,14 +662,14 @@ extern "C" size_t lf_lsq_workspace_bytes(int B, int L, int H, int W, int order) 
     do {                                                                                   \
         if (args.act == LF_ACT_SQUARE) {                                                   \
             if (o_dtype == LF_BF16)                                                        \
-                KERNEL<LF_ACT_SQUARE, true><<<grid, LSQ_THREADS, 0, stream>>>(args);       \
+                lf_launch(KERNEL<LF_ACT_SQUARE, true>, grid, LSQ_THREADS, 0, stream, args);       \
             else                                                                           \
-                KERNEL<LF_ACT_SQUARE, false><<<grid, LSQ_THREADS, 0, stream>>>(args);      \
+                lf_launch(KERNEL<LF_ACT_SQUARE, false>, grid, LSQ_THREADS, 0, stream, args);      \
         } else {                                                                           \
             if (o_dtype == LF_BF16)                                                        \
-                KERNEL<LSQ_ACT_RUNTIME, true><<<grid, LSQ_THREADS, 0, stream>>>(args);     \
+                lf_launch(KERNEL<LSQ_ACT_RUNTIME, true>, grid, LSQ_THREADS, 0, stream, args);     \
             else                                                                           \
-                KERNEL<LSQ_ACT_RUNTIME, false><<<grid, LSQ_THREADS, 0, stream>>>(args);    \
+                lf_launch(KERNEL<LSQ_ACT_RUNTIME, false>, grid, LSQ_THREADS, 0, stream, args);    \
         }                                                                                  \
     } while (0)
 
@@ -673,14 +677,14 @@ extern "C" size_t lf_lsq_workspace_bytes(int B, int L, int H, int W, int order) 
     do {                                                                                       \
         if (args.act == LF_ACT_SQUARE) {                                                       \
             if (o_dtype == LF_BF16)                                                            \
-                KERNEL<LF_ACT_SQUARE, true, NL><<<grid, LSQ_THREADS, 0, stream>>>(args);       \
+                lf_launch(KERNEL<LF_ACT_SQUARE, true, NL>, grid, LSQ_THREADS, 0, stream, args);       \
             else                                                                               \
-                KERNEL<LF_ACT_SQUARE, false, NL><<<grid, LSQ_THREADS, 0, stream>>>(args);      \
+                lf_launch(KERNEL<LF_ACT_SQUARE, false, NL>, grid, LSQ_THREADS, 0, stream, args);      \
         } else {                                                                               \
             if (o_dtype == LF_BF16)                                                            \
-                KERNEL<LSQ_ACT_RUNTIME, true, NL><<<grid, LSQ_THREADS, 0, stream>>>(args);     \
+                lf_launch(KERNEL<LSQ_ACT_RUNTIME, true, NL>, grid, LSQ_THREADS, 0, stream, args);     \
             else                                                                               \
-                KERNEL<LSQ_ACT_RUNTIME, false, NL><<<grid, LSQ_THREADS, 0, stream>>>(args);    \
+                lf_launch(KERNEL<LSQ_ACT_RUNTIME, false, NL>, grid, LSQ_THREADS, 0, stream, args);    \
         }                                                                                      \
     } while (0)
 

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
                                                                long long npix, int C, int pix_per_image,
                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                double* __restrict__ partial) {
+    pdl_entry();
     extern __shared__ double sred[];  // [lanes][2][C]
     const int C4 = C >> 2;
     const int lanes = BN_THREADS / C4;
@@ -100,6 +101,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partial, int nblk,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                                    float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
                                    float* shift) {
+    pdl_entry();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per channel
     if (c >= C) return;
     double s1, s2;
@@ -124,6 +126,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partial, int nblk,
 
 __global__ void bn_eval_prepare_kernel(int C, const float* gamma, const float* beta, float eps, const float* rm,
                                        const float* rv, float* scale, float* shift) {
+    pdl_entry();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float is = 1.f / sqrtf(rv[c] + eps);
@@ -134,6 +137,7 @@ __global__ void bn_eval_prepare_kernel(int C, const float* gamma, const float* b
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, long long npix, int C, float* dgamma,
                                        float* dbeta, float* c1, float* c2) {
+    pdl_entry();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per channel
     if (c >= C) return;
     double s1, s2;
@@ -150,6 +154,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int n
 __global__ void bn_bwd_finalize_sx_kernel(const double* __restrict__ partial, int nblk, long long npix, int C, int fold,
                                           const float* __restrict__ mean, const float* __restrict__ invstd, float* dgamma,
                                           float* dbeta, float* c1, float* c2) {
+    pdl_entry();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per channel
     if (c >= C) return;
     double s1 = 0.0, s2 = 0.0;
@@ -172,6 +177,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        const float* __restrict__ drop, const float* __restrict__ res, int relu,
                                                        float* __restrict__ y) {
+    pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % C4);
         const long long p = i / C4;
@@ -201,6 +207,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ c1,
                                                            const float* __restrict__ c2, float* __restrict__ dx) {
+    pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % C4);
         const long long p = i / C4;
@@ -233,6 +240,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------
 __global__ void maxpool2_fwd_kernel(const float* __restrict__ in, int N, int Hin, int Win, int C, int in_cstride,
                                     float* __restrict__ out, int out_cstride, int out_coff) {
+    pdl_entry();
     const int Ho = Hin >> 1, Wo = Win >> 1;
     const long long total = (long long)N * Ho * Wo * C;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -252,6 +260,7 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ in, int N, int Hin
 __global__ void maxpool2_bwd_kernel(const float* __restrict__ in, int N, int Hin, int Win, int C, int in_cstride,
                                     const float* __restrict__ d_out, int out_cstride, int out_coff, float* __restrict__ d_in,
                                     int din_cstride, int accumulate) {
+    pdl_entry();
     const int Ho = Hin >> 1, Wo = Win >> 1;
     const long long total = (long long)N * Ho * Wo * C;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -297,6 +306,7 @@ constexpr int OC_MAXL = 8;
 __global__ void __launch_bounds__(256) outconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                           const float* __restrict__ bias, int N, int H, int W, int Cin, int L,
                                                           float* __restrict__ out) {
+    pdl_entry();
     __shared__ __align__(16) float ws[OC_MAXCIN * OC_MAXL * 4];
     __shared__ float bs[OC_MAXL];
     for (int k = threadIdx.x; k < Cin * L * 4; k += blockDim.x) ws[k] = w[k];
@@ -331,6 +341,7 @@ __global__ void __launch_bounds__(256) outconv_fwd_kernel(const float* __restric
 
 __global__ void __launch_bounds__(256) outconv_bwd_data_kernel(const float* __restrict__ d_out, const float* __restrict__ w,
                                                                int N, int H, int W, int Cin, int L, float* __restrict__ d_x) {
+    pdl_entry();
     __shared__ __align__(16) float ws[OC_MAXCIN * OC_MAXL * 4];
     for (int k = threadIdx.x; k < Cin * L * 4; k += blockDim.x) ws[k] = w[k];
     __syncthreads();
@@ -365,6 +376,7 @@ constexpr int OCW_PIX_PER_BLOCK = 4096;
 // one block = a pixel range; grid.y = lane l.  partial[blk][Cin*L*4 + L]
 __global__ void __launch_bounds__(256) outconv_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ d_out,
                                                                  int N, int H, int W, int Cin, int L, float* __restrict__ partial) {
+    pdl_entry();
     __shared__ float red[8][OC_MAXCIN * 4 + 1];
     const int l = blockIdx.y;
     const long long npix = (long long)N * H * W;
@@ -426,6 +438,7 @@ __global__ void __launch_bounds__(256) outconv_bwd_weight_kernel(const float* __
 // Layout changes at the module boundary (tiled transposes through shared memory).
 // ------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ in, int N, int C, int HW, int Cpad, float* __restrict__ out) {
+    pdl_entry();
     // thread per output pixel; C is tiny (3) -> each plane read is coalesced across the warp
     const long long total = (long long)N * HW;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
@@ -437,6 +450,7 @@ __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ in, int N, int
 
 // generic [R][S] -> [S][R] per batch item, 32x32 tiles
 __global__ void batched_transpose_kernel(const float* __restrict__ in, int R, int S, float* __restrict__ out) {
+    pdl_entry();
     __shared__ float tile[32][33];
     const size_t boff = (size_t)blockIdx.z * R * S;
     const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -482,7 +496,7 @@ extern "C" int lf_bn_stats(const float* x, long long npix, int C, double* partia
     if (rc) return rc;
     const int lanes = BN_THREADS / (C / 4);
     const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
-    bn_reduce_kernel<0><<<lf_bn_blocks(npix, C), BN_THREADS, smem, stream>>>(x, nullptr, nullptr, nullptr, npix, C, 1, nullptr,
+    lf_launch(bn_reduce_kernel<0>, lf_bn_blocks(npix, C), BN_THREADS, smem, stream, x, nullptr, nullptr, nullptr, npix, C, 1, nullptr,
                                                                             nullptr, partial);
     return check_launch();
 }
@@ -493,7 +507,7 @@ extern "C" int lf_bn_finalize(const double* partial, int nblk, long long npix, i
     STREAM;
     LF_REQUIRE(partial && gamma && beta && mean && invstd && scale && shift && nblk >= 1);
     LF_REQUIRE((running_mean == nullptr) == (running_var == nullptr));
-    bn_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, stream>>>(partial, nblk, npix, C, gamma, beta, eps, momentum, running_mean,
+    lf_launch(bn_finalize_kernel, (C * 32 + 255) / 256, 256, 0, stream, partial, nblk, npix, C, gamma, beta, eps, momentum, running_mean,
                                                             running_var, mean, invstd, scale, shift);
     return check_launch();
 }
@@ -502,7 +516,7 @@ extern "C" int lf_bn_eval_prepare(int C, const float* gamma, const float* beta, 
                                   const float* running_var, float* scale, float* shift, lf_stream_t stream_) {
     STREAM;
     LF_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && C >= 1);
-    bn_eval_prepare_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, gamma, beta, eps, running_mean, running_var, scale, shift);
+    lf_launch(bn_eval_prepare_kernel, (C + 127) / 128, 128, 0, stream, C, gamma, beta, eps, running_mean, running_var, scale, shift);
     return check_launch();
 }
 
@@ -513,7 +527,7 @@ extern "C" int lf_bn_apply(const float* x, long long npix, int C, int pix_per_im
     int rc = bn_check(npix, C);
     if (rc) return rc;
     const long long n4 = npix * (C / 4);
-    bn_apply_kernel<<<grid_for(n4, 256), 256, 0, stream>>>(x, n4, C / 4, pix_per_image, scale, shift, drop, res, relu, y);
+    lf_launch(bn_apply_kernel, grid_for(n4, 256), 256, 0, stream, x, n4, C / 4, pix_per_image, scale, shift, drop, res, relu, y);
     return check_launch();
 }
 
@@ -526,7 +540,7 @@ extern "C" int lf_bn_bwd_reduce(const float* dy, const float* ymask, const float
     if (rc) return rc;
     const int lanes = BN_THREADS / (C / 4);
     const size_t smem = (size_t)lanes * 2 * C * sizeof(double);
-    bn_reduce_kernel<1><<<lf_bn_blocks(npix, C), BN_THREADS, smem, stream>>>(x, dy, ymask, drop, npix, C, pix_per_image, mean,
+    lf_launch(bn_reduce_kernel<1>, lf_bn_blocks(npix, C), BN_THREADS, smem, stream, x, dy, ymask, drop, npix, C, pix_per_image, mean,
                                                                             invstd, partial);
     return check_launch();
 }
@@ -535,7 +549,7 @@ extern "C" int lf_bn_bwd_finalize(const double* partial, int nblk, long long npi
                                   float* c1, float* c2, lf_stream_t stream_) {
     STREAM;
     LF_REQUIRE(partial && dgamma && dbeta && c1 && c2 && nblk >= 1);
-    bn_bwd_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, stream>>>(partial, nblk, npix, C, dgamma, dbeta, c1, c2);
+    lf_launch(bn_bwd_finalize_kernel, (C * 32 + 255) / 256, 256, 0, stream, partial, nblk, npix, C, dgamma, dbeta, c1, c2);
     return check_launch();
 }
 
@@ -543,7 +557,7 @@ extern "C" int lf_bn_bwd_finalize_sx(const double* partial, int nblk, long long 
                                      const float* invstd, float* dgamma, float* dbeta, float* c1, float* c2, lf_stream_t stream_) {
     STREAM;
     LF_REQUIRE(partial && mean && invstd && dgamma && dbeta && c1 && c2 && nblk >= 1 && fold >= 1 && C >= 1);
-    bn_bwd_finalize_sx_kernel<<<(C * 32 + 255) / 256, 256, 0, stream>>>(partial, nblk, npix, C, fold, mean, invstd, dgamma, dbeta,
+    lf_launch(bn_bwd_finalize_sx_kernel, (C * 32 + 255) / 256, 256, 0, stream, partial, nblk, npix, C, fold, mean, invstd, dgamma, dbeta,
                                                                        c1, c2);
     return check_launch();
 }
@@ -556,7 +570,7 @@ extern "C" int lf_bn_bwd_apply(const float* dy, const float* ymask, const float*
     int rc = bn_check(npix, C);
     if (rc) return rc;
     const long long n4 = npix * (C / 4);
-    bn_bwd_apply_kernel<<<grid_for(n4, 256), 256, 0, stream>>>(dy, ymask, drop, x, n4, C / 4, pix_per_image, mean, invstd,
+    lf_launch(bn_bwd_apply_kernel, grid_for(n4, 256), 256, 0, stream, dy, ymask, drop, x, n4, C / 4, pix_per_image, mean, invstd,
                                                               gamma, c1, c2, dx);
     return check_launch();
 }
@@ -566,7 +580,7 @@ extern "C" int lf_maxpool2_fwd(const float* in, int N, int Hin, int Win, int C, 
     STREAM;
     LF_REQUIRE(in && out && N > 0 && Hin > 1 && Win > 1 && C > 0 && Hin % 2 == 0 && Win % 2 == 0);
     const long long total = (long long)N * (Hin / 2) * (Win / 2) * C;
-    maxpool2_fwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, N, Hin, Win, C, in_cstride, out, out_cstride, out_coff);
+    lf_launch(maxpool2_fwd_kernel, grid_for(total, 256), 256, 0, stream, in, N, Hin, Win, C, in_cstride, out, out_cstride, out_coff);
     return check_launch();
 }
 
@@ -576,7 +590,7 @@ extern "C" int lf_maxpool2_bwd(const float* in, int N, int Hin, int Win, int C, 
     STREAM;
     LF_REQUIRE(in && d_out && d_in && N > 0 && Hin > 1 && Win > 1 && C > 0 && Hin % 2 == 0 && Win % 2 == 0);
     const long long total = (long long)N * (Hin / 2) * (Win / 2) * C;
-    maxpool2_bwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, N, Hin, Win, C, in_cstride, d_out, out_cstride, out_coff,
+    lf_launch(maxpool2_bwd_kernel, grid_for(total, 256), 256, 0, stream, in, N, Hin, Win, C, in_cstride, d_out, out_cstride, out_coff,
                                                                  d_in, din_cstride, accumulate);
     return check_launch();
 }
@@ -586,7 +600,7 @@ extern "C" int lf_outconv_fwd(const float* x, const float* w, const float* bias,
     STREAM;
     LF_REQUIRE(x && w && out && N > 0 && H > 0 && W > 0);
     if (Cin != OC_MAXCIN || L < 1 || L > OC_MAXL) return LF_ERR_UNSUPPORTED;
-    outconv_fwd_kernel<<<grid_for((long long)N * H * W, 256), 256, 0, stream>>>(x, w, bias, N, H, W, Cin, L, out);
+    lf_launch(outconv_fwd_kernel, grid_for((long long)N * H * W, 256), 256, 0, stream, x, w, bias, N, H, W, Cin, L, out);
     return check_launch();
 }
 
@@ -595,7 +609,7 @@ extern "C" int lf_outconv_bwd_data(const float* d_out, const float* w, int N, in
     STREAM;
     LF_REQUIRE(d_out && w && d_x && N > 0 && H > 0 && W > 0);
     if (Cin != OC_MAXCIN || L < 1 || L > OC_MAXL) return LF_ERR_UNSUPPORTED;
-    outconv_bwd_data_kernel<<<grid_for((long long)N * H * W, 256), 256, 0, stream>>>(d_out, w, N, H, W, Cin, L, d_x);
+    lf_launch(outconv_bwd_data_kernel, grid_for((long long)N * H * W, 256), 256, 0, stream, d_out, w, N, H, W, Cin, L, d_x);
     return check_launch();
 }
 
@@ -607,7 +621,7 @@ extern "C" int lf_outconv_bwd_weight(const float* x, const float* d_out, int N, 
     LF_REQUIRE(x && d_out && partial && N > 0 && H > 0 && W > 0);
     if (Cin != OC_MAXCIN || L < 1 || L > OC_MAXL) return LF_ERR_UNSUPPORTED;
     dim3 grid(lf_outconv_wgrad_blocks((long long)N * H * W), L);
-    outconv_bwd_weight_kernel<<<grid, 256, 0, stream>>>(x, d_out, N, H, W, Cin, L, partial);
+    lf_launch(outconv_bwd_weight_kernel, grid, 256, 0, stream, x, d_out, N, H, W, Cin, L, partial);
     return check_launch();
 }
 
@@ -625,6 +639,7 @@ struct PackJob {
 static_assert(sizeof(PackJob) == 32, "LfPackJob layout");
 
 __global__ void __launch_bounds__(256) pack_gather_kernel(const PackJob* __restrict__ jobs) {
+    pdl_entry();
     const PackJob j = jobs[blockIdx.y];
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < j.n; k += (long long)gridDim.x * blockDim.x) {
         const int i = __ldg(j.idx + k);
@@ -643,14 +658,14 @@ extern "C" int lf_pack_gather(const LfPackJob* jobs_dev, int njobs, int blocks_p
     STREAM;
     LF_REQUIRE(jobs_dev && njobs > 0 && njobs <= 65535 && blocks_per_job > 0);
     dim3 grid(blocks_per_job, njobs);
-    pack_gather_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const PackJob*>(jobs_dev));
+    lf_launch(pack_gather_kernel, grid, 256, 0, stream, reinterpret_cast<const PackJob*>(jobs_dev));
     return check_launch();
 }
 
 extern "C" int lf_nchw_to_nhwc_pad(const float* in, int N, int C, int H, int W, int Cpad, float* out, lf_stream_t stream_) {
     STREAM;
     LF_REQUIRE(in && out && N > 0 && C > 0 && Cpad >= C);
-    nchw_to_nhwc_pad_kernel<<<grid_for((long long)N * H * W, 256), 256, 0, stream>>>(in, N, C, H * W, Cpad, out);
+    lf_launch(nchw_to_nhwc_pad_kernel, grid_for((long long)N * H * W, 256), 256, 0, stream, in, N, C, H * W, Cpad, out);
     return check_launch();
 }
 
@@ -660,7 +675,7 @@ extern "C" int lf_nhwc_to_nchw(const float* in, int N, int H, int W, int C, floa
     const int R = H * W, S = C;  // [HW][C] -> [C][HW]
     dim3 grid((S + 31) / 32, (R + 31) / 32, N), block(32, 8);
     LF_REQUIRE((R + 31) / 32 <= 65535);
-    batched_transpose_kernel<<<grid, block, 0, stream>>>(in, R, S, out);
+    lf_launch(batched_transpose_kernel, grid, block, 0, stream, in, R, S, out);
     return check_launch();
 }
 
@@ -669,6 +684,6 @@ extern "C" int lf_nchw_to_nhwc(const float* in, int N, int C, int H, int W, floa
     LF_REQUIRE(in && out && N > 0 && N <= 65535);
     const int R = C, S = H * W;  // [C][HW] -> [HW][C]
     dim3 grid((S + 31) / 32, (R + 31) / 32, N), block(32, 8);
-    batched_transpose_kernel<<<grid, block, 0, stream>>>(in, R, S, out);
+    lf_launch(batched_transpose_kernel, grid, block, 0, stream, in, R, S, out);
     return check_launch();
 }

@@ -30,6 +30,7 @@ struct WgCfg {
 
 template <int TP, int TQ>
 __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const WgradArgs a) {
+    pdl_entry();
     using Cfg = WgCfg<TP, TQ>;
     __shared__ __align__(16) float smem[Cfg::SMEM_FLOATS];
     float(*Ps)[Cfg::PXS][TP] = reinterpret_cast<float(*)[Cfg::PXS][TP]>(smem);
@@ -229,6 +230,7 @@ __device__ __forceinline__ void ws_cp_async16(float* smem_dst, const float* gsrc
 }
 
 __global__ void __launch_bounds__(256, 2) wgrad_small_kernel(const WgradArgs a, const WsPlan pl) {
+    pdl_entry();
     extern __shared__ __align__(16) float ws_smem[];
     const int LU = pl.LU, LV = pl.LV, PXS = pl.PXS, G = pl.G;
     float* sU = ws_smem;                  // [2][PXS][LU]
@@ -398,6 +400,7 @@ constexpr int WR_LANES = 8;
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int ntaps, int Cp,
                                                             int Cq, int CpPad, int CqPad, float* __restrict__ dst, int st, int sp,
                                                             int sq) {
+    pdl_entry();
     __shared__ float4 red[256];
     const int Cq4 = (Cq + 3) >> 2;
     const int total4 = ntaps * Cp * Cq4;
@@ -446,6 +449,7 @@ struct ReduceJobs {
     int njobs;
 };
 __global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceJobs js) {
+    pdl_entry();
     __shared__ float4 red[256];
     const LfReduceJob& j = js.job[blockIdx.y];
     const int Cq4 = (j.Cq + 3) >> 2;
@@ -491,6 +495,7 @@ __global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceJobs js) 
 }
 
 __global__ void vec_reduce_kernel(const float* __restrict__ partial, int nsplit, int C, int Cpad, float* __restrict__ dst) {
+    pdl_entry();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float s = 0.f;
@@ -506,6 +511,7 @@ constexpr int COLSUM_MIN_PIX = 128;
 // Thread -> (pixel lane, channel); channels fastest so a warp reads contiguous memory.
 __global__ void __launch_bounds__(COLSUM_THREADS) colsum_kernel(const float* __restrict__ src, long long npix, int C,
                                                                  int cstride, int coff, float* __restrict__ partial, int Cpad) {
+    pdl_entry();
     __shared__ float red[COLSUM_THREADS];
     const int tid = threadIdx.x;
     const long long per = (npix + gridDim.x - 1) / gridDim.x;
@@ -555,7 +561,7 @@ extern "C" int lf_wgrad_f32(const LfWgradArgs* args, lf_stream_t stream_) {
     if (ws_make_plan(a, &wsp)) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        wgrad_small_kernel<<<a.nsplit, wsp.threads, wsp.smem_bytes, stream>>>(a, wsp);
+        lf_launch(wgrad_small_kernel, a.nsplit, wsp.threads, wsp.smem_bytes, stream, a, wsp);
         return check_launch();
     }
     const bool smallP = a.Cp <= 16, smallQ = a.Cq <= 16;
@@ -565,13 +571,13 @@ extern "C" int lf_wgrad_f32(const LfWgradArgs* args, lf_stream_t stream_) {
     const WgradArgs& b = a;
     dim3 grid(tilesP * tilesQ * a.ntaps, a.nsplit);
     if (smallP && smallQ)
-        wgrad_f32_kernel<16, 16><<<grid, WG_THREADS, 0, stream>>>(b);
+        lf_launch(wgrad_f32_kernel<16, 16>, grid, WG_THREADS, 0, stream, b);
     else if (smallP)
-        wgrad_f32_kernel<16, 64><<<grid, WG_THREADS, 0, stream>>>(b);
+        lf_launch(wgrad_f32_kernel<16, 64>, grid, WG_THREADS, 0, stream, b);
     else if (smallQ)
-        wgrad_f32_kernel<64, 16><<<grid, WG_THREADS, 0, stream>>>(b);
+        lf_launch(wgrad_f32_kernel<64, 16>, grid, WG_THREADS, 0, stream, b);
     else
-        wgrad_f32_kernel<64, 64><<<grid, WG_THREADS, 0, stream>>>(b);
+        lf_launch(wgrad_f32_kernel<64, 64>, grid, WG_THREADS, 0, stream, b);
     return check_launch();
 }
 
@@ -598,7 +604,7 @@ extern "C" int lf_wgrad_reduce(const float* partial, int nsplit, int ntaps, int 
     LF_REQUIRE(CqPad % 4 == 0);
     const int total4 = ntaps * Cp * ((Cq + 3) / 4);
     const int per_block = 256 / WR_LANES;
-    wgrad_reduce_kernel<<<(total4 + per_block - 1) / per_block, 256, 0, stream>>>(partial, nsplit, ntaps, Cp, Cq, CpPad, CqPad,
+    lf_launch(wgrad_reduce_kernel, (total4 + per_block - 1) / per_block, 256, 0, stream, partial, nsplit, ntaps, Cp, Cq, CpPad, CqPad,
                                                                                    dst, st, sp, sq);
     return check_launch();
 }
@@ -618,14 +624,14 @@ extern "C" int lf_reduce_multi(const LfReduceJob* jobs, int njobs, lf_stream_t s
         const int nb = (total4 + per_block - 1) / per_block;
         if (nb > max_blocks) max_blocks = nb;
     }
-    reduce_multi_kernel<<<dim3(max_blocks, njobs), 256, 0, stream>>>(js);
+    lf_launch(reduce_multi_kernel, dim3(max_blocks, njobs), 256, 0, stream, js);
     return check_launch();
 }
 
 extern "C" int lf_vec_reduce(const float* partial, int nsplit, int C, int Cpad, float* dst, lf_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     LF_REQUIRE(partial && dst && nsplit >= 1 && C >= 1 && Cpad >= C);
-    vec_reduce_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, nsplit, C, Cpad, dst);
+    lf_launch(vec_reduce_kernel, (C + 127) / 128, 128, 0, stream, partial, nsplit, C, Cpad, dst);
     return check_launch();
 }
 
@@ -639,6 +645,6 @@ extern "C" int lf_colsum(const float* src, long long npix, int C, int cstride, i
                          lf_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     LF_REQUIRE(src && partial && npix > 0 && C >= 1 && Cpad >= C);
-    colsum_kernel<<<lf_colsum_blocks(npix), COLSUM_THREADS, 0, stream>>>(src, npix, C, cstride, coff, partial, Cpad);
+    lf_launch(colsum_kernel, lf_colsum_blocks(npix), COLSUM_THREADS, 0, stream, src, npix, C, cstride, coff, partial, Cpad);
     return check_launch();
 }

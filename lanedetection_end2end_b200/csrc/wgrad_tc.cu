@@ -63,6 +63,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 template <int C>
 __global__ void __launch_bounds__(WT_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WtArgs a) {
+    pdl_trigger();
     using Cfg = WtCfg<C>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -93,6 +94,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0) {
         // TMA producer: whole warp converged (uniform coordinates / addresses), one elected lane issues
@@ -264,11 +266,11 @@ extern "C" int lf_wgrad3_tc(const float* x, const float* dy, int N, int H, int W
     if (C == 128) {
         e = cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WtCfg<128>::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        wgrad_tc_kernel<128><<<nctas, WT_THREADS, WtCfg<128>::SMEM_BYTES, stream>>>(tmX, tmDY, a);
+        lf_launch(wgrad_tc_kernel<128>, nctas, WT_THREADS, WtCfg<128>::SMEM_BYTES, stream, tmX, tmDY, a);
     } else {
         e = cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WtCfg<64>::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        wgrad_tc_kernel<64><<<nctas, WT_THREADS, WtCfg<64>::SMEM_BYTES, stream>>>(tmX, tmDY, a);
+        lf_launch(wgrad_tc_kernel<64>, nctas, WT_THREADS, WtCfg<64>::SMEM_BYTES, stream, tmX, tmDY, a);
     }
     return check_launch();
 }

@@ -65,6 +65,7 @@ __device__ __forceinline__ float4 wx_lo4(float4 v) { return make_float4(wx_lo(v.
 template <int C>
 __global__ void __launch_bounds__(WX_THREADS, 1)
 wgrad_tc_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WxArgs a) {
+    pdl_trigger();
     using Cfg = WxCfg<C>;
     constexpr int CB = Cfg::CB, BOX = Cfg::BOX_BYTES, S = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -102,6 +103,7 @@ wgrad_tc_x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0) {
         // TMA producer: whole warp converged (uniform coordinates / addresses), one elected lane issues
@@ -344,11 +346,11 @@ extern "C" int lf_wgrad3_tc_x3(const float* x, const float* dy, int N, int H, in
     if (C == 128) {
         e = cudaFuncSetAttribute(wgrad_tc_x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WxCfg<128>::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        wgrad_tc_x3_kernel<128><<<nctas, WX_THREADS, WxCfg<128>::SMEM_BYTES, stream>>>(tmX, tmDY, a);
+        lf_launch(wgrad_tc_x3_kernel<128>, nctas, WX_THREADS, WxCfg<128>::SMEM_BYTES, stream, tmX, tmDY, a);
     } else {
         e = cudaFuncSetAttribute(wgrad_tc_x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WxCfg<64>::SMEM_BYTES);
         if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-        wgrad_tc_x3_kernel<64><<<nctas, WX_THREADS, WxCfg<64>::SMEM_BYTES, stream>>>(tmX, tmDY, a);
+        lf_launch(wgrad_tc_x3_kernel<64>, nctas, WX_THREADS, WxCfg<64>::SMEM_BYTES, stream, tmX, tmDY, a);
     }
     return check_launch();
 }

@@ -64,6 +64,7 @@ template <bool X3>
 __global__ void __launch_bounds__(X3 ? WG_THREADS_X3 : WG_THREADS_TC, 1)
 wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const WgtArgs a) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // slack of 3 boxes after the last stage: the trailing M=128 group may read up to 3 boxes past its blocks
@@ -102,6 +103,7 @@ wgrad_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0) {
         // TMA producer: converged warp, elected lane issues
@@ -342,7 +344,7 @@ extern "C" int lf_wgrad_tcg(const LfWgradTcgArgs* args, lf_stream_t stream_) {
     cudaError_t e = x3 ? cudaFuncSetAttribute(wgrad_tcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_LIMIT)
                        : cudaFuncSetAttribute(wgrad_tcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_LIMIT);
     if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
-    if (x3) wgrad_tcg_kernel<true><<<p.nctas, WG_THREADS_X3, smem_bytes, stream>>>(tmA0, tmA1, tmB, a);
-    else wgrad_tcg_kernel<false><<<p.nctas, WG_THREADS_TC, smem_bytes, stream>>>(tmA0, tmA1, tmB, a);
+    if (x3) lf_launch(wgrad_tcg_kernel<true>, p.nctas, WG_THREADS_X3, smem_bytes, stream, tmA0, tmA1, tmB, a);
+    else lf_launch(wgrad_tcg_kernel<false>, p.nctas, WG_THREADS_TC, smem_bytes, stream, tmA0, tmA1, tmB, a);
     return check_launch();
 }

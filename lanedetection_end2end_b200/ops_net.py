@@ -780,15 +780,15 @@ def _bn_state(C, device):
     return s
 
 
-def bn_finalize(part, nblk, npix, C, gamma, beta, running_mean, running_var):
+def bn_finalize(part, nblk, npix, C, gamma, beta, running_mean, running_var, eps=BN_EPS):
     """part: float64 [nblk][2][C] partial sums / sums of squares -> BNState (+ running-stat update)."""
     s = _bn_state(C, part.device)
-    _capi.call("lf_bn_finalize", ptr(part), nblk, npix, C, ptr(gamma), ptr(beta), BN_EPS, BN_MOMENTUM,
+    _capi.call("lf_bn_finalize", ptr(part), nblk, npix, C, ptr(gamma), ptr(beta), eps, BN_MOMENTUM,
                ptr(running_mean), ptr(running_var), ptr(s.mean), ptr(s.invstd), ptr(s.scale), ptr(s.shift), _stream())
     return s
 
 
-def bn_forward_stats(x, gamma, beta, running_mean, running_var, training):
+def bn_forward_stats(x, gamma, beta, running_mean, running_var, training, eps=BN_EPS):
     """x: dense NHWC.  Returns BNState; updates running stats in training mode
     (nn.BatchNorm2d(eps=1e-3, momentum=0.1), ERFNet.py:17,33,39,102)."""
     h = _lib()
@@ -798,9 +798,9 @@ def bn_forward_stats(x, gamma, beta, running_mean, running_var, training):
         nblk = h.lf_bn_blocks(npix, C)
         part = torch.empty(nblk * 2 * C, dtype=torch.float64, device=x.device)
         _capi.call("lf_bn_stats", ptr(x), npix, C, ptr(part), _stream(), nbytes=4 * npix * C)
-        return bn_finalize(part, nblk, npix, C, gamma, beta, running_mean, running_var)
+        return bn_finalize(part, nblk, npix, C, gamma, beta, running_mean, running_var, eps)
     s = _bn_state(C, x.device)
-    _capi.call("lf_bn_eval_prepare", C, ptr(gamma), ptr(beta), BN_EPS, ptr(running_mean), ptr(running_var),
+    _capi.call("lf_bn_eval_prepare", C, ptr(gamma), ptr(beta), eps, ptr(running_mean), ptr(running_var),
                ptr(s.scale), ptr(s.shift), _stream())
     return s
 

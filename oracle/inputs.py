@@ -143,3 +143,37 @@ def make_erfnet_params(in_channels=3, nclasses=2, seed=0, prefix="net.", bias_sc
             w = bias_scale * rng.standard_normal(shape)
         params[prefix + name] = w.astype(np.float32)
     return params
+
+
+HEAD_SHAPES = {   # Classification(class_type, size=(32, 64), channels_in=128, resize=256), BP/Networks/LSQ_layer.py:157-192
+    "common": [("conv1.weight", (128, 128, 1, 1)), ("conv1.bias", (128,)), ("conv1_bn.weight", (128,)), ("conv1_bn.bias", (128,)),
+               ("conv2.weight", (128, 128, 3, 3)), ("conv2.bias", (128,)), ("conv2_bn.weight", (128,)), ("conv2_bn.bias", (128,)),
+               ("conv3.weight", (64, 128, 3, 3)), ("conv3.bias", (64,)), ("conv3_bn.weight", (64,)), ("conv3_bn.bias", (64,)),
+               ("conv4.weight", (64, 64, 3, 3)), ("conv4.bias", (64,)), ("conv4_bn.weight", (64,)), ("conv4_bn.bias", (64,))],
+    "line": [("fully_connected1.weight", (128, 32768)), ("fully_connected1.bias", (128,)),
+             ("fully_connected_line1.weight", (4, 128)), ("fully_connected_line1.bias", (4,))],
+    "horizon": [("fully_connected_horizon.weight", (256, 2048)), ("fully_connected_horizon.bias", (256,))],
+}
+
+
+def make_head_params(class_type, seed):
+    """Synthetic parameters of one Classification head keyed like its state_dict (kaiming-style weights, N(1, 0.02)
+    BatchNorm weights, N(0, 0.05) biases so that every bias path is exercised)."""
+    rng = np.random.default_rng(seed)
+    params = {}
+    for name, shape in HEAD_SHAPES["common"] + HEAD_SHAPES[class_type]:
+        if name.endswith("_bn.weight"):
+            w = 1.0 + 0.02 * rng.standard_normal(shape)
+        elif name.endswith(".bias"):
+            w = 0.05 * rng.standard_normal(shape)
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            w = rng.standard_normal(shape) * math.sqrt(2.0 / fan_in)
+        params[name] = w.astype(np.float32)
+    return params
+
+
+def make_encoder_map(B, seed, C=128, H=32, W=64):
+    """A post-ReLU-like encoder output [B,C,H,W]: max(0, N(0.3, 1))."""
+    rng = np.random.default_rng(seed)
+    return np.maximum(rng.standard_normal((B, C, H, W)) + 0.3, 0.0).astype(np.float32)

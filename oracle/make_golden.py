@@ -253,7 +253,47 @@ def run_area_loss():
     return "area_loss", out
 
 
+def run_clas_heads():
+    """Classification heads (`--clas 1`, BP/Networks/LSQ_layer.py:157-207): the reference's own class on a seeded encoder
+    map, fp32 and fp64, forward + backward of sum(out * g)."""
+    ns = ri.import_reference("Backprojection_Loss")
+    B = 2
+    x_np = inputs.make_encoder_map(B, seed=21)
+    out = {"meta": json.dumps(dict(B=B, map_seed=21, param_seeds={"line": 31, "horizon": 32}, g_seeds={"line": 41, "horizon": 42}))}
+    for kind, pseed, gseed in (("line", 31, 41), ("horizon", 32, 42)):
+        P = inputs.make_head_params(kind, pseed)
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            torch.manual_seed(0)
+            m = ns.LSQ_layer.Classification(kind, size=(32, 64), channels_in=128, resize=256)
+            sd = m.state_dict()
+            for k, v in P.items():
+                assert tuple(sd[k].shape) == v.shape, (k, sd[k].shape, v.shape)
+                sd[k] = torch.from_numpy(v)
+            m.load_state_dict(sd)
+            m = m.to(dt).train()
+            x = torch.from_numpy(x_np).to(dt).requires_grad_(True)
+            y = m(x)
+            g = torch.from_numpy(np.random.default_rng(gseed).standard_normal(tuple(y.shape))).to(dt)
+            (y * g).sum().backward()
+            out["%s/out_%s" % (kind, tag)] = y.detach().double().numpy()
+            summarize("%s/dx_%s" % (kind, tag), x.grad, 4096, out)
+            for n, p in m.named_parameters():
+                summarize("%s/grad_%s/%s" % (kind, tag, n), p.grad, 1024, out)
+            for n, b in m.named_buffers():
+                if n.endswith("running_mean") or n.endswith("running_var"):
+                    out["%s/buf_%s/%s" % (kind, tag, n)] = b.detach().double().numpy()
+        out["%s/g" % kind] = np.random.default_rng(gseed).standard_normal(tuple(y.shape))
+    return "clas_heads", out
+
+
 def main():
+    if "--only-clas" in sys.argv:
+        os.makedirs(GOLDEN_DIR, exist_ok=True)
+        name, out = run_clas_heads()
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes")
+        return 0
     if "--only-area" in sys.argv:      # add the A12 fixture without touching the (bit-identical) existing ones
         os.makedirs(GOLDEN_DIR, exist_ok=True)
         name, out = run_area_loss()
@@ -263,7 +303,7 @@ def main():
         return 0
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    jobs = [run_homography(), run_area_loss()]
+    jobs = [run_homography(), run_area_loss(), run_clas_heads()]
     for i, c in enumerate(LSQ_CASES):
         name, out = run_lsq_case(c)
         if c[0] not in ("bp_l2_d2", "bev_l2_d2"):

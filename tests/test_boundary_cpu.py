@@ -252,3 +252,22 @@ def test_backprojection_loss_all_lanes_at_once_equals_the_lane_loop():
         for l in range(L):
             torch.testing.assert_close(xcal[:, l], crit(betas[l], x_gt[:, l], valid[:, l])[1], rtol=1e-13, atol=1e-10)
             torch.testing.assert_close(gours[l], gref[l], rtol=1e-10, atol=1e-16)
+
+
+def test_classification_heads_state_dict_and_no_cpu_fallback():
+    """`--clas 1` heads (BP/Networks/LSQ_layer.py:157-207): parameter names / shapes of the reference (checkpoints round-trip),
+    and no CPU path -- a CPU tensor raises instead of silently running torch modules."""
+    import pytest
+    import torch
+    from oracle import inputs
+    from lanedetection_end2end_b200 import _capi
+    from lanedetection_end2end_b200.Networks.LSQ_layer import Classification
+    for kind in ("line", "horizon"):
+        m = Classification(kind, size=(32, 64), channels_in=128, resize=256)
+        sd = m.state_dict()
+        want = dict(inputs.HEAD_SHAPES["common"] + inputs.HEAD_SHAPES[kind])
+        have = {k: tuple(v.shape) for k, v in sd.items() if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))}
+        assert have == want
+        assert m.conv1_bn.eps == 1e-5
+        with pytest.raises(_capi.LanefitError):
+            m(torch.zeros(1, 128, 32, 64))

@@ -146,3 +146,27 @@ def test_area_loss_matches_reference_golden(order, wf):
                 assert np.abs(p.grad.double().numpy() - wgrad).max() <= tol * np.abs(wgrad).max(), (impl, key)
         z = Area_Loss(2, "none")(torch.from_numpy(g["params"]).float(), torch.zeros(6, 3))
         assert float(z) == float(g[variant + "/all_absent"]) == 0.0
+
+
+@pytest.mark.parametrize("kind", ["line", "horizon"])
+def test_heads_restatement_matches_reference_golden(kind):
+    """oracle/heads_oracle.py (fp64) against the reference's own Classification class (clas_heads.npz): forward and the
+    sampled input / parameter gradients."""
+    import json
+    from oracle import heads_oracle
+    g = np.load(os.path.join(GOLDEN, "clas_heads.npz"))
+    meta = json.loads(str(g["meta"]))
+    P = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in inputs.make_head_params(kind, meta["param_seeds"][kind]).items()}
+    x = torch.from_numpy(inputs.make_encoder_map(meta["B"], seed=meta["map_seed"])).double().requires_grad_(True)
+    y = heads_oracle.head_forward(P, x, kind)
+    ref = g["%s/out_f64" % kind]
+    assert np.abs(y.detach().numpy() - ref).max() <= 1e-9 * np.abs(ref).max()
+    (y * torch.from_numpy(g["%s/g" % kind])).sum().backward()
+    k = "%s/dx_f64" % kind
+    assert np.abs(x.grad.numpy().reshape(-1)[g[k + "/idx"]] - g[k + "/val"]).max() <= 1e-8 * g[k + "/stat"][2]
+    for n, p in P.items():
+        k = "%s/grad_f64/%s" % (kind, n)
+        scale = max(g[k + "/stat"][2], 1e-12)
+        if n.startswith("conv") and n.endswith(".bias") and "_bn" not in n:
+            continue        # analytically zero (conv feeding a training-mode BatchNorm): pure round-off on both sides
+        assert np.abs(p.grad.numpy().reshape(-1)[g[k + "/idx"]] - g[k + "/val"]).max() <= 1e-7 * scale, n
