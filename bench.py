@@ -46,6 +46,7 @@ MODE_ACCURACY = {"tf32x3": "meets the reference-fp32 gates: on the reference's g
                          "the 1e-4 gate; labelled extra only (profiles/r01/tf32_accuracy_*.json)",
                  "fp32": "meets the same gates as tf32x3 (tests/test_net_gpu.py)"}
 FWD_GFLOP_PER_IMG = {(2, 256): 13.231, (4, 256): 13.239, (4, 320): 20.686, (2, 320): 20.673}
+FWD_GFLOP_PER_IMG_CLAS = {(4, 256): 15.497}        # + the two Classification heads
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -111,6 +112,8 @@ def build_args(cfg, no_cuda=False):
     argv = ["--image_dir", "x", "--gt_dir", "y", "--nclasses", str(cfg["nclasses"]), "--order", str(cfg["order"]),
             "--batch_size", str(cfg["batch"]), "--mask_percentage", str(cfg["mask"]), "--resize", str(cfg["resize"]),
             "--loss_policy", "backproject", "--end_to_end", "True"]
+    if cfg.get("clas"):
+        argv += ["--clas", "1"]          # line-type + horizon heads on the shared encoder output (BP/train.sh:1)
     if no_cuda:
         argv.append("--no_cuda")
     return define_args().parse_args(argv)
@@ -178,7 +181,8 @@ def cpu_reference_run(cfg, steps, warmup, sample_images):
     L, order, R = cfg["nclasses"], cfg["order"], cfg["resize"]
     Bs = max(1, min(cfg["batch"], sample_images))
     args = ri.make_args(ns, ["--nclasses", str(L), "--order", str(order), "--batch_size", str(Bs), "--mask_percentage",
-                             str(cfg["mask"]), "--resize", str(R), "--loss_policy", "backproject", "--end_to_end", "True"])
+                             str(cfg["mask"]), "--resize", str(R), "--loss_policy", "backproject", "--end_to_end", "True"]
+                       + (["--clas", "1"] if cfg.get("clas") else []))
     torch.manual_seed(0)
     model = ns.LSQ_layer.Net(args)
     with contextlib.redirect_stdout(io.StringIO()):
@@ -192,10 +196,17 @@ def cpu_reference_run(cfg, steps, warmup, sample_images):
     valid[:, :, :8] = 0
     gt_line = torch.zeros(Bs, 4)
 
+    bce = torch.nn.BCEWithLogitsLoss()
+    gt_cls = torch.ones(Bs, 4)
+    gt_hor = torch.zeros(Bs, R)
+    gt_hor[:, 80] = 1.0
+
     def one_step(n=Bs):
         model.zero_grad()
         out = model(x[:n], gt_line[:n], True)
         loss = sum(crit(out[l], xgt[:n, l], valid[:n, l])[0] for l in range(L)) / L
+        if cfg.get("clas"):      # BP/main.py:321-326
+            loss = loss + (bce(out[6], gt_cls[:n]) + bce(out[7], gt_hor[:n])).double()
         loss.backward()
 
     # the reference sizes its grid / constants for args.batch_size: the probe uses the full sample
@@ -336,6 +347,16 @@ def run_ours(a, cfg):
     dx, dxgt, dvalid = hx.to(dev), hxgt.to(dev), hvalid.to(dev)
     gt_line = torch.zeros(B, 4)
 
+    clas = bool(cfg.get("clas"))
+    if clas:
+        # BP/main.py:109-110,321-326: BCEWithLogits on the two heads, added with weight_class = weight_fit = 1
+        bce = torch.nn.BCEWithLogitsLoss()
+        gt_cls = torch.ones(B, 4, device=dev)
+        gt_hor = torch.zeros(B, cfg["resize"], device=dev)
+        gt_hor[:, 80] = 1.0
+
+    extra_loss = (lambda out: (bce(out[6], gt_cls) + bce(out[7], gt_hor)).double()) if clas else None
+
     def step(x, xgt, valid):
         model.zero_grad(set_to_none=True)
         out = model(x, gt_line, True)
@@ -344,6 +365,8 @@ def run_ours(a, cfg):
             ll, _ = crit(out[l], xgt[:, l], valid[:, l])
             loss = loss + ll
         loss = loss / L
+        if clas:
+            loss = loss + extra_loss(out)
         loss.backward()
         if reducer is not None:
             reducer()
@@ -385,7 +408,7 @@ def run_ours(a, cfg):
         ok = 1
         try:
             gstep = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, reducer,
-                                     capture_error_mode="thread_local" if world > 1 else "global")
+                                     capture_error_mode="thread_local" if world > 1 else "global", extra_loss=extra_loss)
         except Exception as e:        # capture failed: report it and measure eagerly instead
             sys.stderr.write("CUDA graph capture failed (%s: %s); falling back to eager launches\n" % (type(e).__name__, e))
             ok = 0
@@ -449,7 +472,7 @@ def run_ours(a, cfg):
                 if a.graph:
                     from lanedetection_end2end_b200.engine import GraphedTrainStep
                     try:
-                        pg = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, None)
+                        pg = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, None, extra_loss=extra_loss)
                     except Exception as e:
                         sys.stderr.write("%s: graph capture failed (%s: %s); timing eager launches\n" % (label, type(e).__name__, e))
                         pg = None
@@ -553,7 +576,7 @@ def run_ours(a, cfg):
     if rank == 0:
         imgs = world * B * a.steps
         h2d = hx.numel() * 4 + hxgt.numel() * 8 + hvalid.numel() * 8
-        gflop = FWD_GFLOP_PER_IMG.get((L, cfg["resize"]))
+        gflop = (FWD_GFLOP_PER_IMG_CLAS if cfg.get("clas") else FWD_GFLOP_PER_IMG).get((L, cfg["resize"]))
         line = {"metric": "images/sec (fwd+bwd)", "value": imgs / (ms_dev * 1e-3), "unit": "images/sec",
                 "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -596,6 +619,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
+    ap.add_argument("--clas", action="store_true",
+                    help="add the Classification heads (--clas 1 of BP/train.sh:1; SURVEY.md 8f-2) and their BCE losses to the step")
     ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=32,
                     help="images per CPU-baseline / reference-arm step (default: the whole 32-image batch of config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -615,6 +640,9 @@ def main():
     cfg = dict(CONFIGS[a.config])
     if a.batch:
         cfg["batch"] = a.batch
+    if a.clas:
+        cfg["clas"] = True
+        cfg["name"] += "_clas"
     if a.impl == "reference":
         run_reference_arm(a, cfg)
     else:

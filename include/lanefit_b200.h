@@ -404,6 +404,16 @@ int lf_linear_bwd_data(const float* dy, const float* relu_out, const float* W, i
 int lf_linear_bwd_weight(const float* dy, const float* relu_out, const float* x, int B, int K, int O, float* dW, float* db,
                          lf_stream_t stream);
 
+/* Loader image path on the GPU (csrc/input_pipe.cu; replaces BP/Dataloader/Load_Data_new.py:127-131,166-167,178-181):
+ * frames uint8 [N][Hin][Win][3] (decoded RGB) -> rows [crop_y0, crop_y0+crop_rows) -> PIL-BILINEAR resize to [Ho][Wo]
+ * (Pillow's fixed-point two-pass resample, bit-identical) -> per-image horizontal flip (flip[n] != 0; NULL = none) ->
+ * float32 / 255.  xb/yb: [Wo][2] / [Ho][2] (first source index, tap count) and xk/yk: [Wo][kx] / [Ho][ky] integer
+ * coefficients (22 fractional bits) of the two axes, built by input_pipeline.resample_tables (the vertical axis over the
+ * crop_rows rows).  layout 0: out [N][3][Ho][Wo]; 1: out [N][Ho][Wo][4] (NHWC, channel 3 = 0). */
+int lf_frame_preprocess(const unsigned char* frames, int N, int Hin, int Win, int crop_y0, int crop_rows, const int* xb, const int* xk,
+                        int kx, const int* yb, const int* yk, int ky, int Ho, int Wo, const unsigned char* flip, int layout,
+                        float* out, lf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -204,6 +204,9 @@ class Net(nn.Module):
         if self.classification_branch:
             self.line_classification = Classification("line", size=(32, 64), channels_in=128, resize=resize)
             self.horizon_estimation = Classification("horizon", size=(32, 64), channels_in=128, resize=resize)
+            # the heads' conv weights are re-packed by the ERFNet module's one-launch weight packer (plain dict entry:
+            # not a second registration of the submodules)
+            self.net.__dict__["_pack_extra"] = (self.line_classification, self.horizon_estimation)
         if not args.no_cuda:
             self.idx_row = self.idx_row.cuda()
         self.defer_status_check = False

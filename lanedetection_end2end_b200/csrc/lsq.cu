@@ -337,6 +337,39 @@ __device__ void lsq_chunk_tail(const LsqArgs& a, double (*red)[LSQ_MAXL][LSQ_MAX
     lsq_finalize(a, b, l0, nl, mom, ticket_idx);
 }
 
+// Warp reduction of NV (2, 4 or 8) per-thread values at once: each butterfly step also halves the number of values a
+// lane carries, so the whole reduction takes NV/2 + NV/4 + .. + 1 + (5 - log2 NV) shuffles instead of 5 * NV.
+// Returns, in every lane, the warp total of ONE value: value i ends up in the lanes packed_holder<NV>(i) + {0 .. 32/NV - 1}.
+template <int NV>
+__device__ __forceinline__ float warp_sum_packed(float (&v)[NV], int lane) {
+    int m = 16;
+#pragma unroll
+    for (int n = NV; n > 1; n >>= 1, m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (; m > 0; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+    return r;
+}
+// first lane that holds the total of value i after warp_sum_packed<NV>: step s (mask 16 >> s) keeps the upper half of the
+// remaining values in the lanes whose bit (4 - s) is set, i.e. lane bit (4 - s) = bit (log2 NV - 1 - s) of i
+template <int NV>
+__device__ __forceinline__ int packed_holder(int i) {
+    constexpr int LOG = NV == 8 ? 3 : NV == 4 ? 2 : 1;
+    int lane = 0;
+#pragma unroll
+    for (int s = 0; s < LOG; ++s)
+        if ((i >> (LOG - 1 - s)) & 1) lane |= 16 >> s;
+    return lane;
+}
+
 // ---------------------------------------------------------------------------------
 // Forward, row-separable fast path.  grid = (nchunks, B, ceil(L/4)), 256 threads.
 // ---------------------------------------------------------------------------------
@@ -352,6 +385,8 @@ __global__ void __launch_bounds__(LSQ_THREADS, LSQ_FWD_CTAS_PER_SM) lsq_fwd_rows
     const int l0 = lg * NL;
     const int nl = min(NL, a.L - l0);
     constexpr int UNR = (NL <= 2) ? 4 : 2;
+    constexpr int NLP = NL <= 1 ? 1 : NL <= 2 ? 2 : 4;   // lanes padded to a power of two
+    constexpr int NV = 2 * NLP;                          // values per packed warp reduction
     const int d = a.order, NM = 3 * d + 2;
     constexpr int V = MapVec<BF16>::V;
     const int WV = a.W / V;
@@ -429,11 +464,21 @@ __global__ void __launch_bounds__(LSQ_THREADS, LSQ_FWD_CTAS_PER_SM) lsq_fwd_rows
             const double y = (double)__ldg(a.yrow + r + u);
             double pw = 1.0;
             for (int i = 0; i < ek && i < 2 * LF_MAX_ORDER; ++i) pw *= y;
+            // The 2*NL row sums (A_l, B_l) are reduced over the warp TOGETHER, in fp32: NV/2 + NV/4 + .. shuffles instead of
+            // 2*NL full fp64 butterflies (80 64-bit shuffles per row at NL = 4, the kernel's issue bound: a row is only 2-8 KB
+            // of map data).  The per-thread partials are fp32 sums of 16-32 products already; five more fp32 additions do
+            // not change the error class, and the sum over rows -- where the cancellation lives -- stays fp64.
+            float v[NV];
+#pragma unroll
+            for (int l = 0; l < NLP; ++l) {
+                v[l] = l < NL ? A[u][l] : 0.f;
+                v[NLP + l] = l < NL ? Bx[u][l] : 0.f;
+            }
+            const float tot = warp_sum_packed<NV>(v, lane);
 #pragma unroll
             for (int l = 0; l < NL; ++l) {
-                const double As = warp_sum((double)A[u][l]);
-                const double Bs = warp_sum((double)Bx[u][l]);
-                acc[l] = fma(pw, useB ? Bs : As, acc[l]);
+                const float s = __shfl_sync(0xffffffffu, tot, packed_holder<NV>((useB ? NLP : 0) + l));
+                acc[l] = fma(pw, (double)s, acc[l]);
             }
         }
     }

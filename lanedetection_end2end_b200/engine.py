@@ -22,8 +22,9 @@ FUSED_LOSS = os.environ.get("LANEFIT_FUSED_LOSS", "1") != "0"
 
 class GraphedTrainStep:
     def __init__(self, model, criterion, nclasses, example_x, example_xgt, example_valid, reducer=None, warmup=3,
-                 capture_error_mode="global"):
+                 capture_error_mode="global", extra_loss=None):
         self.model = model
+        self.extra_loss = extra_loss      # callable(forward 9-tuple) -> scalar added to the loss (e.g. the --clas head losses)
         self.crit = criterion
         self.L = nclasses
         self.reducer = reducer
@@ -70,6 +71,8 @@ class GraphedTrainStep:
                 ll, _ = self.crit(out[l], self.xgt[:, l], self.valid[:, l])
                 loss = loss + ll
             loss = loss / self.L
+        if self.extra_loss is not None:
+            loss = loss + self.extra_loss(out)
         loss.backward()
         if self.reducer is not None:
             self.reducer()

@@ -342,7 +342,10 @@ class WeightPackCache:
         self.dirty = False
 
     def _scan(self):
-        self.by_ptr = {p.data_ptr(): p for p in self.module.parameters() if p.is_cuda}
+        # `_pack_extra`: further modules whose conv weights are served by this cache (the Classification heads, which
+        # hang off LSQ_layer.Net next to the ERFNet module that owns the cache)
+        mods = [self.module] + list(self.module.__dict__.get("_pack_extra", ()))
+        self.by_ptr = {p.data_ptr(): p for m in mods for p in m.parameters() if p.is_cuda}
 
     def get(self, w, kind, fn, split=False):
         if not w.is_cuda:
