@@ -166,7 +166,8 @@ typedef struct LfConvTcArgs {
     const float* mask_shift;
     int N, H, W, C;
     int dy[3], dx[3];
-    int relu;
+    int relu;                /* bit 0: ReLU on conv + bias (before mask / add_src); bit 1: ReLU after add_src -- the closing
+                                relu(conv + x) of an eval-mode block whose BatchNorm is folded into the weights */
 } LfConvTcArgs;
 /* 0 = unsupported shape, else the number of CTA rows of colsum_partial */
 int lf_conv1d_tc_supported(int N, int H, int W, int C);
@@ -250,6 +251,10 @@ int lf_colsum(const float* src, long long npix, int C, int cstride, int coff, fl
  * gradient (first maximum wins, like ATen); accumulate != 0 adds into d_in. */
 int lf_maxpool2_fwd(const float* in, int N, int Hin, int Win, int C, int in_cstride, float* out,
                     int out_cstride, int out_coff, lf_stream_t stream);
+/* eval mode: out = relu(pool * scale[out_coff + c] + shift[out_coff + c]) -- the pooled half of relu(bn(cat[conv, pool]))
+ * with the BatchNorm reduced to its running-statistics affine (lf_bn_eval_prepare) */
+int lf_maxpool2_affine_relu(const float* in, int N, int Hin, int Win, int C, int in_cstride, const float* scale,
+                            const float* shift, float* out, int out_cstride, int out_coff, lf_stream_t stream);
 int lf_maxpool2_bwd(const float* in, int N, int Hin, int Win, int C, int in_cstride, const float* d_out,
                     int out_cstride, int out_coff, float* d_in, int din_cstride, int accumulate,
                     lf_stream_t stream);
@@ -326,6 +331,7 @@ typedef struct LfConvTcgArgs {
     int map[LF_TCG_MAX_TAPS], dy[LF_TCG_MAX_TAPS], dx[LF_TCG_MAX_TAPS];
     int precision;          /* 0 = TF32 multiply; 1 = 3xTF32 (fp32-grade): wg is [2][Ng][ntaps*Kc], the TF32 hi parts then
                                the lo parts (LF_PACK_TF32_HI / _LO), activations are split in shared memory */
+    int relu;               /* ReLU on conv + bias (eval-mode layers with the BatchNorm folded into wg / bias) */
 } LfConvTcgArgs;
 int lf_conv_tcg_supported(int N, int Hs, int Ws, int Kc, int Ng);
 int lf_conv_tcg(const LfConvTcgArgs* args, lf_stream_t stream);

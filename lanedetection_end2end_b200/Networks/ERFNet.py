@@ -11,7 +11,13 @@ import torch.nn as nn
 
 from ._pkg import submodule
 
+import os
+
 _ops = submodule("ops_net")
+_eval = submodule("ops_eval")
+# eval-mode inference with every BatchNorm folded into the convolution weights (ops_eval.py); LANEFIT_EVAL_FUSED=0 keeps
+# the unfused eval path (the training kernels with running statistics)
+EVAL_FUSED = os.environ.get("LANEFIT_EVAL_FUSED", "1") != "0"
 
 
 _PENDING_COUNTERS = None      # when a list: BatchNorm step counters to bump with ONE fused launch
@@ -77,6 +83,10 @@ class DownsamplerBlock(nn.Module):
             x = _ops.image_to_nhwc_pad(input, (self.ninput + 3) // 4 * 4)
         else:
             x = _ops.as_nhwc(input)
+        if not self.training and x.is_cuda and EVAL_FUSED and _eval.inference_only(x, self.conv.weight):
+            y = _eval.down(x, self)
+            if y is not None:
+                return _ops.as_nchw_view(y)
         y = _ops.DownFunction.apply(x, self.ninput, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias,
                                     self.bn.running_mean, self.bn.running_var, self.training, need_dx)
         _track(self.bn, self.training)
@@ -113,6 +123,10 @@ class non_bottleneck_1d(nn.Module):
 
     def forward(self, input):
         x = _ops.as_nhwc(input)
+        if not self.training and x.is_cuda and EVAL_FUSED and _eval.inference_only(x, self.conv3x1_1.weight):
+            y = _eval.nb1d(x, self)                  # BatchNorm folded into the weights: 4 conv launches, nothing else
+            if y is not None:
+                return _ops.as_nchw_view(y)
         y = _ops.Nb1dFunction.apply(
             x, self.conv3x1_1.weight, self.conv3x1_1.bias, self.conv1x3_1.weight, self.conv1x3_1.bias,
             self.bn1.weight, self.bn1.bias, self.conv3x1_2.weight, self.conv3x1_2.bias,
@@ -180,6 +194,10 @@ class UpsamplerBlock(nn.Module):
 
     def forward(self, input):
         x = _ops.as_nhwc(input)
+        if not self.training and x.is_cuda and EVAL_FUSED and _eval.inference_only(x, self.conv.weight):
+            y = _eval.up(x, self)
+            if y is not None:
+                return _ops.as_nchw_view(y)
         y = _ops.UpFunction.apply(x, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias,
                                   self.bn.running_mean, self.bn.running_var, self.training)
         _track(self.bn, self.training)

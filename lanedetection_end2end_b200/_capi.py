@@ -83,7 +83,7 @@ class LfTcgView(ctypes.Structure):
 class LfConvTcgArgs(ctypes.Structure):
     _fields_ = [("a", LfTcgView * 2), ("wg", _p), ("bias", _p), ("out", _p), ("osn", _ll), ("osy", _ll), ("osx", _ll),
                 ("oy_mul", _i), ("oy0", _i), ("N", _i), ("Hs", _i), ("Ws", _i), ("Kc", _i), ("Ng", _i), ("ntaps", _i),
-                ("map", _i * TCG_MAX_TAPS), ("dy", _i * TCG_MAX_TAPS), ("dx", _i * TCG_MAX_TAPS), ("precision", _i)]
+                ("map", _i * TCG_MAX_TAPS), ("dy", _i * TCG_MAX_TAPS), ("dx", _i * TCG_MAX_TAPS), ("precision", _i), ("relu", _i)]
 
 
 REDUCE_MAX_JOBS = 8
@@ -130,6 +130,7 @@ _NET_PROTOS = {
     "lf_colsum_blocks": (_i, [ctypes.c_longlong]),
     "lf_colsum": (_i, [_p, ctypes.c_longlong, _i, _i, _i, _p, _i, _p]),
     "lf_maxpool2_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "lf_maxpool2_affine_relu": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p]),
     "lf_maxpool2_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p]),
     "lf_bn_blocks": (_i, [ctypes.c_longlong, _i]),
     "lf_bn_stats": (_i, [_p, ctypes.c_longlong, _i, _p, _p]),

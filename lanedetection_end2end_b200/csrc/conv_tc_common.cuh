@@ -35,7 +35,7 @@ struct TcArgs {
     int dil;                // tap spacing d
     int tap_row[3];         // first slab row (128-byte rows) of the view used by weight slot t
     int tiles_a, tiles_b;
-    int relu;
+    int relu;               // bit 0: ReLU on conv + bias (before mask / add); bit 1: ReLU after the residual add
     int n_halves;
     int total_m_tiles;
     int stages, stage_bytes;
@@ -192,7 +192,7 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
                         const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n_half * TC_BN + 32 * h + c0 + 4 * q));
                         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                     }
-                    if (a.relu) {
+                    if (a.relu & 1) {
                         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                     }
                     *reinterpret_cast<float4*>(&stg_g[m * TC_STG_LD + c0 + 4 * q]) = o;
@@ -226,6 +226,9 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
                         ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
                     }
                     o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+                }
+                if (a.relu & 2) {   // ReLU AFTER the residual add: the closing relu(conv + x) of an eval-mode (BN-folded) block
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                 }
                 *reinterpret_cast<float4*>(a.out + off) = o;
                 csum[hh].x += o.x; csum[hh].y += o.y; csum[hh].z += o.z; csum[hh].w += o.w;

@@ -200,7 +200,7 @@ conv1d_tc_v1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n_half * TC_BN_V1 + c));
                         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                     }
-                    if (a.relu) {
+                    if (a.relu & 1) {
                         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                     }
                     if (a.mask_src) {
@@ -216,6 +216,9 @@ conv1d_tc_v1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             ad.z = mk.z > 0.f ? ad.z : 0.f; ad.w = mk.w > 0.f ? ad.w : 0.f;
                         }
                         o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+                    }
+                    if (a.relu & 2) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                     }
                     *reinterpret_cast<float4*>(a.out + off + c) = o;
                     csum[c] += o.x; csum[c + 1] += o.y; csum[c + 2] += o.z; csum[c + 3] += o.w;

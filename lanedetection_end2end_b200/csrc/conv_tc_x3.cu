@@ -46,13 +46,15 @@ __device__ __forceinline__ float x3_hw_tf32(float a) { return __uint_as_float(__
 __device__ __forceinline__ float x3_rna_tf32(float a) { return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ float x3_lo(float a) { return x3_rna_tf32(a - x3_hw_tf32(a)); }
 
-template <int C, bool AHEAD = false>
+template <int C, bool AHEAD = false, int EG = 2>
 struct X3Cfg {
     static constexpr int NCB = C / TC_KCH;          // 32-channel blocks = slabs per tile
     // Two epilogue groups (one 32-channel half each) for every shape: at C = 128 the tiles of a group complete in a burst
     // (block-major walk) and the next group needs their TMEM buffers back at once -- a single group (5k cycles per
     // tile) stalled the MMA issuer for ~9 us per launch (tools/x3_ablate.py, profiles/r02).
-    static constexpr int EPI_GROUPS = 2;
+    // EG = 1 (one group walks both halves, 18 KB less staging) only where two groups would leave fewer than two slab
+    // stages: the 48 KB slabs of the large dilations on 40 x 80 maps (320 x 640 inputs).
+    static constexpr int EPI_GROUPS = EG;
     static constexpr int SPLIT_WARPS = 2;
     static constexpr int EPI_T0 = 32 * (2 + SPLIT_WARPS);
     static constexpr int THREADS = EPI_T0 + 128 * EPI_GROUPS;
@@ -60,11 +62,11 @@ struct X3Cfg {
     static constexpr bool BLOCK_MAJOR = C > 64;     // walk order inside a group of X3_NBUF tiles
 };
 
-template <int C, bool AHEAD>
-__global__ void __launch_bounds__(X3Cfg<C, AHEAD>::THREADS, 1)
+template <int C, bool AHEAD, int EG>
+__global__ void __launch_bounds__(X3Cfg<C, AHEAD, EG>::THREADS, 1)
 conv1d_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     pdl_trigger();
-    using Cfg = X3Cfg<C, AHEAD>;
+    using Cfg = X3Cfg<C, AHEAD, EG>;
     constexpr int NCB = Cfg::NCB;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -319,13 +321,13 @@ conv1d_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------
 struct X3Plan {
     int vertical, dil, fwd_order;  // fwd_order: weight slot t reads offset (t-1)*d (1) or -(t-1)*d (0)
-    int TA, TB, tb_shift, tiles_a, tiles_b, stages, stage_bytes, smem_bytes, m_ctas;
+    int TA, TB, tb_shift, tiles_a, tiles_b, stages, stage_bytes, smem_bytes, m_ctas, epi_groups;
 };
 
 // Derive the plan from the public arguments; false = shape / tap pattern not served by this kernel.
 // Tile shapes: TA x TB = 128 pixels with TB a power of two such that the tap shift d*TB is a multiple of the 8-row
 // swizzle period; the slab with the fewest rows wins (tall tiles for the large dilations: halo 2d / TA).
-static bool x3_make_plan(int N, int H, int W, int C, const int* dy, const int* dx, int epi_groups, X3Plan* p) {
+static bool x3_make_plan(int N, int H, int W, int C, const int* dy, const int* dx, X3Plan* p) {
     if (!(C == 64 || C == 128) || N <= 0) return false;
     const bool vert = dy[0] != 0 || dy[2] != 0;
     const int* o = vert ? dy : dx;
@@ -351,8 +353,16 @@ static bool x3_make_plan(int N, int H, int W, int C, const int* dy, const int* d
     p->tiles_a = ext_a / p->TA;
     p->tiles_b = ext_b / p->TB;
     p->stage_bytes = best_rows * 128;
-    const int fixed = 1024 + X3_B_BYTES + epi_groups * TC_STG_BYTES + 512;  // alignment slack + weights + epilogue staging + barriers
+    // alignment slack + weights + epilogue staging + barriers; two epilogue groups unless that leaves a single stage
+    int epi_groups = 2;
+    int fixed = 1024 + X3_B_BYTES + epi_groups * TC_STG_BYTES + 512;
     int stages = (TC_SMEM_LIMIT - fixed) / p->stage_bytes;
+    if (stages < 2) {
+        epi_groups = 1;
+        fixed = 1024 + X3_B_BYTES + epi_groups * TC_STG_BYTES + 512;
+        stages = (TC_SMEM_LIMIT - fixed) / p->stage_bytes;
+    }
+    p->epi_groups = epi_groups;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return false;   // the lo MMAs of slab i are issued after the hi MMAs of slab i+1: two slabs in flight at least
     p->stages = stages;
@@ -368,12 +378,12 @@ static bool x3_make_plan(int N, int H, int W, int C, const int* dy, const int* d
     return tc_get_encode_fn() != nullptr;
 }
 
-template <int C, bool AHEAD>
+template <int C, bool AHEAD, int EG>
 static cudaError_t x3_launch(int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                              const TcArgs& a) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_x3_kernel<C, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_x3_kernel<C, AHEAD, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
-    lf_launch(conv1d_tc_x3_kernel<C, AHEAD>, grid, X3Cfg<C, AHEAD>::THREADS, smem_bytes, stream, tmA, tmB, a);
+    lf_launch(conv1d_tc_x3_kernel<C, AHEAD, EG>, grid, X3Cfg<C, AHEAD, EG>::THREADS, smem_bytes, stream, tmA, tmB, a);
     return cudaSuccess;
 }
 
@@ -386,7 +396,7 @@ extern "C" int lf_conv1d_tc_x3_rows(int N, int H, int W, int C, int vertical, in
     if (dil < 1) return 0;
     X3Plan pl;
     const int zero[3] = {0, 0, 0}, off[3] = {-dil, 0, dil};
-    if (!x3_make_plan(N, H, W, C, vertical ? off : zero, vertical ? zero : off, 2, &pl)) return 0;
+    if (!x3_make_plan(N, H, W, C, vertical ? off : zero, vertical ? zero : off, &pl)) return 0;
     return pl.m_ctas;
 }
 
@@ -401,9 +411,9 @@ extern "C" int lf_conv1d_tc_x3(const LfConvTcArgs* args, lf_stream_t stream_) {
     const LfConvTcArgs& p = *args;
     LF_REQUIRE(p.in && p.wpack && p.out);
     X3Plan pl;
-    if (!x3_make_plan(p.N, p.H, p.W, p.C, p.dy, p.dx, 2, &pl)) return LF_ERR_UNSUPPORTED;
-    // residual-add launches: operands one tile ahead
-    const bool ahead = p.add_src && !p.mask_src;
+    if (!x3_make_plan(p.N, p.H, p.W, p.C, p.dy, p.dx, &pl)) return LF_ERR_UNSUPPORTED;
+    // residual-add launches: operands one tile ahead (two epilogue groups only: one half per thread)
+    const bool ahead = p.add_src && !p.mask_src && pl.epi_groups == 2;
     TcEncodeTiledFn enc = tc_get_encode_fn();
     TcArgs a{};
     a.out = p.out; a.bias = p.bias; a.mask_src = p.mask_src; a.add_src = p.add_src; a.add_mask = p.add_mask;
@@ -449,10 +459,13 @@ extern "C" int lf_conv1d_tc_x3(const LfConvTcArgs* args, lf_stream_t stream_) {
     }
     const int grid = pl.m_ctas * a.n_halves;
     cudaError_t e;
-    if (p.C == 128 && ahead) e = x3_launch<128, true>(grid, pl.smem_bytes, stream, tmA, tmB, a);
-    else if (p.C == 128) e = x3_launch<128, false>(grid, pl.smem_bytes, stream, tmA, tmB, a);
-    else if (ahead) e = x3_launch<64, true>(grid, pl.smem_bytes, stream, tmA, tmB, a);
-    else e = x3_launch<64, false>(grid, pl.smem_bytes, stream, tmA, tmB, a);
+    if (pl.epi_groups == 1) {
+        e = p.C == 128 ? x3_launch<128, false, 1>(grid, pl.smem_bytes, stream, tmA, tmB, a)
+                       : x3_launch<64, false, 1>(grid, pl.smem_bytes, stream, tmA, tmB, a);
+    } else if (p.C == 128 && ahead) e = x3_launch<128, true, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a);
+    else if (p.C == 128) e = x3_launch<128, false, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a);
+    else if (ahead) e = x3_launch<64, true, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a);
+    else e = x3_launch<64, false, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a);
     if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
     return check_launch();
 }

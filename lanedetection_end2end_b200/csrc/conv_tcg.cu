@@ -42,6 +42,7 @@ struct TgArgs {
     const float* bias;
     long long osn, osy, osx;
     int oy_mul, oy0;
+    int relu;
     int N, Hs, Ws;
     int bx, by;
     int kchunks, Ng, ntaps;
@@ -252,6 +253,9 @@ conv_tcg_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + 4 * q));
                         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                     }
+                    if (a.relu) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
                     *reinterpret_cast<float4*>(orow + c0 + 4 * q) = o;
                 }
             }
@@ -312,7 +316,7 @@ extern "C" int lf_conv_tcg(const LfConvTcgArgs* args, lf_stream_t stream_) {
     TcEncodeTiledFn enc = tc_get_encode_fn();
     TgArgs a{};
     tg_pick_patch(p.Hs, p.Ws, &a.bx, &a.by);
-    a.out = p.out; a.bias = p.bias;
+    a.out = p.out; a.bias = p.bias; a.relu = p.relu;
     a.osn = p.osn; a.osy = p.osy; a.osx = p.osx; a.oy_mul = p.oy_mul; a.oy0 = p.oy0;
     a.N = p.N; a.Hs = p.Hs; a.Ws = p.Ws;
     a.kchunks = p.Kc / 32; a.Ng = p.Ng; a.ntaps = p.ntaps;

@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 // 2x2 stride-2 max pooling into a channel slice, and its gradient.
 // ------------------------------------------------------------------------------------------
 __global__ void maxpool2_fwd_kernel(const float* __restrict__ in, int N, int Hin, int Win, int C, int in_cstride,
-                                    float* __restrict__ out, int out_cstride, int out_coff) {
+                                    float* __restrict__ out, int out_cstride, int out_coff, const float* __restrict__ scale,
+                                    const float* __restrict__ shift) {
     pdl_entry();
     const int Ho = Hin >> 1, Wo = Win >> 1;
     const long long total = (long long)N * Ho * Wo * C;
@@ -253,7 +254,9 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ in, int N, int Hin
         const int n = (int)(p / Ho);
         const float* b = in + ((size_t)(n * Hin + 2 * oy) * Win + 2 * ox) * in_cstride + c;
         const float v00 = b[0], v01 = b[in_cstride], v10 = b[(size_t)Win * in_cstride], v11 = b[(size_t)(Win + 1) * in_cstride];
-        out[((size_t)(n * Ho + oy) * Wo + ox) * out_cstride + out_coff + c] = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
+        float m = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
+        if (scale) m = fmaxf(fmaf(m, __ldg(scale + out_coff + c), __ldg(shift + out_coff + c)), 0.f);   // eval: relu(bn(pool))
+        out[((size_t)(n * Ho + oy) * Wo + ox) * out_cstride + out_coff + c] = m;
     }
 }
 
@@ -580,7 +583,20 @@ extern "C" int lf_maxpool2_fwd(const float* in, int N, int Hin, int Win, int C, 
     STREAM;
     LF_REQUIRE(in && out && N > 0 && Hin > 1 && Win > 1 && C > 0 && Hin % 2 == 0 && Win % 2 == 0);
     const long long total = (long long)N * (Hin / 2) * (Win / 2) * C;
-    lf_launch(maxpool2_fwd_kernel, grid_for(total, 256), 256, 0, stream, in, N, Hin, Win, C, in_cstride, out, out_cstride, out_coff);
+    lf_launch(maxpool2_fwd_kernel, grid_for(total, 256), 256, 0, stream, in, N, Hin, Win, C, in_cstride, out, out_cstride, out_coff,
+              (const float*)nullptr, (const float*)nullptr);
+    return check_launch();
+}
+
+// eval-mode DownsamplerBlock: the pooled half of relu(bn(cat[conv, pool])) with the BatchNorm as a per-channel affine
+// (scale / shift indexed by the OUTPUT channel out_coff + c), so no BatchNorm pass over the concatenated tensor is needed
+extern "C" int lf_maxpool2_affine_relu(const float* in, int N, int Hin, int Win, int C, int in_cstride, const float* scale,
+                                       const float* shift, float* out, int out_cstride, int out_coff, lf_stream_t stream_) {
+    STREAM;
+    LF_REQUIRE(in && out && scale && shift && N > 0 && Hin > 1 && Win > 1 && C > 0 && Hin % 2 == 0 && Win % 2 == 0);
+    const long long total = (long long)N * (Hin / 2) * (Win / 2) * C;
+    lf_launch(maxpool2_fwd_kernel, grid_for(total, 256), 256, 0, stream, in, N, Hin, Win, C, in_cstride, out, out_cstride, out_coff,
+              scale, shift);
     return check_launch();
 }
 

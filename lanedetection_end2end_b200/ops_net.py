@@ -170,7 +170,7 @@ def tcg_s2conv_ok(x, C, O):
             and int(_lib().lf_conv_tcg_supported(N, H // 2, W // 2, 2 * C, plans.pad_to(O, 16))) > 0)
 
 
-def run_tcg_s2conv(x, wg, O, out, bias=None):
+def run_tcg_s2conv(x, wg, O, out, bias=None, relu=False):
     """out[n,i,j,:O] = bias + conv3x3/s2/p1(x) with wg = pack_tcg_s2conv(w); x dense [N,H,W,C]; out [N,H/2,W/2,Co_total]
     (the first pad16(O) channels are written: the caller overwrites / ignores any padding columns)."""
     N, H, W, C = x.shape
@@ -182,6 +182,7 @@ def run_tcg_s2conv(x, wg, O, out, bias=None):
     a.osn, a.osy, a.osx, a.oy_mul, a.oy0 = Ho * Wo * cot, Wo * cot, cot, 1, 0
     a.N, a.Hs, a.Ws, a.Kc, a.Ng, a.ntaps = N, Ho, Wo, 2 * C, wg.shape[-2], 6
     a.precision = int(wg.dim() == 3)       # [2, Ng, K]: the TF32 hi / lo pair of the 3xTF32 mode
+    a.relu = int(relu)
     for t, (m, dy, dx) in enumerate(TCG_S2CONV_TAPS):
         a.map[t], a.dy[t], a.dx[t] = m, dy, dx
     _capi.call("lf_conv_tcg", ctypes.byref(a), _stream(), flops=2 * N * Ho * Wo * 9 * C * O, nbytes=4 * N * (H * W * C + Ho * Wo * O))
@@ -196,7 +197,7 @@ def tcg_s2convT_ok(x, I, O):
             and int(_lib().lf_conv_tcg_supported(N, H, W, kc, 2 * O)) > 0)
 
 
-def run_tcg_s2convT(x, I, wgs, O, out, bias2=None):
+def run_tcg_s2convT(x, I, wgs, O, out, bias2=None, relu=False):
     """out [N,2H,2W,O] = bias + convT3x3/s2/p1/op1(x[..., :I]); wgs = (pack_tcg_s2convT(w,0,kc), pack_tcg_s2convT(w,1,kc));
     bias2 = bias tiled twice (pair pixel)."""
     N, H, W, cx = x.shape
@@ -209,6 +210,7 @@ def run_tcg_s2convT(x, I, wgs, O, out, bias2=None):
         a.osn, a.osy, a.osx, a.oy_mul, a.oy0 = 4 * H * W * O, 2 * W * O, 2 * O, 2, par
         a.N, a.Hs, a.Ws, a.Kc, a.Ng, a.ntaps = N, H, W, kc, 2 * O, len(taps)
         a.precision = int(wgs[par].dim() == 3)
+        a.relu = int(relu)
         for t, (dy, dx, _ky) in enumerate(taps):
             a.map[t], a.dy[t], a.dx[t] = 0, dy, dx
         _capi.call("lf_conv_tcg", ctypes.byref(a), _stream(), flops=2 * N * H * W * len(taps) * I * 2 * O,
@@ -618,16 +620,17 @@ def flush_deferred_reductions(jobs):
         _capi.call("lf_reduce_multi", arr, len(chunk), _stream())
 
 
-def _super_conv_launch(taps, xs, w, vertical, transposed, out, N, H, W, C, cs, epi_s):
-    run_conv_tc(taps, xs, packed(w, "tc_super_%d%d" % (vertical, transposed), lambda t: pack_tc_super(t, vertical, transposed),
-                                 split=x3_mode()),
-                out.view(N, H, W // SUPER, SUPER * C), colsum=cs, **epi_s)
+def _super_conv_launch(taps, xs, w, vertical, transposed, out, N, H, W, C, cs, epi_s, wp=None):
+    if wp is None:
+        wp = packed(w, "tc_super_%d%d" % (vertical, transposed), lambda t: pack_tc_super(t, vertical, transposed), split=x3_mode())
+    run_conv_tc(taps, xs, wp, out.view(N, H, W // SUPER, SUPER * C), colsum=cs, **epi_s)
 
 
-def conv3(x, w, vertical, dil, transposed, colsum=None, **epi):
+def conv3(x, w, vertical, dil, transposed, colsum=None, wp=None, **epi):
     """One factorised 3-tap convolution of non_bottleneck_1d (or its input gradient when
     ``transposed``): dispatches to the tcgen05 kernel in tf32 mode, else to the fp32 kernel.
-    ``colsum`` ([C] tensor): also produce the per-channel sums of the result."""
+    ``colsum`` ([C] tensor): also produce the per-channel sums of the result.
+    ``wp``: the already packed tensor-core operand (ops_eval's BatchNorm-folded weights) -- tensor-core routes only."""
     N, H, W, C = x.shape
     out = torch.empty_like(x)
     if super_ok(x, dil):
@@ -641,7 +644,7 @@ def conv3(x, w, vertical, dil, transposed, colsum=None, **epi):
         global _DEFERRED
         saved, _DEFERRED = _DEFERRED, None     # the column sums are post-processed right below: reduce them now
         try:
-            _super_conv_launch(taps, xs, w, vertical, transposed, out, N, H, W, C, cs, epi_s)
+            _super_conv_launch(taps, xs, w, vertical, transposed, out, N, H, W, C, cs, epi_s, wp=wp)
         finally:
             _DEFERRED = saved
         if colsum is not None:
@@ -650,9 +653,12 @@ def conv3(x, w, vertical, dil, transposed, colsum=None, **epi):
     if tc_supported(x, vertical, dil):
         sgn = -1 if transposed else 1
         taps = [((sgn * (k - 1) * dil, 0) if vertical else (0, sgn * (k - 1) * dil)) for k in range(3)]
-        wp = (packed(w, "tc_dgrad", pack_tc_dgrad, split=x3_mode()) if transposed
-              else packed(w, "tc_fwd", pack_tc_fwd, split=x3_mode()))
+        if wp is None:
+            wp = (packed(w, "tc_dgrad", pack_tc_dgrad, split=x3_mode()) if transposed
+                  else packed(w, "tc_fwd", pack_tc_fwd, split=x3_mode()))
         return run_conv_tc(taps, x, wp, out, colsum=colsum, **epi)
+    if wp is not None:
+        raise _capi.LanefitError("conv3: a pre-packed operand needs a tensor-core route")
     kh, kw = (3, 1) if vertical else (1, 3)
     ph, pw = (dil, 0) if vertical else (0, dil)
     dh, dw = (dil, 1) if vertical else (1, dil)

@@ -385,13 +385,14 @@ def test_x3_forward_generic_operands_fp32_accuracy(N, C, H, W, vertical, dil):
     assert e_x3 <= 2 * e_f32 + 5e-7, (e_x3, e_f32)
 
 
-@pytest.mark.parametrize("C,H,W,dil", [(64, 16, 128, 1), (128, 32, 64, 8), (128, 32, 64, 16)])
-def test_x3_epilogues_and_dgrad(C, H, W, dil):
+@pytest.mark.parametrize("C,H,W,dil,vertical", [(64, 16, 128, 1, False), (128, 32, 64, 8, False), (128, 32, 64, 16, False),
+                                                (128, 32, 64, 16, True), (128, 32, 64, 8, True), (128, 40, 80, 8, True)])
+def test_x3_epilogues_and_dgrad(C, H, W, dil, vertical):
     o = ops()
     g = torch.Generator().manual_seed(7)
     N = 3
     x = torch.randn(N, H, W, C, generator=g).cuda()
-    w = (torch.randn(C, C, 1, 3, generator=g) / (3 * C) ** 0.5).cuda()
+    w = (torch.randn(C, C, *((3, 1) if vertical else (1, 3)), generator=g) / (3 * C) ** 0.5).cuda()
     b = torch.randn(C, generator=g).cuda()
     mask = torch.randn(N, H, W, C, generator=g).cuda()
     add = torch.randn(N, H, W, C, generator=g).cuda()
@@ -400,9 +401,9 @@ def test_x3_epilogues_and_dgrad(C, H, W, dil):
     for mode in ("fp32", "tf32x3"):
         o.set_conv_mode(mode)
         cs = torch.empty(C, device="cuda")
-        outs[mode] = (o.conv3(x, w, False, dil, False, bias=b, relu=True),
-                      o.conv3(x, w, False, dil, True, mask_src=mask, colsum=cs),
-                      o.conv3(x, w, False, dil, True, add_src=add, add_mask=addm), cs)
+        outs[mode] = (o.conv3(x, w, vertical, dil, False, bias=b, relu=True),
+                      o.conv3(x, w, vertical, dil, True, mask_src=mask, colsum=cs),
+                      o.conv3(x, w, vertical, dil, True, add_src=add, add_mask=addm), cs)
         torch.cuda.synchronize()
     for a, r in zip(outs["tf32x3"][:3], outs["fp32"][:3]):
         assert float((a - r).abs().max()) <= 3e-6 * float(r.abs().max())
@@ -443,7 +444,8 @@ def test_x3_block_level_matches_fp32_mode():
 
 
 @pytest.mark.parametrize("N,C,H,W,vertical,dil", [(2, 64, 16, 128, True, 1), (3, 64, 64, 128, False, 1), (3, 128, 32, 64, True, 2),
-                                                  (2, 128, 32, 64, False, 16), (1, 128, 40, 80, True, 8), (32, 128, 32, 64, False, 4)])
+                                                  (2, 128, 32, 64, False, 16), (1, 128, 40, 80, True, 8), (32, 128, 32, 64, False, 4),
+                                                  (3, 128, 32, 64, True, 16), (3, 128, 32, 64, True, 8)])
 def test_x3_weight_gradient_generic_operands(N, C, H, W, vertical, dil):
     """lf_wgrad3_tc_x3 on generic fp32 operands vs torch fp64: as accurate as the fp32 split-K kernel."""
     o = ops()

@@ -234,6 +234,66 @@ def test_eval_mode_forward_and_early_return():
     assert int(model.net.encoder.initial_block.bn.num_batches_tracked) == 0
 
 
+def test_eval_fused_matches_unfused_and_launches_convs_only():
+    """Eval-mode inference with the BatchNorms folded into the weights (ops_eval.py) against the unfused
+    eval path (training kernels + running statistics): same maps / beta to fp32 rounding, and a quarter fewer launches
+    (no lf_bn_* launch inside the tensor-core blocks)."""
+    from lanedetection_end2end_b200 import _capi
+    from lanedetection_end2end_b200.Networks import ERFNet
+    model, args = _build_net(4, 3, 0.2, 2)
+    sd = model.state_dict()
+    for k, v in inputs.make_erfnet_params(3, 4, seed=11).items():
+        sd[k] = torch.from_numpy(v)
+    rng = np.random.default_rng(1)
+    for k in sd:
+        if k.endswith("running_mean"):
+            sd[k] = torch.from_numpy(rng.standard_normal(sd[k].shape).astype(np.float32) * 0.1)
+        if k.endswith("running_var"):
+            sd[k] = torch.from_numpy((0.5 + rng.random(sd[k].shape)).astype(np.float32))
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    x = torch.from_numpy(inputs.make_images(2, 256, 512, seed=9)).cuda()
+    res, launches = {}, {}
+    try:
+        for fused in (False, True):
+            ERFNet.EVAL_FUSED = fused
+            with torch.no_grad():
+                model(x, torch.zeros(2, 4), True)                      # first call builds / caches the folded operands
+                l0 = _capi.LAUNCHES
+                _capi.TRACE = []
+                res[fused] = model(x, torch.zeros(2, 4), True)
+                names = [t[0] for t in _capi.TRACE]
+                _capi.TRACE = None
+                launches[fused] = (_capi.LAUNCHES - l0, names)
+    finally:
+        ERFNet.EVAL_FUSED = True
+        _capi.TRACE = None
+    a, b = res[False], res[True]
+    assert rel(b[5], a[5]) <= 2e-5 and rel(b[8], a[8]) <= 2e-5                    # decoder maps, encoder output
+    for l in range(4):
+        assert rel(b[l], a[l]) <= 1e-4
+    n_unfused, n_fused = launches[False][0], launches[True][0]
+    if conv_mode_is_tc():          # the fp32 FFMA mode keeps the unfused eval path
+        assert n_fused <= 0.8 * n_unfused, (n_fused, n_unfused)
+        # only the stem (3 -> 13 channels: not a tensor-core shape) still runs its BatchNorm as separate launches
+        assert sum(n.startswith("lf_bn_") for n in launches[True][1]) <= 3, launches[True][1]
+    # folded operands follow in-place parameter updates (cache keyed on tensor versions)
+    with torch.no_grad():
+        model.net.encoder.layers[1].bn2.weight.mul_(1.5)
+        c = model(x, torch.zeros(2, 4), True)
+        ERFNet.EVAL_FUSED = False
+        try:
+            d = model(x, torch.zeros(2, 4), True)
+        finally:
+            ERFNet.EVAL_FUSED = True
+    assert rel(c[5], d[5]) <= 2e-5 and rel(c[5], a[5]) > 1e-3
+
+
+def conv_mode_is_tc():
+    from lanedetection_end2end_b200 import ops_net
+    return ops_net.tc_mode()
+
+
 def test_error_conventions():
     """order > 3 -> NotImplementedError, unknown activation -> NotImplementedError, unknown model -> KeyError
     (BP/Networks/LSQ_layer.py:44,105-107; BP/Networks/__init__.py:16-17); CPU tensors are refused."""

@@ -5,6 +5,7 @@ set -x
 mkdir -p gpurun_out/r02
 O=gpurun_out/r02
 timeout 900 python -m pytest tests -m gpu -q --maxfail=20 > $O/pytest_gpu_s8.log 2>&1; tail -8 $O/pytest_gpu_s8.log
+timeout 300 python tools/r02/diag_block.py > $O/diag_block_s8.jsonl 2> $O/diag_block_s8.err; tail -3 $O/diag_block_s8.err
 timeout 300 python __graft_entry__.py --smoke > $O/smoke_s8.log 2>&1; tail -4 $O/smoke_s8.log
 timeout 400 python bench.py --steps 10 --warmup 3 --no-parity-arm --no-cpu-baseline > $O/bench_s8_pdl1.json 2> $O/bench_s8_pdl1.err; head -c 250 $O/bench_s8_pdl1.json; tail -3 $O/bench_s8_pdl1.err
 cp gpurun_out/kernel_table_tf32x3_n1.json $O/kernel_table_s8_pdl1.json
