@@ -61,8 +61,9 @@ typedef struct CUstream_st* lf_stream_t; /* == cudaStream_t */
 #define LF_MAX_ORDER 4
 
 int lf_version(void);
-/* Programmatic dependent launch of the library's kernels (default on; LANEFIT_PDL=0 disables): each kernel may be
- * scheduled while its predecessor in the stream drains and waits (griddepcontrol.wait) before touching global memory. */
+/* Programmatic dependent launch of the library's kernels (default off; LANEFIT_PDL=1 or lf_set_pdl(1) enables): each kernel
+ * may then be scheduled while its predecessor in the stream drains, and waits (griddepcontrol.wait) before touching global
+ * memory.  Measured neutral on the graph-replayed training step. */
 void lf_set_pdl(int on);
 int lf_get_pdl(void);
 const char* lf_error_string(int code);
@@ -409,6 +410,18 @@ int lf_linear_fwd(const float* x, const float* W, const float* bias, int B, int 
 int lf_linear_bwd_data(const float* dy, const float* relu_out, const float* W, int B, int K, int O, float* dx, lf_stream_t stream);
 int lf_linear_bwd_weight(const float* dy, const float* relu_out, const float* x, int B, int K, int O, float* dW, float* db,
                          lf_stream_t stream);
+
+/* Segmentation-pretraining branch (csrc/seg.cu).  lf_seg_lane_maps replaces BP/Networks/LSQ_layer.py:279-293,301:
+ * out [B][C][H][W] class planes (C = nl + 1) -> maps [B][nl][H][W], maps[b][k] = (argmax == k+1) ? k+1 : 0, rows < mask_rows
+ * zeroed.  lf_ce2d_fwd / _bwd replace nn.CrossEntropyLoss(weight) on the planar logits (BP/Loss_crit.py:64-65,
+ * BP/main.py:258,307): target [B][H][W] int64, weight [C] or NULL; partial = 2*lf_ce2d_blocks() doubles of scratch, sums = 2
+ * doubles (weighted loss sum, weight sum) kept for the backward, loss = 1 double; dx = gout * dloss/dx (gout NULL = 1). */
+int lf_seg_lane_maps(const float* out, int B, int C, int H, int W, int nl, int mask_rows, float* maps, lf_stream_t stream);
+int lf_ce2d_blocks(int B, int H, int W);
+int lf_ce2d_fwd(const float* x, const long long* target, const float* weight, int B, int C, int H, int W, double* partial, double* sums,
+                double* loss, lf_stream_t stream);
+int lf_ce2d_bwd(const float* x, const long long* target, const float* weight, int B, int C, int H, int W, const double* sums,
+                const double* gout, float* dx, lf_stream_t stream);
 
 /* Loader image path on the GPU (csrc/input_pipe.cu; replaces BP/Dataloader/Load_Data_new.py:127-131,166-167,178-181):
  * frames uint8 [N][Hin][Win][3] (decoded RGB) -> rows [crop_y0, crop_y0+crop_rows) -> PIL-BILINEAR resize to [Ho][Wo]

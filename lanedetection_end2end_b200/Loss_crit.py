@@ -13,8 +13,10 @@ import torch.nn as nn
 
 if __package__:                        # imported as lanedetection_end2end_b200.Loss_crit
     from .Networks.utils import get_homography
+    from . import _capi
 else:                                  # imported as top-level `Loss_crit` by the reference's main.py
     from Networks.utils import get_homography
+    import _capi
 
 
 def define_loss_crit(options):
@@ -32,7 +34,53 @@ def define_loss_crit(options):
     weights = torch.Tensor([1] + [options.weight_seg] * options.nclasses)
     if not getattr(options, "no_cuda", False) and torch.cuda.is_available():
         weights = weights.cuda()       # the reference moves them unconditionally (:64); honour --no_cuda on a GPU box
-    return loss_crit, nn.CrossEntropyLoss(weights)
+    return loss_crit, CrossEntropyLoss2d(weights)
+
+
+class _CE2dFunction(torch.autograd.Function):
+    """Weighted pixel-wise cross entropy on planar [B,C,H,W] logits: lf_ce2d_fwd / lf_ce2d_bwd (csrc/seg.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, target, weight):
+        _capi.require_cuda(x, target)
+        x = x.contiguous().float()
+        target = target.contiguous()
+        B, C, H, W = x.shape
+        h = _capi.lib()
+        scratch = torch.empty(2 * int(h.lf_ce2d_blocks(B, H, W)) + 3, dtype=torch.float64, device=x.device)
+        sums, loss = scratch[-3:-1], scratch[-1:]
+        _capi.call("lf_ce2d_fwd", _capi.ptr(x), _capi.ptr(target), _capi.ptr(weight), B, C, H, W, _capi.ptr(scratch), _capi.ptr(sums),
+                   _capi.ptr(loss), _capi.stream_ptr(), nbytes=4 * x.numel() + 8 * target.numel())
+        ctx.save_for_backward(x, target, weight if weight is not None else x.new_empty(0), sums)
+        ctx.has_weight = weight is not None
+        return loss.reshape(()).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, target, weight, sums = ctx.saved_tensors
+        B, C, H, W = x.shape
+        dx = torch.empty_like(x)
+        _capi.call("lf_ce2d_bwd", _capi.ptr(x), _capi.ptr(target), _capi.ptr(weight if ctx.has_weight else None), B, C, H, W,
+                   _capi.ptr(sums), _capi.ptr(g.double().contiguous()), _capi.ptr(dx), _capi.stream_ptr(), nbytes=8 * x.numel())
+        return dx, None, None
+
+
+class CrossEntropyLoss2d(nn.Module):
+    """The segmentation criterion `define_loss_crit` returns (nn.CrossEntropyLoss(weights) in the reference,
+    BP/Loss_crit.py:64-65; used at BP/main.py:258,307 on the decoder's [B, L+1, H, W] logits and the [B, H, W] label map):
+    same value and gradient, one fused kernel each way on CUDA tensors (no log-softmax / nll intermediates)."""
+
+    def __init__(self, weight=None):
+        super().__init__()
+        self.register_buffer("weight", weight)
+
+    def forward(self, output, target):
+        if target.dim() == 4:                       # the loader hands [B,1,H,W] (main.py squeezes it)
+            target = target[:, 0]
+        w = self.weight
+        if w is not None and w.device != output.device:
+            w = self.weight = w.to(output.device)
+        return _CE2dFunction.apply(output, target.long(), None if w is None else w.float().contiguous())
 
 
 def _design(y, order):

@@ -231,10 +231,13 @@ class Net(nn.Module):
         if not end_to_end:
             # segmentation pre-training branch (:279-293): argmax -> per-lane label maps,
             # detached; fitted without gradient
-            labels = torch.max(output.detach(), 1)[1].float()
             nl = 2 if self.nclasses < 3 else 4
-            activated = torch.stack([labels * (labels == (k + 1)).float() for k in range(nl)], 1)
-            masked = activated.index_fill(2, self.idx_row.to(output.device), 0)
+            _capi.require_cuda(output)
+            # argmax + per-lane label maps + row mask in one launch (csrc/seg.cu: lf_seg_lane_maps)
+            od = output.detach().contiguous().float()
+            masked = torch.empty(od.shape[0], nl, od.shape[2], od.shape[3], dtype=torch.float32, device=od.device)
+            _capi.call("lf_seg_lane_maps", _capi.ptr(od), od.shape[0], od.shape[1], od.shape[2], od.shape[3], nl,
+                       self.zero_rows, _capi.ptr(masked), _capi.stream_ptr())
             if gt_line.sum() != 0:                                       # :308-311
                 gt_mask = gt_line[:, :, None, None].bool().expand_as(masked).to(masked.device)
                 masked[gt_mask] = masked[0, 0].unsqueeze(0).repeat(int(gt_line.sum().item()), 1, 1).view(-1)

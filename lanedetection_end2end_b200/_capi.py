@@ -151,6 +151,10 @@ _NET_PROTOS = {
     "lf_pack_gather": (_i, [_p, _i, _i, _p]),
     "lf_backproj_loss": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "lf_backproj_loss_host": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "lf_seg_lane_maps": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "lf_ce2d_blocks": (_i, [_i, _i, _i]),
+    "lf_ce2d_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "lf_ce2d_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "lf_frame_preprocess": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i, _i, _i, _p, _i, _p, _p]),
     "lf_linear_chunks": (_i, [_i]),
     "lf_rowmean_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p]),

@@ -6,11 +6,11 @@
 namespace lf {
 static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
-static int g_pdl = -1;   // -1: not decided yet (LANEFIT_PDL, default on)
+static int g_pdl = -1;   // -1: not decided yet (LANEFIT_PDL=1 turns it on; default off, see lf_common.cuh)
 bool pdl_enabled() {
     if (g_pdl < 0) {
         const char* e = getenv("LANEFIT_PDL");
-        g_pdl = (e && e[0] == '0') ? 0 : 1;
+        g_pdl = (e && e[0] == '1') ? 1 : 0;
     }
     return g_pdl != 0;
 }

@@ -53,10 +53,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // tile i lives in TMEM accumulator buffer i % NBUF (BUF_COLS columns apart).  X3: the buffer holds the large term in
 // columns [0,64) and the sum of the two small correction terms in [64,128); the result is small + large.
 // Group g of 4 warps (one warp per TMEM lane quadrant) walks HALVES 32-channel halves of every tile:
-//  (1) tcgen05.ld 32x32b (thread = pixel row) + bias + ReLU, staged into a padded shared-memory half-tile (18 KB);
+//  (1) tcgen05.ld 32x32b (thread = pixel row), staged into a padded shared-memory half-tile (18 KB);
 //  (2) the half-tile is walked row-major so that 8 consecutive threads cover one pixel's 32 channels (one 128-byte
-//      line): ReLU-backward mask, residual-gradient add, column sums / sums of squares (bias gradient, BatchNorm
-//      statistics) and the output stores are fully coalesced 128-bit accesses.
+//      line): bias (this thread's four columns, held in registers for the whole kernel -- loading it per tile in (1) was
+//      the top stall line of the round-2 ncu source view), ReLU, ReLU-backward mask, residual-gradient add, column sums /
+//      sums of squares (bias gradient, BatchNorm statistics) and the output stores are fully coalesced 128-bit accesses.
 // The mask / residual operands of a tile are prefetched into registers BEFORE waiting for its accumulator (AHEAD: one
 // whole tile ahead), so their latency hides behind the MMAs.
 template <int EPI_GROUPS, bool AHEAD, int EPI_T0, int NBUF, int BUF_COLS, bool X3>
@@ -78,10 +79,12 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
     const bool pre_add = (a.add_src != nullptr) && !pre_mask;  // both given: add_src is read in the loop
     float4 csum[NH], csq[NH];               // running column sums / sums of squares, per channel half
     float4 msc[NH], msh[NH];                // BatchNorm scale / shift of this thread's columns (mask_scale mode)
+    float4 bsv[NH];                         // bias of this thread's (fixed) phase-2 columns: loaded once, not per tile
     const bool affine_mask = a.mask_scale != nullptr;
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh) {
-        csum[hh] = csq[hh] = msc[hh] = msh[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+        csum[hh] = csq[hh] = msc[hh] = msh[hh] = bsv[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias) bsv[hh] = __ldg(reinterpret_cast<const float4*>(a.bias + n_half * TC_BN + 32 * (h_first + hh) + 4 * c4));
         if (affine_mask) {
             msc[hh] = __ldg(reinterpret_cast<const float4*>(a.mask_scale + n_half * TC_BN + 32 * (h_first + hh) + 4 * c4));
             msh[hh] = __ldg(reinterpret_cast<const float4*>(a.mask_shift + n_half * TC_BN + 32 * (h_first + hh) + 4 * c4));
@@ -185,18 +188,10 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
                     tmem_ld_wait();
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                           __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                    if (a.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n_half * TC_BN + 32 * h + c0 + 4 * q));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
-                    if (a.relu & 1) {
-                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                    }
-                    *reinterpret_cast<float4*>(&stg_g[m * TC_STG_LD + c0 + 4 * q]) = o;
-                }
+                for (int q = 0; q < 4; ++q)   // raw accumulator values: bias / ReLU are applied in phase 2 (bias in registers)
+                    *reinterpret_cast<float4*>(&stg_g[m * TC_STG_LD + c0 + 4 * q]) =
+                        make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                    __uint_as_float(v[4 * q + 3]));
             }
             if (hh == NH - 1) tc_fence_before();
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // staging complete (this group only)
@@ -207,6 +202,10 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
                 const int r = r0 + 16 * j;
                 const size_t off = roff[j] + 32 * hh;
                 float4 o = *reinterpret_cast<const float4*>(&stg_g[r * TC_STG_LD + 4 * c4]);
+                o.x += bsv[hh].x; o.y += bsv[hh].y; o.z += bsv[hh].z; o.w += bsv[hh].w;
+                if (a.relu & 1) {
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
                 if (pre_mask) {
                     float4 mk = pre[hh][j];
                     if (affine_mask) {   // the same fma the forward BatchNorm-apply performed before its ReLU: bit-identical mask

@@ -404,8 +404,12 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     __shared__ float4 red[256];
     const int Cq4 = (Cq + 3) >> 2;
     const int total4 = ntaps * Cp * Cq4;
-    const int o = blockIdx.x * (256 / WR_LANES) + (threadIdx.x / WR_LANES);
-    const int lane = threadIdx.x % WR_LANES;
+    // thread = (output float4 `o`, split lane): a WARP covers 32 consecutive outputs of one split lane, so each load
+    // instruction reads 512 contiguous bytes of one partial (the previous (o, lane) = (tid / 8, tid % 8) mapping read eight
+    // 64-byte pieces 100s of KB apart: 36 % of the DRAM roof in the round-2 ncu capture); same per-lane k sequence and
+    // the same lane-ordered combine, so the result is bit-identical
+    const int o = blockIdx.x * (256 / WR_LANES) + (threadIdx.x & 31);
+    const int lane = threadIdx.x >> 5;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cq = 0, cp = 0, t = 0;
     if (o < total4) {
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
         float4 s4 = red[threadIdx.x];
 #pragma unroll
         for (int l = 1; l < WR_LANES; ++l) {
-            const float4 v = red[threadIdx.x + l];
+            const float4 v = red[threadIdx.x + 32 * l];
             s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
         }
         const float vals[4] = {s4.x, s4.y, s4.z, s4.w};
@@ -455,8 +459,8 @@ __global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceJobs js) 
     const int Cq4 = (j.Cq + 3) >> 2;
     const int total4 = j.ntaps * j.Cp * Cq4;
     if ((int)(blockIdx.x * (256 / WR_LANES)) >= total4) return;   // whole block beyond this job (uniform)
-    const int o = blockIdx.x * (256 / WR_LANES) + (threadIdx.x / WR_LANES);
-    const int lane = threadIdx.x % WR_LANES;
+    const int o = blockIdx.x * (256 / WR_LANES) + (threadIdx.x & 31);   // warp = 32 consecutive outputs of one split lane
+    const int lane = threadIdx.x >> 5;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cq = 0, cp = 0, t = 0;
     if (o < total4) {
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceJobs js) 
         float4 s4 = red[threadIdx.x];
 #pragma unroll
         for (int l = 1; l < WR_LANES; ++l) {
-            const float4 v = red[threadIdx.x + l];
+            const float4 v = red[threadIdx.x + 32 * l];
             s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
         }
         const float vals[4] = {s4.x, s4.y, s4.z, s4.w};

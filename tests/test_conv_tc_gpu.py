@@ -436,11 +436,15 @@ def test_x3_block_level_matches_fp32_mode():
         # fp32 round-off level and the share of entries beyond it.  The arithmetic of every kernel is gated entry by
         # entry in the operand-level tests above and below.
         assert float((res["tf32x3"][0] - res["fp32"][0]).abs().max()) <= 2e-5 * float(res["fp32"][0].abs().max())
+        npix = 2 * H * W
         for a, r in zip(res["tf32x3"][1:], res["fp32"][1:]):
             sc = max(float(r.abs().max()), 1e-6)
             d = (a - r).abs().flatten()
-            assert float(d.median()) <= 1e-5 * sc, (C, float(d.median()), sc)   # BN statistics couple every entry to the flips
-            assert float((d > 1e-4 * sc).float().mean()) <= 0.05, (C, float((d > 1e-4 * sc).float().mean()))
+            # the BatchNorm statistics couple EVERY entry behind them to a flip: one flipped bit moves the batch sums by one
+            # entry out of `npix`, i.e. all those gradients by ~1/npix of their scale (measured 1.3e-4 at npix = 4096 with one
+            # flip, session 7); allow three
+            assert float(d.median()) <= (1e-5 + 3.0 / npix) * sc, (C, float(d.median()), sc)
+            assert float((d > (1e-4 + 3.0 / npix) * sc).float().mean()) <= 0.05, (C, float((d > 1e-4 * sc).float().mean()))
 
 
 @pytest.mark.parametrize("N,C,H,W,vertical,dil", [(2, 64, 16, 128, True, 1), (3, 64, 64, 128, False, 1), (3, 128, 32, 64, True, 2),

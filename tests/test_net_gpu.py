@@ -81,24 +81,34 @@ def run_block(block, x_nchw, gy_seed=0):
 
 
 def check_grads(block, oracle_P, prefix, tol=TOL, flips=0):
-    """Per-parameter norm-wise gate.  Biases of convs that feed a BatchNorm have an analytically zero
-    gradient (the BN removes the mean): both sides are pure round-off there, so those are gated against
-    the block's overall gradient scale instead of their own.
-    flips > 0 (rel_up_to_relu_flips found ReLU-mask flips against the fp64 oracle in this run): a flipped mask bit
-    perturbs the handful of gradient pixels behind it by O(1), i.e. every weight-gradient entry by ~1/pixels of its
-    scale (measured 2.7e-3 on the 6144-pixel test maps, 3 flips) -- the gate is then 2e-2; the arithmetic of each kernel
-    is gated at 2e-6 on flip-free operand-level tests (tests/test_conv_tc_gpu.py)."""
-    if flips:
-        tol = max(tol, 2e-2)
+    """Per-parameter gate against the fp64 oracle.  Biases of convs that feed a BatchNorm have an analytically zero
+    gradient (the BN removes the mean): both sides are pure round-off there, so those are gated against the block's
+    overall gradient scale instead of their own.
+    flips == 0: max-norm error <= tol on every parameter gradient.
+    flips > 0 (rel_up_to_relu_flips found ReLU-mask flips against the fp64 oracle in this run -- a pre-activation within
+    fp32 round-off of zero landing on the other side): ONE flipped bit adds / removes a single (pixel, channel) product
+    in the weight gradients that consume it -- up to max|activation| * max|gradient| on the ~3 C entries of that output
+    channel, 2.3 % of the largest entry in the measured case (profiles/r02/diag_block_s8.jsonl: conv3x1_2.weight, C = 128,
+    d = 16, one flip; the same block has 0 flips and 1e-6 errors in the other arithmetic mode) -- and shifts everything
+    behind the next BatchNorm by ~1/pixels through the batch statistics.  A wrong tap, stride or operand corrupts MOST
+    entries by O(1) instead.  So the gate becomes robust: at most 5 % of the entries beyond 1e-3 of the scale, median
+    error <= 1e-3 (a few flips / pixels); the arithmetic of every kernel is gated entry by entry at 2e-6 in the flip-free
+    operand-level tests (tests/test_conv_tc_gpu.py)."""
     gmax = max(float(q.grad.abs().max()) for q in oracle_P.values() if q.grad is not None)
     for n, p in block.named_parameters():
         ref = oracle_P[prefix + "." + n].grad
-        err = float((p.grad.double().cpu() - ref).abs().max())
+        d = (p.grad.double().cpu() - ref).abs()
+        err = float(d.max())
         if float(ref.abs().max()) < 1e-6 * gmax:
             assert err <= 1e-3 * gmax, (n, err, gmax)
-        else:
-            scale = max(float(ref.abs().max()), 1e-3 * gmax)
+            continue
+        scale = max(float(ref.abs().max()), 1e-3 * gmax)
+        if not flips:
             assert err <= tol * scale, (n, err, scale)
+        else:
+            assert float((d > 1e-3 * scale).double().mean()) <= 0.05, (n, float((d > 1e-3 * scale).double().mean()), flips)
+            assert float(d.median()) <= 1e-3 * scale, (n, float(d.median()) / scale, flips)
+            assert err <= 0.25 * scale, (n, err, scale)
 
 
 @pytest.mark.parametrize("cin,cout,H,W", [(3, 16, 32, 48), (16, 64, 16, 24), (64, 128, 8, 12)])
@@ -504,3 +514,52 @@ def test_projections_compute_coordinates_matches_reference_formulas():
     assert len(lanes) == B and len(lanes[0]) == 4 and len(lanes[0][0]) == 56
     assert all(v == -2 for v in lanes[0][1])            # line_pred[:, [1, 2, 0, 3]] = [1, 0, 1, 1]: lane 1 is switched off
     assert all(v == -2 for v in lanes[1][0][:8])        # horizon 240 -> the first (240 - 160) / 10 samples are cut
+
+
+def test_segmentation_branch_kernels():
+    """`--end_to_end False` (BP/Networks/LSQ_layer.py:279-293,301; BP/Loss_crit.py:64-65): lf_seg_lane_maps against the
+    reference's torch formulation, lf_ce2d against torch's weighted CrossEntropyLoss in float64 (value and gradient), and the
+    branch through Net.forward (end_to_end False: 3 class planes, maps fitted without gradient)."""
+    from lanedetection_end2end_b200 import _capi
+    from lanedetection_end2end_b200.Loss_crit import CrossEntropyLoss2d
+    g = torch.Generator().manual_seed(4)
+    B, L, H, W = 2, 4, 64, 96
+    out = torch.randn(B, L + 1, H, W, generator=g).cuda()
+    maps = torch.empty(B, L, H, W, device="cuda")
+    _capi.call("lf_seg_lane_maps", _capi.ptr(out), B, L + 1, H, W, L, 13, _capi.ptr(maps), _capi.stream_ptr())
+    labels = torch.max(out, 1)[1].float()
+    want = torch.stack([labels * (labels == (k + 1)).float() for k in range(L)], 1)
+    want[:, :, :13] = 0
+    assert torch.equal(maps, want)
+    gt = torch.randint(0, L + 1, (B, H, W), generator=g).cuda()
+    w = torch.tensor([1.0] + [2.5] * L).cuda()
+    x = out.clone().requires_grad_(True)
+    loss = CrossEntropyLoss2d(w)(x, gt)
+    (loss * 3.0).backward()
+    xd = out.double().cpu().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(xd, gt.cpu(), w.double().cpu())
+    (ref * 3.0).backward()
+    assert abs(float(loss) - float(ref)) <= 2e-6 * abs(float(ref))
+    assert rel(x.grad, xd.grad) <= 2e-6
+    # through the module: segmentation mode builds L+1 output planes
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    from lanedetection_end2end_b200.Networks.LSQ_layer import Net
+    args = define_args().parse_args(["--image_dir", "x", "--gt_dir", "y", "--nclasses", "2", "--order", "2", "--batch_size", "2",
+                                     "--end_to_end", "False"])
+    torch.manual_seed(0)
+    model = Net(args).cuda().train()
+    model.defer_status_check = True
+    xin = torch.from_numpy(inputs.make_images(2, 256, 512, seed=3)).cuda()
+    res = model(xin, torch.zeros(2, 4), False)
+    assert res[5].shape == (2, 3, 256, 512) and res[4].shape == (2, 2, 256, 512) and not res[4].requires_grad
+    lab = torch.max(res[5].detach(), 1)[1].float()
+    exp = torch.stack([lab * (lab == 1).float(), lab * (lab == 2).float()], 1)
+    exp[:, :, :77] = 0
+    assert torch.equal(res[4], exp)
+    gt2 = torch.randint(0, 3, (2, 256, 512), generator=g).cuda()
+    from lanedetection_end2end_b200.Loss_crit import define_loss_crit
+    args.loss_policy = "backproject"
+    _, crit_seg = define_loss_crit(args)
+    crit_seg(res[5], gt2).backward()
+    torch.cuda.synchronize()
+    assert model.net.decoder.output_conv.weight.grad is not None
