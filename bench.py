@@ -221,6 +221,63 @@ def cpu_reference_run(cfg, steps, warmup, sample_images):
             "ms_per_step": med * 1e3, "images_per_step": Bs}
 
 
+def gpu_stock_reference_run(cfg, steps, warmup, allow_tf32):
+    """Labelled extra ("library-kernel comparison point"): the reference's OWN modules, unmodified, on
+    the same B200 through stock PyTorch (cuDNN / cuBLAS / torch.inverse), `cudnn.benchmark = True` as BP/main.py:62 sets it,
+    with torch's default TF32 convolutions (allow_tf32 True: 1e-3-accurate) or strict fp32 (False).  Eager launches, the
+    way the reference runs.  None of this repo's kernels is on that path."""
+    import contextlib
+    import io
+    import torch
+    from oracle import reference_import as ri
+    ns = ri.import_reference("Backprojection_Loss")
+    L, order, R, B = cfg["nclasses"], cfg["order"], cfg["resize"], cfg["batch"]
+    args = ri.make_args(ns, ["--nclasses", str(L), "--order", str(order), "--batch_size", str(B), "--mask_percentage",
+                             str(cfg["mask"]), "--resize", str(R), "--loss_policy", "backproject", "--end_to_end", "True"], no_cuda=False)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = bool(allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    try:
+        torch.manual_seed(0)
+        model = ns.LSQ_layer.Net(args)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ns.utils.define_init_weights(model, "kaiming")
+        model = model.cuda().train()
+        crit = ns.Loss_crit.backprojection_loss(args)
+        g = torch.Generator().manual_seed(0)
+        x = torch.rand(B, 3, R, 2 * R, generator=g).cuda()
+        xgt = (torch.rand(B, 4, 56, generator=g, dtype=torch.float64) * 500.0).cuda()
+        valid = torch.ones(B, 4, 56, dtype=torch.float64)
+        valid[:, :, :8] = 0
+        valid = valid.cuda()
+        gt_line = torch.zeros(B, 4)
+
+        def one_step():
+            model.zero_grad()
+            out = model(x, gt_line, True)
+            loss = sum(crit(out[l], xgt[:, l], valid[:, l])[0] for l in range(L)) / L
+            loss.backward()
+
+        for _ in range(max(3, warmup)):
+            one_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+        ri.purge()
+    return {"value": B / ms * 1e3, "unit": "images/sec", "ms_per_step": ms, "steps": steps,
+            "what": "the reference's unmodified Networks.LSQ_layer.Net + backprojection_loss on this GPU through stock PyTorch %s "
+                    "(cuDNN convolutions %s, cudnn.benchmark, eager launches)" % (torch.__version__, "TF32 (torch default)" if allow_tf32 else "fp32"),
+            "accuracy": "convolutions in TF32: ~1e-3 from fp64 on beta (tests/test_tf32_emulation_cpu.py)" if allow_tf32 else "fp32"}
+
+
 def cpu_port_run(cfg, steps, warmup, sample_images):
     import torch
     from oracle import erfnet_oracle as eo, lsq_oracle as lo, inputs
@@ -491,6 +548,13 @@ def run_ours(a, cfg):
                                  "ms_per_step": pms / psteps, "steps": psteps, "inputs": "resident in HBM"}
             finally:
                 ops_net.set_conv_mode(a.conv_mode)
+        if cfg["resize"] == 256 and not cfg.get("clas"):
+            for tf32, label in ((True, "stock_pytorch_reference_gpu_tf32"), (False, "stock_pytorch_reference_gpu_fp32")):
+                try:
+                    extras[label] = gpu_stock_reference_run(cfg, max(3, a.steps // 2), 3, tf32)
+                except Exception as e:      # the reference's GPU path is not ours to fix: report why it did not run
+                    extras[label] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+                torch.cuda.empty_cache()
 
     # one traced step: CUDA events around every C-ABI launch on the launching stream
     table, roofline, roofline_lsq, roofline_kernels = None, None, None, None

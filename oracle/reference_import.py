@@ -103,7 +103,7 @@ def import_reference(variant="Backprojection_Loss"):
     return ns
 
 
-def make_args(ns, extra=()):
+def make_args(ns, extra=(), no_cuda=True):
     """argparse Namespace the reference's ``Net(args)`` consumes (utils.py:24-99)."""
-    argv = ["--image_dir", "x", "--gt_dir", "y", "--no_cuda"] + list(extra)
+    argv = ["--image_dir", "x", "--gt_dir", "y"] + (["--no_cuda"] if no_cuda else []) + list(extra)
     return ns.utils.define_args().parse_args(argv)

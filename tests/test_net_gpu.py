@@ -91,9 +91,10 @@ def check_grads(block, oracle_P, prefix, tol=TOL, flips=0):
     channel, 2.3 % of the largest entry in the measured case (profiles/r02/diag_block_s8.jsonl: conv3x1_2.weight, C = 128,
     d = 16, one flip; the same block has 0 flips and 1e-6 errors in the other arithmetic mode) -- and shifts everything
     behind the next BatchNorm by ~1/pixels through the batch statistics.  A wrong tap, stride or operand corrupts MOST
-    entries by O(1) instead.  So the gate becomes robust: at most 5 % of the entries beyond 1e-3 of the scale, median
-    error <= 1e-3 (a few flips / pixels); the arithmetic of every kernel is gated entry by entry at 2e-6 in the flip-free
-    operand-level tests (tests/test_conv_tc_gpu.py)."""
+    entries by O(1) instead.  So the gate becomes robust: at most 5 % of the entries beyond 1e-2 of the scale (measured
+    with one flip: 0.2-0.5 % on every entry behind the BatchNorm, 1.1 % / 2.3 % on the two gradients that consume the flipped
+    bit), median error <= 2e-3, nothing beyond 25 %; the arithmetic of every kernel is gated entry by entry at 2e-6 in the
+    flip-free operand-level tests (tests/test_conv_tc_gpu.py) and the whole path against the reference's goldens."""
     gmax = max(float(q.grad.abs().max()) for q in oracle_P.values() if q.grad is not None)
     for n, p in block.named_parameters():
         ref = oracle_P[prefix + "." + n].grad
@@ -106,8 +107,8 @@ def check_grads(block, oracle_P, prefix, tol=TOL, flips=0):
         if not flips:
             assert err <= tol * scale, (n, err, scale)
         else:
-            assert float((d > 1e-3 * scale).double().mean()) <= 0.05, (n, float((d > 1e-3 * scale).double().mean()), flips)
-            assert float(d.median()) <= 1e-3 * scale, (n, float(d.median()) / scale, flips)
+            assert float((d > 1e-2 * scale).double().mean()) <= 0.05, (n, float((d > 1e-2 * scale).double().mean()), flips)
+            assert float(d.median()) <= 2e-3 * scale, (n, float(d.median()) / scale, flips)
             assert err <= 0.25 * scale, (n, err, scale)
 
 
@@ -205,7 +206,7 @@ def _build_net(L, order, mask_pct, B):
     return golden_check.build_net(L, order, mask_pct, B)
 
 
-@pytest.mark.parametrize("name", ["net_l2_d2", "net_l4_d3"])
+@pytest.mark.parametrize("name", ["net_l2_d2", "net_l4_d3", "net_l2_d2_b32"])     # _b32: the BASELINE batch size of config 2
 def test_full_path_matches_reference_golden(name):
     """ERFNet -> activation -> mask -> LSQ -> backprojection loss, forward + backward, through the
     same calls the reference's main.py makes (BP/main.py:286-305,338-339), vs the golden outputs
