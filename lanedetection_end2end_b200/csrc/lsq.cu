@@ -440,12 +440,33 @@ __global__ void __launch_bounds__(LSQ_THREADS, LSQ_FWD_CTAS_PER_SM) lsq_fwd_rows
                     float o[V];
                     load_mapv<BF16>(a.o, off, o);
                     float sa = 0.f, sb = 0.f;
+                    if constexpr (ACT_T == LF_ACT_SQUARE) {
+                        // default activation: two pixels per instruction (FMUL2 / FADD2 / FFMA2) -- per 8 bf16 pixels 18
+                        // math instructions instead of 32; the bf16 forward was issue-bound (same time as fp32 for half
+                        // the bytes).  Each lane is rounded like the scalar op; only the order of the final two adds differs.
+                        f32x2_t sa2 = f2_pack(0.f, 0.f), sb2 = sa2;
 #pragma unroll
-                    for (int e = 0; e < V; ++e) {
-                        o[e] = act_fn<ACT_T>(o[e], a.act);
-                        const float w = o[e] * o[e];
-                        sa += w;
-                        sb = fmaf(w, x[e], sb);
+                        for (int e = 0; e < V; e += 2) {
+                            const f32x2_t o2 = f2_pack(o[e], o[e + 1]);
+                            const f32x2_t a2 = f2_mul(o2, o2);            // activation o^2
+                            const f32x2_t w2 = f2_mul(a2, a2);            // weight (o^2)^2
+                            sa2 = f2_add(sa2, w2);
+                            sb2 = f2_fma(w2, f2_pack(x[e], x[e + 1]), sb2);
+                            f2_unpack(a2, o[e], o[e + 1]);                // the activated values (`masked` output)
+                        }
+                        float s0, s1, t0, t1;
+                        f2_unpack(sa2, s0, s1);
+                        f2_unpack(sb2, t0, t1);
+                        sa = s0 + s1;
+                        sb = t0 + t1;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < V; ++e) {
+                            o[e] = act_fn<ACT_T>(o[e], a.act);
+                            const float w = o[e] * o[e];
+                            sa += w;
+                            sb = fmaf(w, x[e], sb);
+                        }
                     }
                     if (a.masked && l < nl && rvalid[u]) {
 #pragma unroll
@@ -611,9 +632,21 @@ __global__ void __launch_bounds__(LSQ_THREADS, 4) lsq_bwd_rowsep_kernel(const Ls
                 const size_t off = ((size_t)(b * a.L + min(l0 + l, a.L - 1)) * a.H) * a.W + rowoff + (size_t)V * cv;
                 float o[V], g[V];
                 load_mapv<BF16>(a.o, off, o);
+                if constexpr (ACT_T == LF_ACT_SQUARE) {
+                    // two pixels per instruction (see the forward kernel): g = o^3 * (((x - q_hi) - q_lo) * (2 s))
+                    const f32x2_t nqh = f2_pack(-qh[l], -qh[l]), nql = f2_pack(-ql[l], -ql[l]), s2 = f2_pack(2.f * sf[l], 2.f * sf[l]);
 #pragma unroll
-                for (int e = 0; e < V; ++e)
-                    g[e] = dact_times_act<ACT_T>(o[e], a.act) * (((x[e] - qh[l]) - ql[l]) * sf[l]);
+                    for (int e = 0; e < V; e += 2) {
+                        const f32x2_t o2 = f2_pack(o[e], o[e + 1]);
+                        const f32x2_t o3 = f2_mul(f2_mul(o2, o2), o2);
+                        const f32x2_t t = f2_mul(f2_add(f2_add(f2_pack(x[e], x[e + 1]), nqh), nql), s2);
+                        f2_unpack(f2_mul(o3, t), g[e], g[e + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < V; ++e)
+                        g[e] = dact_times_act<ACT_T>(o[e], a.act) * (((x[e] - qh[l]) - ql[l]) * sf[l]);
+                }
                 if (l < nl) store_mapv<BF16>(a.d_o, off, g);
             }
         }
