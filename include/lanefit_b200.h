@@ -291,6 +291,11 @@ int lf_bn_bwd_finalize_sx(const double* partial, int nblk, long long npix, int C
 int lf_bn_bwd_apply(const float* dy, const float* ymask, const float* drop, const float* x, long long npix,
                     int C, int pix_per_image, const float* mean, const float* invstd, const float* gamma,
                     const float* c1, const float* c2, float* dx, lf_stream_t stream);
+/* lf_bn_bwd_apply that also stores gated = dy * (ymask > 0): the skip connection's gradient of a residual block, added by
+ * the block's last input-gradient conv as one pre-masked operand (LfConvTcArgs.add_src without add_mask) */
+int lf_bn_bwd_apply_gated(const float* dy, const float* ymask, const float* drop, const float* x, long long npix, int C,
+                          int pix_per_image, const float* mean, const float* invstd, const float* gamma, const float* c1,
+                          const float* c2, float* dx, float* gated, lf_stream_t stream);
 
 /* Decoder.output_conv: ConvTranspose2d(16 -> L, 2, stride 2) (ERFNet.py:124,152).
  * x NHWC [N,H,W,Cin] -> out planar [N,L,2H,2W] (the layout the LSQ layer reads).

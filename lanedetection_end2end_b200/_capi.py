@@ -141,6 +141,7 @@ _NET_PROTOS = {
     "lf_bn_bwd_reduce": (_i, [_p, _p, _p, _p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p]),
     "lf_bn_bwd_finalize": (_i, [_p, _i, ctypes.c_longlong, _i, _p, _p, _p, _p, _p]),
     "lf_bn_bwd_apply": (_i, [_p, _p, _p, _p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "lf_bn_bwd_apply_gated": (_i, [_p, _p, _p, _p, ctypes.c_longlong, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "lf_outconv_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "lf_outconv_bwd_data": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "lf_outconv_wgrad_blocks": (_i, [ctypes.c_longlong]),

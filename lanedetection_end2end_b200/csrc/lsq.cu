@@ -440,33 +440,15 @@ __global__ void __launch_bounds__(LSQ_THREADS, LSQ_FWD_CTAS_PER_SM) lsq_fwd_rows
                     float o[V];
                     load_mapv<BF16>(a.o, off, o);
                     float sa = 0.f, sb = 0.f;
-                    if constexpr (ACT_T == LF_ACT_SQUARE) {
-                        // default activation: two pixels per instruction (FMUL2 / FADD2 / FFMA2) -- per 8 bf16 pixels 18
-                        // math instructions instead of 32; the bf16 forward was issue-bound (same time as fp32 for half
-                        // the bytes).  Each lane is rounded like the scalar op; only the order of the final two adds differs.
-                        f32x2_t sa2 = f2_pack(0.f, 0.f), sb2 = sa2;
+                    // (packed fp32 pairs -- FMUL2 / FADD2 / FFMA2 -- were tried here in round 2: fewer instructions but more live
+                    // registers; the forward got SLOWER at 128 registers / thread (bf16 L=4: 0.36 -> 0.31 of the copy bandwidth,
+                    // profiles/r02/lsq_stress_s10.jsonl).  The backward kernel keeps them: bit-identical there, +15 % on bf16.)
 #pragma unroll
-                        for (int e = 0; e < V; e += 2) {
-                            const f32x2_t o2 = f2_pack(o[e], o[e + 1]);
-                            const f32x2_t a2 = f2_mul(o2, o2);            // activation o^2
-                            const f32x2_t w2 = f2_mul(a2, a2);            // weight (o^2)^2
-                            sa2 = f2_add(sa2, w2);
-                            sb2 = f2_fma(w2, f2_pack(x[e], x[e + 1]), sb2);
-                            f2_unpack(a2, o[e], o[e + 1]);                // the activated values (`masked` output)
-                        }
-                        float s0, s1, t0, t1;
-                        f2_unpack(sa2, s0, s1);
-                        f2_unpack(sb2, t0, t1);
-                        sa = s0 + s1;
-                        sb = t0 + t1;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < V; ++e) {
-                            o[e] = act_fn<ACT_T>(o[e], a.act);
-                            const float w = o[e] * o[e];
-                            sa += w;
-                            sb = fmaf(w, x[e], sb);
-                        }
+                    for (int e = 0; e < V; ++e) {
+                        o[e] = act_fn<ACT_T>(o[e], a.act);
+                        const float w = o[e] * o[e];
+                        sa += w;
+                        sb = fmaf(w, x[e], sb);
                     }
                     if (a.masked && l < nl && rvalid[u]) {
 #pragma unroll

@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            long long n4, int C4, int pix_per_image,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ c1,
-                                                           const float* __restrict__ c2, float* __restrict__ dx) {
+                                                           const float* __restrict__ c2, float* __restrict__ dx,
+                                                           float* __restrict__ gated_out) {
     pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % C4);
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
             const float4 m = __ldg(reinterpret_cast<const float4*>(ymask) + i);
             g.x = gate(g.x, m.x); g.y = gate(g.y, m.y); g.z = gate(g.z, m.z); g.w = gate(g.w, m.w);
         }
+        if (gated_out) reinterpret_cast<float4*>(gated_out)[i] = g;   // dy * (ymask > 0): the residual branch's gradient
         if (drop) {
             const float4 d = __ldg(reinterpret_cast<const float4*>(drop) + (p / pix_per_image) * C4 + c4);
             g.x *= d.x; g.y *= d.y; g.z *= d.z; g.w *= d.w;
@@ -574,7 +576,23 @@ extern "C" int lf_bn_bwd_apply(const float* dy, const float* ymask, const float*
     if (rc) return rc;
     const long long n4 = npix * (C / 4);
     lf_launch(bn_bwd_apply_kernel, grid_for(n4, 256), 256, 0, stream, dy, ymask, drop, x, n4, C / 4, pix_per_image, mean, invstd,
-                                                              gamma, c1, c2, dx);
+                                                              gamma, c1, c2, dx, (float*)nullptr);
+    return check_launch();
+}
+
+// Same, and also stores gated = dy * (ymask > 0) (before the dropout factor): in a residual block that is the gradient of
+// the skip connection, which the block's last input-gradient conv then adds as ONE pre-masked operand instead of reading
+// dy and the mask tensor again in its epilogue (the two-operand residual epilogue was the slowest conv flavour).
+extern "C" int lf_bn_bwd_apply_gated(const float* dy, const float* ymask, const float* drop, const float* x, long long npix, int C,
+                                     int pix_per_image, const float* mean, const float* invstd, const float* gamma, const float* c1,
+                                     const float* c2, float* dx, float* gated, lf_stream_t stream_) {
+    STREAM;
+    LF_REQUIRE(dy && x && mean && invstd && gamma && c1 && c2 && dx && gated && pix_per_image > 0);
+    int rc = bn_check(npix, C);
+    if (rc) return rc;
+    const long long n4 = npix * (C / 4);
+    lf_launch(bn_bwd_apply_kernel, grid_for(n4, 256), 256, 0, stream, dy, ymask, drop, x, n4, C / 4, pix_per_image, mean, invstd,
+                                                              gamma, c1, c2, dx, gated);
     return check_launch();
 }
 

@@ -840,8 +840,12 @@ def bn_apply(x, s, relu, drop=None, res=None):
     return y
 
 
-def bn_backward(dy, ymask, drop, x, s, gamma):
-    """-> (dx, dgamma, dbeta).  g = dy*(ymask>0)*drop is recomputed on the fly."""
+PREMASK_RESIDUAL = os.environ.get("LANEFIT_PREMASK_RES", "1") != "0"
+
+
+def bn_backward(dy, ymask, drop, x, s, gamma, want_gated=False):
+    """-> (dx, dgamma, dbeta[, gated]).  g = dy*(ymask>0)*drop is recomputed on the fly; want_gated: also return
+    dy*(ymask>0), stored by the apply pass (lf_bn_bwd_apply_gated)."""
     h = _lib()
     C = x.shape[-1]
     npix = x.numel() // C
@@ -855,6 +859,11 @@ def bn_backward(dy, ymask, drop, x, s, gamma):
     dgamma, dbeta, c1, c2 = buf[0], buf[1], buf[2], buf[3]
     _capi.call("lf_bn_bwd_finalize", ptr(part), nblk, npix, C, ptr(dgamma), ptr(dbeta), ptr(c1), ptr(c2), st)
     dx = torch.empty_like(x)
+    if want_gated:
+        gated = torch.empty_like(x)
+        _capi.call("lf_bn_bwd_apply_gated", ptr(dy), ptr(ymask), ptr(drop), ptr(x), npix, C, ppi, ptr(s.mean), ptr(s.invstd),
+                   ptr(gamma), ptr(c1), ptr(c2), ptr(dx), ptr(gated), st, nbytes=4 * npix * C * (4 + (ymask is not None)))
+        return dx, dgamma, dbeta, gated
     _capi.call("lf_bn_bwd_apply", ptr(dy), ptr(ymask), ptr(drop), ptr(x), npix, C, ppi, ptr(s.mean), ptr(s.invstd),
                                   ptr(gamma), ptr(c1), ptr(c2), ptr(dx), st, nbytes=4 * npix * C * (3 + (ymask is not None)))
     return dx, dgamma, dbeta
@@ -1006,8 +1015,13 @@ class Nb1dFunction(torch.autograd.Function):
     @staticmethod
     def _backward_body(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1, s2, drop, dil, dy, jobs):
         N, H, W, C = x.shape
-        # y = relu(bn2(t5)*drop + x)
-        d5, dg2, dbe2 = bn_backward(dy, y, drop, t5, s2, g2)
+        # y = relu(bn2(t5)*drop + x).  The apply pass also emits gm = dy*(y>0), the gradient of the skip connection, so the
+        # block's last conv adds one pre-masked operand instead of reading dy and y again in its epilogue.
+        gm = None
+        if PREMASK_RESIDUAL and tc_mode():
+            d5, dg2, dbe2, gm = bn_backward(dy, y, drop, t5, s2, g2, want_gated=True)
+        else:
+            d5, dg2, dbe2 = bn_backward(dy, y, drop, t5, s2, g2)
         # Bias gradients.  conv1x3_1 / conv1x3_2 feed a BatchNorm: sum_pixels(BN backward output) == 0
         # identically (the reference's autograd returns pure round-off there), so db2 = db4 = 0.
         # conv3x1_1 / conv3x1_2 feed a ReLU: db = column sums of the masked input gradient, which the
@@ -1032,7 +1046,7 @@ class Nb1dFunction(torch.autograd.Function):
         d1 = conv3(d2, w2, False, 1, True, colsum=db1, mask_src=t1)
         # conv3x1_1, plus the residual branch: dx = dgrad + dy*(y>0)
         dw1, _ = wgrad3(x, d1, w1, True, 1, bias_grad="skip")
-        dx = conv3(d1, w1, True, 1, True, add_src=dy, add_mask=y)
+        dx = conv3(d1, w1, True, 1, True, add_src=gm) if gm is not None else conv3(d1, w1, True, 1, True, add_src=dy, add_mask=y)
         if jobs:
             flush_deferred_reductions(jobs)
         return (dx, dw1, db1, dw2, db2, dg1, dbe1, dw3, db3, dw4, db4, dg2, dbe2, None, None, None, None, None, None,

@@ -502,3 +502,30 @@ def test_x3_c16_super_pixel_layers(vertical):
     for i, (a, r) in enumerate(zip(res["tf32x3"], res["fp32"])):
         tol = 3e-6 if i < 2 else 1e-4
         assert float((a - r).abs().max()) <= tol * float(r.abs().max()), i
+
+
+def test_premasked_residual_gradient_is_bit_identical():
+    """lf_bn_bwd_apply_gated + single-operand residual add (ops_net.PREMASK_RESIDUAL) against the two-operand epilogue
+    (add_src = dy, add_mask = y): the same values are added, so every gradient of the block must be bit-identical."""
+    from lanedetection_end2end_b200.Networks import ERFNet
+    o = ops()
+    o.set_conv_mode("tf32x3")
+    for C, dil, H, W in ((64, 1, 64, 128), (128, 2, 32, 64)):
+        torch.manual_seed(1)
+        blk = ERFNet.non_bottleneck_1d(C, 0.3, dil).cuda().train()
+        blk.drop_mask_override = (torch.rand(2, C) >= 0.3).float() / 0.7
+        x = torch.randn(2, C, H, W, device="cuda")
+        gy = torch.randn(2, C, H, W, device="cuda")
+        res = {}
+        try:
+            for pre in (False, True):
+                o.PREMASK_RESIDUAL = pre
+                xi = x.clone().requires_grad_(True)
+                blk.zero_grad()
+                blk(xi).backward(gy)
+                torch.cuda.synchronize()
+                res[pre] = [xi.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
+        finally:
+            o.PREMASK_RESIDUAL = True
+        for a, b in zip(res[True], res[False]):
+            assert torch.equal(a, b)
