@@ -180,7 +180,7 @@ conv1d_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else {
         // ================= epilogue (warps 2..): conv_tc_common.cuh =================
-        tc_epilogue<Cfg::EPI_GROUPS, AHEAD, 64, 2, TC_BN, false>(a, stg, tmem_base, tfull, tempty, n_half, cta_m, m_stride);
+        tc_epilogue<Cfg::EPI_GROUPS, (AHEAD ? 2 : 0), 64, 2, TC_BN, false>(a, stg, tmem_base, tfull, tempty, n_half, cta_m, m_stride);
     }
     tc_fence_before();
     __syncthreads();

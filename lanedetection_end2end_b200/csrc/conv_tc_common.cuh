@@ -60,7 +60,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 //      sums of squares (bias gradient, BatchNorm statistics) and the output stores are fully coalesced 128-bit accesses.
 // The mask / residual operands of a tile are prefetched into registers BEFORE waiting for its accumulator (AHEAD: one
 // whole tile ahead), so their latency hides behind the MMAs.
-template <int EPI_GROUPS, bool AHEAD, int EPI_T0, int NBUF, int BUF_COLS, bool X3>
+template <int EPI_GROUPS, int AHEAD, int EPI_T0, int NBUF, int BUF_COLS, bool X3>
 __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
                                             int n_half, int cta_m, int m_stride) {
     constexpr int NH = 2 / EPI_GROUPS;      // 32-channel halves each group walks per tile
@@ -90,7 +90,9 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
             msh[hh] = __ldg(reinterpret_cast<const float4*>(a.mask_shift + n_half * TC_BN + 32 * (h_first + hh) + 4 * c4));
         }
     }
-    float4 nxt_a[AHEAD ? 8 : 1], nxt_m[AHEAD ? 8 : 1];  // operands of the next tile in flight
+    // AHEAD: 0 = operands fetched just before the accumulator wait; 1 = ONE operand (the ReLU mask, or a pre-masked residual
+    // gradient) a whole tile ahead; 2 = add_src and add_mask both a tile ahead (32 more registers)
+    float4 nxt_a[AHEAD ? 8 : 1], nxt_m[AHEAD == 2 ? 8 : 1];  // operands of the next tile in flight
     int it = 0;
     for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
         const int buf = it % NBUF;
@@ -113,7 +115,7 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
         // tile of epilogue work (the epilogue, not the tensor pipe, bounds these layers).  Two halves per
         // thread (one group): no registers for that; prefetch this tile's operands before waiting on the accumulator.
         float4 pre[NH][8];
-        if constexpr (NH == 1 && AHEAD) {
+        if constexpr (NH == 1 && AHEAD != 0) {
             if (pre_mask || pre_add) {
                 auto issue = [&](int mtn) {
                     const int tan = mtn % a.tiles_a;
@@ -127,17 +129,21 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
                         const int y = a.vertical ? pa : pb, x = a.vertical ? pb : pa;
                         const size_t off = ((size_t)(nn * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN + 32 * h_first + 4 * c4;
                         nxt_a[j] = __ldg(reinterpret_cast<const float4*>((pre_mask ? a.mask_src : a.add_src) + off));
-                        if (!pre_mask && a.add_mask) nxt_m[j] = __ldg(reinterpret_cast<const float4*>(a.add_mask + off));
+                        if constexpr (AHEAD == 2) {
+                            if (!pre_mask && a.add_mask) nxt_m[j] = __ldg(reinterpret_cast<const float4*>(a.add_mask + off));
+                        }
                     }
                 };
                 if (it == 0) issue(mt);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float4 v = nxt_a[j];
-                    if (!pre_mask && a.add_mask) {
-                        const float4 mk = nxt_m[j];
-                        v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
-                        v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+                    if constexpr (AHEAD == 2) {
+                        if (!pre_mask && a.add_mask) {
+                            const float4 mk = nxt_m[j];
+                            v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
+                            v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+                        }
                     }
                     pre[0][j] = v;
                 }

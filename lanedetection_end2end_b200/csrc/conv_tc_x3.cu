@@ -26,6 +26,8 @@
 //    sub-phase (4 slabs) before it is needed again and is re-read from L2 once per 4 tiles.
 // Warp roles: 0 = TMA producer (activation slabs + weight slot refills), 1 = MMA issuer (+TMEM alloc), 2.. = split warps,
 // then 8 epilogue warps; 12 warps in all (3 per SM sub-partition keeps the register cap at 168).
+#include <stdlib.h>
+
 #include "conv_tc_common.cuh"
 
 namespace lf {
@@ -46,7 +48,7 @@ __device__ __forceinline__ float x3_hw_tf32(float a) { return __uint_as_float(__
 __device__ __forceinline__ float x3_rna_tf32(float a) { return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ float x3_lo(float a) { return x3_rna_tf32(a - x3_hw_tf32(a)); }
 
-template <int C, bool AHEAD = false, int EG = 2>
+template <int C, int AHEAD = 0, int EG = 2>
 struct X3Cfg {
     static constexpr int NCB = C / TC_KCH;          // 32-channel blocks = slabs per tile
     // Two epilogue groups (one 32-channel half each) for every shape: at C = 128 the tiles of a group complete in a burst
@@ -62,7 +64,7 @@ struct X3Cfg {
     static constexpr bool BLOCK_MAJOR = C > 64;     // walk order inside a group of X3_NBUF tiles
 };
 
-template <int C, bool AHEAD, int EG>
+template <int C, int AHEAD, int EG>
 __global__ void __launch_bounds__(X3Cfg<C, AHEAD, EG>::THREADS, 1)
 conv1d_tc_x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     pdl_trigger();
@@ -378,7 +380,7 @@ static bool x3_make_plan(int N, int H, int W, int C, const int* dy, const int* d
     return tc_get_encode_fn() != nullptr;
 }
 
-template <int C, bool AHEAD, int EG>
+template <int C, int AHEAD, int EG>
 static cudaError_t x3_launch(int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                              const TcArgs& a) {
     cudaError_t e = cudaFuncSetAttribute(conv1d_tc_x3_kernel<C, AHEAD, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
@@ -412,8 +414,16 @@ extern "C" int lf_conv1d_tc_x3(const LfConvTcArgs* args, lf_stream_t stream_) {
     LF_REQUIRE(p.in && p.wpack && p.out);
     X3Plan pl;
     if (!x3_make_plan(p.N, p.H, p.W, p.C, p.dy, p.dx, &pl)) return LF_ERR_UNSUPPORTED;
-    // residual-add launches: operands one tile ahead (two epilogue groups only: one half per thread)
-    const bool ahead = p.add_src && !p.mask_src && pl.epi_groups == 2;
+    // Epilogue operands one tile ahead (two epilogue groups only: one half per thread): 2 = add_src + add_mask, 1 = a single
+    // operand -- the ReLU mask of a masked input gradient or a pre-masked residual gradient (round 2: the mask loads issued
+    // just before the accumulator wait were the top stall line of the masked launches in the ncu source view)
+    int ahead = 0;
+    if (pl.epi_groups == 2) {
+        if (p.add_src && p.add_mask && !p.mask_src) ahead = 2;
+        else if (p.mask_src || p.add_src) ahead = 1;
+    }
+    static const bool no_ahead1 = getenv("LANEFIT_X3_NOAHEAD1") != nullptr;   // A/B switch for the measurement of AHEAD = 1
+    if (no_ahead1 && ahead == 1 && !(p.add_src && !p.mask_src)) ahead = 0;
     TcEncodeTiledFn enc = tc_get_encode_fn();
     TcArgs a{};
     a.out = p.out; a.bias = p.bias; a.mask_src = p.mask_src; a.add_src = p.add_src; a.add_mask = p.add_mask;
@@ -460,12 +470,17 @@ extern "C" int lf_conv1d_tc_x3(const LfConvTcArgs* args, lf_stream_t stream_) {
     const int grid = pl.m_ctas * a.n_halves;
     cudaError_t e;
     if (pl.epi_groups == 1) {
-        e = p.C == 128 ? x3_launch<128, false, 1>(grid, pl.smem_bytes, stream, tmA, tmB, a)
-                       : x3_launch<64, false, 1>(grid, pl.smem_bytes, stream, tmA, tmB, a);
-    } else if (p.C == 128 && ahead) e = x3_launch<128, true, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a);
-    else if (p.C == 128) e = x3_launch<128, false, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a);
-    else if (ahead) e = x3_launch<64, true, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a);
-    else e = x3_launch<64, false, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a);
+        e = p.C == 128 ? x3_launch<128, 0, 1>(grid, pl.smem_bytes, stream, tmA, tmB, a)
+                       : x3_launch<64, 0, 1>(grid, pl.smem_bytes, stream, tmA, tmB, a);
+    } else if (p.C == 128) {
+        e = ahead == 2 ? x3_launch<128, 2, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a)
+          : ahead == 1 ? x3_launch<128, 1, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a)
+                       : x3_launch<128, 0, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a);
+    } else {
+        e = ahead == 2 ? x3_launch<64, 2, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a)
+          : ahead == 1 ? x3_launch<64, 1, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a)
+                       : x3_launch<64, 0, 2>(grid, pl.smem_bytes, stream, tmA, tmB, a);
+    }
     if (e != cudaSuccess) { set_last_cuda_error(e); return LF_ERR_CUDA; }
     return check_launch();
 }
