@@ -116,10 +116,12 @@ class backprojection_loss(nn.Module):
             self._c_den = Mi[2, 1] * yp + Mi[2, 2]
             self._dev = device
 
-    def forward_lanes(self, betas, x_gt, valid_samples):
+    def forward_lanes(self, betas, x_gt, valid_samples, lane_scale=None):
         """``mean_l forward(betas[l], x_gt[:, l], valid[:, l])[0]`` -- the lane loop of BP/main.py:297-305 -- evaluated for
         all lanes at once (same float64 arithmetic per element, a third of the launches).  betas: L tensors
-        [B, order+1, 1]; x_gt, valid_samples: [B, >=L, 56].  Returns (loss, x_cal * valid [B, L, 56])."""
+        [B, order+1, 1]; x_gt, valid_samples: [B, >=L, 56].  Returns (loss, x_cal * valid [B, L, 56]).
+        lane_scale ([L], optional): per-lane factors, e.g. ddp.lane_valid_scale (batch-global normaliser under data
+        parallelism)."""
         L = len(betas)
         self._to(betas[0].device)
         p = torch.stack([b.reshape(b.size(0), -1) for b in betas], 1).double()     # [B, L, n]
@@ -130,8 +132,10 @@ class backprojection_loss(nn.Module):
         x_err = (x_gt[:, :L] - x_cal) * v
         nvalid = v.sum(dim=(0, 2))                                                  # per lane, like the per-lane calls
         sq = (x_err ** 2).sum(dim=(0, 2))
-        loss = (sq / torch.where(nvalid == 0, torch.ones_like(nvalid), nvalid)).mean()
-        return loss, x_cal * v
+        lane = sq / torch.where(nvalid == 0, torch.ones_like(nvalid), nvalid)
+        if lane_scale is not None:
+            lane = lane * lane_scale.to(lane.dtype)
+        return lane.mean(), x_cal * v
 
     def _fused_host_constants(self):
         """(Y56 [56, n], y' [56], M^-1 [9]) as contiguous float64 numpy arrays for lf_backproj_loss."""
@@ -172,7 +176,7 @@ class _FusedBackprojLoss(torch.autograd.Function):
     """mean over lanes of backprojection_loss, forward + gradient in ONE launch (csrc/loss.cu: lf_backproj_loss)."""
 
     @staticmethod
-    def forward(ctx, beta, x_gt, valid, crit):
+    def forward(ctx, beta, x_gt, valid, crit, lane_scale=None):
         import ctypes
         if __package__:
             from . import _capi
@@ -189,6 +193,10 @@ class _FusedBackprojLoss(torch.autograd.Function):
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         _capi.call("lf_backproj_loss", host[0].ctypes.data, host[1].ctypes.data, host[2].ctypes.data, p(beta), p(x_gt), p(valid),
                    B, L, n, p(lane), p(loss), p(dbeta), p(xcal), p(ticket), _capi.stream_ptr())
+        if lane_scale is not None:      # per-lane factors (ddp.lane_valid_scale): the kernel's outputs are linear in them
+            ls = lane_scale.to(torch.float64)
+            loss = (lane * ls).mean().reshape(1)
+            dbeta = dbeta * ls.view(1, L, 1)
         ctx.save_for_backward(dbeta)
         ctx.mark_non_differentiable(xcal)
         return loss.reshape(()), xcal
@@ -196,16 +204,16 @@ class _FusedBackprojLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, _g_xcal):
         (dbeta,) = ctx.saved_tensors
-        return dbeta * g, None, None, None
+        return dbeta * g, None, None, None, None
 
 
-def fused_backprojection_loss(crit, betas, x_gt, valid):
+def fused_backprojection_loss(crit, betas, x_gt, valid, lane_scale=None):
     """``mean_l crit(betas[l], x_gt[:, l], valid[:, l])[0]`` (what BP/main.py:297-305 computes) in one launch.
     betas: sequence of L tensors [B, order+1, 1] float64 (Net.forward's beta0..3); x_gt, valid: [B, >=L, 56] float64.
     Returns (loss scalar, x_cal*valid [B, L, 56])."""
     L = len(betas)
     beta = torch.stack([b.reshape(b.shape[0], -1) for b in betas], 1).double().contiguous()      # [B, L, n]
-    return _FusedBackprojLoss.apply(beta, x_gt[:, :L].double().contiguous(), valid[:, :L].double().contiguous(), crit)
+    return _FusedBackprojLoss.apply(beta, x_gt[:, :L].double().contiguous(), valid[:, :L].double().contiguous(), crit, lane_scale)
 
 
 class Area_Loss(nn.Module):

@@ -70,3 +70,21 @@ def broadcast_parameters(module, src=0, group=None):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src, group=group)
+
+
+def lane_valid_scale(valid, nlanes, group=None):
+    """Per-lane factors that turn DDP's "mean of per-shard losses" into the reference's batch-global normaliser.
+
+    ``backprojection_loss`` divides the squared error of lane l by the number of valid samples of lane l in the WHOLE batch
+    (BP/Loss_crit.py:215).  With the batch sharded over R ranks each shard divides by its own count n_r; multiplying the
+    shard's lane loss by  f = R * n_r / sum_r n_r  (one all-reduce of `nlanes` scalars) makes the rank-mean of the losses --
+    and of every gradient, which the flat all-reduce averages -- identical to the single-process big-batch value
+    (SURVEY.md 8e "subtlety").  valid: [B, >= nlanes, 56]; returns float64 [nlanes] on valid's device.  Pass it as
+    ``lane_scale`` to Loss_crit.fused_backprojection_loss / backprojection_loss.forward_lanes."""
+    local = valid[:, :nlanes].double().sum(dim=(0, 2))
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return torch.ones_like(local)
+    total = local.clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    world = dist.get_world_size(group)
+    return torch.where(total == 0, torch.ones_like(total), world * local / torch.where(total == 0, torch.ones_like(total), total))

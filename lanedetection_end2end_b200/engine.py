@@ -22,8 +22,9 @@ FUSED_LOSS = os.environ.get("LANEFIT_FUSED_LOSS", "1") != "0"
 
 class GraphedTrainStep:
     def __init__(self, model, criterion, nclasses, example_x, example_xgt, example_valid, reducer=None, warmup=3,
-                 capture_error_mode="global", extra_loss=None):
+                 capture_error_mode="global", extra_loss=None, global_valid=False):
         self.model = model
+        self.global_valid = global_valid  # batch-global sum(valid) normaliser across ranks (ddp.lane_valid_scale)
         self.extra_loss = extra_loss      # callable(forward 9-tuple) -> scalar added to the loss (e.g. the --clas head losses)
         self.crit = criterion
         self.L = nclasses
@@ -60,11 +61,15 @@ class GraphedTrainStep:
         else:
             torch._foreach_zero_(self.grads)
         out = self.model(self.x, self.gt_line, True)
+        scale = None
+        if self.global_valid:
+            from .ddp import lane_valid_scale
+            scale = lane_valid_scale(self.valid, self.L)
         if FUSED_LOSS and hasattr(self.crit, "_fused_host_constants"):
             from .Loss_crit import fused_backprojection_loss
-            loss, _ = fused_backprojection_loss(self.crit, out[:self.L], self.xgt, self.valid)
+            loss, _ = fused_backprojection_loss(self.crit, out[:self.L], self.xgt, self.valid, lane_scale=scale)
         elif hasattr(self.crit, "forward_lanes"):
-            loss, _ = self.crit.forward_lanes(out[:self.L], self.xgt, self.valid)    # all lanes in one pass
+            loss, _ = self.crit.forward_lanes(out[:self.L], self.xgt, self.valid, lane_scale=scale)    # all lanes in one pass
         else:
             loss = 0
             for l in range(self.L):

@@ -81,3 +81,71 @@ def test_flat_gradient_allreduce_two_ranks():
         off += n
     # ... but the unused layer contributed zeros to the flat buffer (fixed layout on every rank)
     assert float(fa[off:].abs().sum()) == 0.0 and fa.numel() - off == 2 * 2 + 2
+
+
+def _worker_valid(rank, world, port, q):
+    import numpy as np
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lanedetection_end2end_b200.ddp import lane_valid_scale
+    from lanedetection_end2end_b200.Loss_crit import backprojection_loss
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    args = define_args().parse_args(["--image_dir", "x", "--gt_dir", "y", "--nclasses", "4", "--order", "3", "--no_cuda"])
+    crit = backprojection_loss(args)
+    beta, xgt, valid = _valid_shard(rank)
+    betas = [beta[:, l].unsqueeze(-1).clone().requires_grad_(True) for l in range(4)]
+    scale = lane_valid_scale(valid, 4)
+    loss, _ = crit.forward_lanes(betas, xgt, valid, lane_scale=scale)
+    loss.backward()
+    g = torch.stack([b.grad.squeeze(-1) for b in betas], 1)          # [B, L, n]
+    lt = loss.detach().clone().reshape(1)
+    dist.all_reduce(lt)                                                # what DDP does: mean over ranks
+    q.put((rank, float(lt) / world, (g / world).numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _valid_shard(rank):
+    """Shards with DIFFERENT numbers of valid samples per lane (lane 3 of rank 1 has none at all)."""
+    g = torch.Generator().manual_seed(7 + rank)
+    B = 3
+    beta = torch.randn(B, 4, 4, generator=g, dtype=torch.float64) * torch.tensor([1e-6, 1e-3, 0.5, 200.0], dtype=torch.float64)
+    xgt = torch.rand(B, 4, 56, generator=g, dtype=torch.float64) * 500
+    valid = (torch.rand(B, 4, 56, generator=g) > (0.3 + 0.4 * rank)).double()
+    if rank == 1:
+        valid[:, 3] = 0
+    return beta, xgt, valid
+
+
+def test_batch_global_valid_normaliser_two_ranks():
+    """ddp.lane_valid_scale: with it, the rank-mean of the per-shard losses and gradients equals the single-process value on
+    the concatenated batch (the reference's batch-global sum(valid), BP/Loss_crit.py:215)."""
+    import numpy as np
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_valid, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(2):
+        r, loss, g = q.get(timeout=120)
+        got[r] = (loss, g)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from lanedetection_end2end_b200.Loss_crit import backprojection_loss
+    from lanedetection_end2end_b200.Networks.utils import define_args
+    args = define_args().parse_args(["--image_dir", "x", "--gt_dir", "y", "--nclasses", "4", "--order", "3", "--no_cuda"])
+    crit = backprojection_loss(args)
+    shards = [_valid_shard(r) for r in range(2)]
+    beta = torch.cat([s[0] for s in shards]).requires_grad_(True)
+    xgt, valid = torch.cat([s[1] for s in shards]), torch.cat([s[2] for s in shards])
+    # the reference's own per-lane calls on the whole batch (BP/main.py:297-305)
+    loss = sum(crit(beta[:, l].unsqueeze(-1), xgt[:, l], valid[:, l])[0] for l in range(4)) / 4
+    loss.backward()
+    assert abs(got[0][0] - float(loss)) <= 1e-12 * abs(float(loss)) and abs(got[1][0] - float(loss)) <= 1e-12 * abs(float(loss))
+    want = beta.grad.numpy()
+    have = np.concatenate([got[0][1], got[1][1]])       # each rank holds the (already 1/world-averaged) gradient of ITS shard
+    np.testing.assert_allclose(have, want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
