@@ -271,3 +271,25 @@ def test_classification_heads_state_dict_and_no_cpu_fallback():
         assert m.conv1_bn.eps == 1e-5
         with pytest.raises(_capi.LanefitError):
             m(torch.zeros(1, 128, 32, 64))
+
+
+def test_tusimple_writer_and_lane_gating_host_logic():
+    """inference.lanes_from_predictions / write_tusimple_predictions (BP/test.py:66-99) are host logic: lanes switched off by
+    the line-type head, samples above the horizon and outside the frame become -2; one JSON line per image."""
+    import io
+    import json
+    import torch
+    from lanedetection_end2end_b200.inference import lanes_from_predictions, write_tusimple_predictions
+    x = torch.full((2, 4, 56), 100.0, dtype=torch.float64)
+    x[0, 0, 10] = 1500.0            # outside the 1280-wide frame
+    x[1, 2, 5] = -3.0
+    lanes = lanes_from_predictions(x, torch.tensor([[1., 1, 0, 1], [1., 1, 1, 1]]), torch.tensor([200, 160]))
+    assert lanes[0][0][10] == -2 and lanes[1][2][5] == -2
+    assert all(v == -2 for v in lanes[0][1])                 # head order [1, 2, 0, 3]: output lane 1 <- line_pred[:, 2] = 0 -> gated
+    assert lanes[0][0][:4] == [-2] * 4 and lanes[0][0][4] == 100    # horizon 200 -> the first (200 - 160) / 10 samples
+    assert lanes[1][0][0] == 100
+    buf = io.StringIO()
+    gt = [{"raw_file": "a.jpg", "h_samples": list(range(160, 720, 10))}, {"raw_file": "b.jpg", "h_samples": list(range(160, 720, 10))}]
+    write_tusimple_predictions(buf, gt, lanes, 0)
+    rows = [json.loads(l) for l in buf.getvalue().splitlines()]
+    assert len(rows) == 2 and rows[1]["raw_file"] == "b.jpg" and rows[0]["run_time"] == 20 and rows[0]["lanes"] == lanes[0]
