@@ -61,8 +61,10 @@ __global__ void __launch_bounds__(SEG_THREADS) ce2d_kernel(const float* __restri
 #pragma unroll
         for (int c = 0; c < SEG_MAXC; ++c)
             if (c < C) s += expf(v[c] - m);
-        const int t = (int)target[i];
-        const float w = weight ? __ldg(weight + t) : 1.f;
+        const long long tl = target[i];
+        const bool counted = tl >= 0 && tl < C;          // anything else (e.g. torch's ignore_index = -100) contributes nothing
+        const int t = counted ? (int)tl : 0;
+        const float w = counted ? (weight ? __ldg(weight + t) : 1.f) : 0.f;
         if (!GRAD) {
             float xt = 0.f;
 #pragma unroll
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(SEG_THREADS) ce2d_kernel(const float* __restri
             float* di = dx + (size_t)b * C * HW + p;
 #pragma unroll
             for (int c = 0; c < SEG_MAXC; ++c)
-                if (c < C) di[(size_t)c * HW] = gscale * w * (expf(v[c] - m) * inv - (c == t ? 1.f : 0.f));
+                if (c < C) di[(size_t)c * HW] = gscale * w * (expf(v[c] - m) * inv - ((counted && c == t) ? 1.f : 0.f));
         }
     }
     if (!GRAD) {
