@@ -293,3 +293,30 @@ def test_tusimple_writer_and_lane_gating_host_logic():
     write_tusimple_predictions(buf, gt, lanes, 0)
     rows = [json.loads(l) for l in buf.getvalue().splitlines()]
     assert len(rows) == 2 and rows[1]["raw_file"] == "b.jpg" and rows[0]["run_time"] == 20 and rows[0]["lanes"] == lanes[0]
+
+
+def test_eval_batchnorm_folding_algebra():
+    """ops_eval folds an eval-mode BatchNorm into the convolution that feeds it (w' = w * scale[co], b' = b * scale + shift;
+    ConvTranspose2d: scale along dim 1).  The algebra, checked with torch's own convolutions on the CPU (the kernels are
+    checked on the GPU by test_eval_fused_matches_unfused...)."""
+    import torch
+    import torch.nn.functional as F
+    from lanedetection_end2end_b200 import ops_eval
+    g = torch.Generator().manual_seed(0)
+    bn = torch.nn.BatchNorm2d(8, eps=1e-3).double().eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(8, generator=g, dtype=torch.float64))
+        bn.bias.copy_(torch.randn(8, generator=g, dtype=torch.float64))
+        bn.running_mean.copy_(torch.randn(8, generator=g, dtype=torch.float64))
+        bn.running_var.copy_(torch.rand(8, generator=g, dtype=torch.float64) + 0.5)
+    scale, shift = ops_eval.bn_affine(bn)
+    x = torch.randn(2, 5, 9, 11, generator=g, dtype=torch.float64)
+    w = torch.randn(8, 5, 3, 1, generator=g, dtype=torch.float64)
+    b = torch.randn(8, generator=g, dtype=torch.float64)
+    want = bn(F.conv2d(x, w, b, padding=(1, 0)))
+    got = F.conv2d(x, w * scale.view(-1, 1, 1, 1), b * scale + shift, padding=(1, 0))
+    assert float((got - want).abs().max()) < 1e-12
+    wt = torch.randn(5, 8, 3, 3, generator=g, dtype=torch.float64)          # ConvTranspose2d: [Cin, Cout, kh, kw]
+    want = bn(F.conv_transpose2d(x, wt, b, stride=2, padding=1, output_padding=1))
+    got = F.conv_transpose2d(x, wt * scale.view(1, -1, 1, 1), b * scale + shift, stride=2, padding=1, output_padding=1)
+    assert float((got - want).abs().max()) < 1e-12
