@@ -548,6 +548,26 @@ def run_ours(a, cfg):
                                  "ms_per_step": pms / psteps, "steps": psteps, "inputs": "resident in HBM"}
             finally:
                 ops_net.set_conv_mode(a.conv_mode)
+        # experiment: 3xTF32 forward / input gradients with single-pass TF32 weight gradients (ops_net.WGRAD_SINGLE_PASS)
+        ops_net.WGRAD_SINGLE_PASS = True
+        try:
+            psteps = max(3, a.steps // 2)
+            from lanedetection_end2end_b200.engine import GraphedTrainStep
+            pg = GraphedTrainStep(model, crit, L, dx, dxgt, dvalid, None, extra_loss=extra_loss) if a.graph else None
+            fn = (lambda: pg()) if pg is not None else (lambda: step(dx, dxgt, dvalid))
+            for _ in range(3):
+                fn()
+            pms = timed(fn, psteps)
+            del pg
+            extras["tf32x3_with_single_pass_tf32_weight_gradients"] = {
+                "value": world * B * psteps / (pms * 1e-3), "unit": "images/sec", "ms_per_step": pms / psteps, "steps": psteps,
+                "accuracy": "activations, beta, loss and input gradients as the default mode; PARAMETER gradients carry TF32 rounding "
+                            "noise (~5e-4 norm-wise): above the 1e-4 the north star names, so never the headline",
+                "inputs": "resident in HBM"}
+        except Exception as e:
+            extras["tf32x3_with_single_pass_tf32_weight_gradients"] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        finally:
+            ops_net.WGRAD_SINGLE_PASS = False
         if cfg["resize"] == 256 and not cfg.get("clas"):
             for tf32, label in ((True, "stock_pytorch_reference_gpu_tf32"), (False, "stock_pytorch_reference_gpu_fp32")):
                 try:

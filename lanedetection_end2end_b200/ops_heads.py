@@ -103,7 +103,7 @@ def _wgrad_tcg_dense(x, dy, taps):
         a.a[1] = a.a[0]
         a.b = o._tcg_view(dy, H, W, H * W * Co, W * Co, Co)
         a.partial, a.N, a.Hs, a.Ws, a.Ka, a.Nn, a.nblocks, a.nctas = partial.data_ptr(), N, H, W, Ci, Co, nblocks, nctas
-        a.precision = int(o.x3_mode())
+        a.precision = int(o.wgrad_x3())
         for i in range(nblocks):
             dyy, dxx = taps[t0 + i // per_tap]
             a.map[i], a.dy[i], a.dx[i], a.cblk[i] = 0, dyy, dxx, i % per_tap
