@@ -64,7 +64,7 @@ def run_full_path(name, tol=1e-4, enforce=True, golden_dir=GOLDEN):
     loss.backward()
     torch.cuda.synchronize()
 
-    rep = {"case": name, "act": (0.0, 0.0, ""), "grad": (0.0, 0.0, "")}
+    rep = {"case": name, "act": (0.0, 0.0, ""), "grad": (0.0, 0.0, ""), "grad_significant": (0.0, 0.0, "")}
 
     def check(ok, msg):
         if enforce:
@@ -103,6 +103,10 @@ def run_full_path(name, tol=1e-4, enforce=True, golden_dir=GOLDEN):
         e_ref = float(np.abs(g[k32 + "/val"] - g[k64 + "/val"]).max() / scale)
         if e_ours > rep["grad"][0]:
             rep["grad"] = (e_ours, e_ref, n)
+        # the same, restricted to gradients that are not analytically zero (conv biases in front of a training-mode
+        # BatchNorm are pure round-off on both sides: their "relative" error is O(1) for the reference as well)
+        if g[k64 + "/stat"][2] >= 1e-3 * gscale and e_ours > rep["grad_significant"][0]:
+            rep["grad_significant"] = (e_ours, e_ref, n)
         check(e_ours <= 4 * e_ref + 10 * tol, ("gradient", n, e_ours, e_ref))
     # BN running statistics after one step
     for n, b in model.named_buffers():
