@@ -14,7 +14,6 @@
 // Epilogue: + bias[co], ReLU, * (mask_src > 0) (ReLU backward), + add_src * (add_mask > 0)
 // (residual gradient), all optional.
 #include "lf_common.cuh"
-#include "lf_net.h"
 
 namespace lf {
 

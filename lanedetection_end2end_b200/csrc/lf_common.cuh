@@ -7,6 +7,9 @@
 
 namespace lf {
 
+using ConvArgs = LfConvArgs;      // internal names of the public argument structs
+using WgradArgs = LfWgradArgs;
+
 void set_last_cuda_error(cudaError_t e);
 
 inline int check_launch() {

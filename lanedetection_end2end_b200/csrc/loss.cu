@@ -14,7 +14,6 @@
 // STATUS: validated on CPU only (round 1 ran out of GPU budget); the module path keeps the torch implementation
 // unless LANEFIT_FUSED_LOSS=1.
 #include "lf_common.cuh"
-#include "lf_net.h"
 
 namespace lf {
 

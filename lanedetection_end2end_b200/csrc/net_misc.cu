@@ -5,7 +5,6 @@
 // Reference: BP/Networks/ERFNet.py:16-22 (pool/cat/bn/relu), :33,39,48-58 (bn, dropout,
 // residual), :102-107, :124,152 (output_conv).
 #include "lf_common.cuh"
-#include "lf_net.h"
 
 namespace lf {
 

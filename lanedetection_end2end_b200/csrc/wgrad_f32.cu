@@ -3,7 +3,6 @@
 // Replaces autograd's convolution_backward weight/bias paths for every Conv2d /
 // ConvTranspose2d of BP/Networks/ERFNet.py (:15,29-37,101).
 #include "lf_common.cuh"
-#include "lf_net.h"
 
 namespace lf {
 

@@ -19,7 +19,6 @@
 #include <cuda.h>
 
 #include "lf_common.cuh"
-#include "lf_net.h"
 #include "tc_ptx.cuh"
 
 namespace lf {
