@@ -564,3 +564,24 @@ def test_segmentation_branch_kernels():
     crit_seg(res[5], gt2).backward()
     torch.cuda.synchronize()
     assert model.net.decoder.output_conv.weight.grad is not None
+
+
+def test_graphed_inference_matches_eager_eval():
+    """engine.GraphedInference (eval forward as one CUDA-graph replay) returns exactly what the eager eval forward returns,
+    for successive batches."""
+    from lanedetection_end2end_b200.engine import GraphedInference
+    model, args = _build_net(2, 2, 0.3, 2)
+    sd = model.state_dict()
+    for k, v in inputs.make_erfnet_params(3, 2, seed=11).items():
+        sd[k] = torch.from_numpy(v)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    xs = [torch.from_numpy(inputs.make_images(2, 256, 512, seed=s)).cuda() for s in (9, 10)]
+    gi = GraphedInference(model, xs[0])
+    for x in (xs[1], xs[0]):
+        got = [t.clone() if torch.is_tensor(t) else t for t in gi.infer(x)]
+        gi.check()
+        with torch.no_grad():
+            want = model(x, torch.zeros(2, 4), True)
+        for a, b in zip(got, want):
+            assert (a is None and b is None) or torch.equal(a, b)

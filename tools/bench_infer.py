@@ -40,14 +40,9 @@ def main():
             l0 = _capi.LAUNCHES
             model(x, gt_line, True)
             launches = _capi.LAUNCHES - l0
-            g = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                model(x, gt_line, True)
-            torch.cuda.current_stream().wait_stream(side)
-            with torch.cuda.graph(g):
-                out = model(x, gt_line, True)
+            from lanedetection_end2end_b200.engine import GraphedInference
+            gi = GraphedInference(model, x)
+            g, out = gi.graph, gi.out
             for _ in range(3):
                 g.replay()
             torch.cuda.synchronize()
