@@ -169,10 +169,6 @@ typedef struct LfConvTcArgs {
     int dy[3], dx[3];
     int relu;                /* bit 0: ReLU on conv + bias (before mask / add_src); bit 1: ReLU after add_src -- the closing
                                 relu(conv + x) of an eval-mode block whose BatchNorm is folded into the weights */
-    void* relu_bits_out;            /* NULL, or [N][H][W][C/4] bytes: bit k of byte (pixel, c/4) = relu(conv + bias)[pixel][4*(c/4)+k] > 0
-                                       (needs relu bit 0): the ReLU mask at 1/16 of the bytes of the activation */
-    const void* mask_bits;          /* NULL (or instead of mask_src): such a byte tensor as the ReLU-backward mask of this launch --
-                                       the masked input gradient then reads 1 byte per 4 channels instead of 16 */
 } LfConvTcArgs;
 /* 0 = unsupported shape, else the number of CTA rows of colsum_partial */
 int lf_conv1d_tc_supported(int N, int H, int W, int C);

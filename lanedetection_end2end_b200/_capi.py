@@ -59,7 +59,7 @@ class LfConvArgs(ctypes.Structure):
 class LfConvTcArgs(ctypes.Structure):
     _fields_ = [("inp", _p), ("wpack", _p), ("bias", _p), ("out", _p), ("mask_src", _p), ("add_src", _p),
                 ("add_mask", _p), ("colsum_partial", _p), ("stats_partial", _p), ("mask_scale", _p), ("mask_shift", _p), ("N", _i), ("H", _i), ("W", _i), ("C", _i), ("dy", _i * 3),
-                ("dx", _i * 3), ("relu", _i), ("relu_bits_out", _p), ("mask_bits", _p)]
+                ("dx", _i * 3), ("relu", _i)]
 
 
 class LfWgradArgs(ctypes.Structure):

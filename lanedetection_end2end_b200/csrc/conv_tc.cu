@@ -283,9 +283,6 @@ extern "C" int lf_conv1d_tc(const LfConvTcArgs* args, lf_stream_t stream_) {
     a.stats_partial = p.stats_partial;
     a.mask_scale = p.mask_scale;
     a.mask_shift = p.mask_shift;
-    a.relu_bits_out = static_cast<uint8_t*>(p.relu_bits_out);
-    a.mask_bits = static_cast<const uint8_t*>(p.mask_bits);
-    LF_REQUIRE(!(p.mask_bits && p.mask_src) && (!p.relu_bits_out || (p.relu & 1)));
     LF_REQUIRE(!p.mask_scale || (p.mask_shift && p.mask_src && p.stats_partial));
     a.N = p.N; a.H = p.H; a.W = p.W; a.Ctot = p.C; a.relu = p.relu;
     a.vertical = pl.vertical; a.TA = pl.TA; a.TB = pl.TB; a.dil = pl.dil;

@@ -27,8 +27,6 @@ struct TcArgs {
     double* stats_partial;  // [gridDim.x / n_halves][2][Ctot] per-CTA sum and sum of squares (BatchNorm), or NULL
     const float* mask_scale;  // non-NULL (with mask_shift): mask_src is a PRE-activation x; the ReLU mask bit is
     const float* mask_shift;  // fma(x, scale[c], shift[c]) > 0 and the second statistic = sum out*x  (BatchNorm backward)
-    uint8_t* relu_bits_out;   // [pixels][C/4] bytes: the ReLU mask of this launch's output, 4 channels per byte (or NULL)
-    const uint8_t* mask_bits; // such a tensor as this launch's ReLU-backward mask (instead of mask_src)
     int N, H, W, Ctot;
     int vertical;           // conv axis: 1 = y (3x1), 0 = x (1x3)
     int TA, TB;             // tile extent along / across the conv axis (TA*TB = 128)
@@ -77,7 +75,6 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
     float* stg_g = stg + grp * (TC_STG_BYTES / 4);
     const int bar_id = 1 + grp;
     const bool pre_mask = a.mask_src != nullptr;
-    const bool bit_mask = a.mask_bits != nullptr;     // byte masks: 1 byte per float4 instead of 16
     const bool pre_add = (a.add_src != nullptr) && !pre_mask;  // both given: add_src is read in the loop
     float4 csum[NH], csq[NH];               // running column sums / sums of squares, per channel half
     float4 msc[NH], msh[NH];                // BatchNorm scale / shift of this thread's columns (mask_scale mode)
@@ -95,7 +92,6 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
     // AHEAD: 0 = operands fetched just before the accumulator wait; 1 = ONE operand (the ReLU mask, or a pre-masked residual
     // gradient) a whole tile ahead; 2 = add_src and add_mask both a tile ahead (32 more registers)
     float4 nxt_a[AHEAD ? 8 : 1], nxt_m[AHEAD == 2 ? 8 : 1];  // operands of the next tile in flight
-    uint8_t nxt_b[AHEAD ? 8 : 1];                             // ... or its byte mask
     int it = 0;
     for (int mt = cta_m; mt < a.total_m_tiles; mt += m_stride, ++it) {
         const int buf = it % NBUF;
@@ -118,28 +114,7 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
         // tile of epilogue work (the epilogue, not the tensor pipe, bounds these layers).  Two halves per
         // thread (one group): no registers for that; prefetch this tile's operands before waiting on the accumulator.
         float4 pre[NH][8];
-        uint8_t preb[NH][8];
         if constexpr (NH == 1 && AHEAD != 0) {
-            if (bit_mask) {
-                auto issue_b = [&](int mtn) {
-                    const int tan = mtn % a.tiles_a;
-                    const int tbn = (mtn / a.tiles_a) % a.tiles_b;
-                    const int nn = mtn / (a.tiles_a * a.tiles_b);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int r = r0 + 16 * j;
-                        const int ap = r >> tb_shift, bp = r & (a.TB - 1);
-                        const int pa = tan * a.TA + ap, pb = tbn * a.TB + bp;
-                        const int y = a.vertical ? pa : pb, x = a.vertical ? pb : pa;
-                        const size_t off = ((size_t)(nn * a.H + y) * a.W + x) * a.Ctot + n_half * TC_BN + 32 * h_first + 4 * c4;
-                        nxt_b[j] = __ldg(a.mask_bits + (off >> 2));
-                    }
-                };
-                if (it == 0) issue_b(mt);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) preb[0][j] = nxt_b[j];
-                if (mt + m_stride < a.total_m_tiles) issue_b(mt + m_stride);
-            }
             if (pre_mask || pre_add) {
                 auto issue = [&](int mtn) {
                     const int tan = mtn % a.tiles_a;
@@ -173,11 +148,6 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
                 }
                 if (mt + m_stride < a.total_m_tiles) issue(mt + m_stride);
             }
-        } else if (bit_mask) {
-#pragma unroll
-            for (int hh = 0; hh < NH; ++hh)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) preb[hh][j] = __ldg(a.mask_bits + ((roff[j] + 32 * hh) >> 2));
         } else if (pre_mask || pre_add) {
 #pragma unroll
             for (int hh = 0; hh < NH; ++hh)
@@ -240,12 +210,6 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, float* stg, uint32_
                 o.x += bsv[hh].x; o.y += bsv[hh].y; o.z += bsv[hh].z; o.w += bsv[hh].w;
                 if (a.relu & 1) {
                     o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                    if (a.relu_bits_out)
-                        a.relu_bits_out[off >> 2] = (uint8_t)((o.x > 0.f ? 1 : 0) | (o.y > 0.f ? 2 : 0) | (o.z > 0.f ? 4 : 0) | (o.w > 0.f ? 8 : 0));
-                }
-                if (bit_mask) {
-                    const unsigned b = preb[hh][j];
-                    o.x = (b & 1u) ? o.x : 0.f; o.y = (b & 2u) ? o.y : 0.f; o.z = (b & 4u) ? o.z : 0.f; o.w = (b & 8u) ? o.w : 0.f;
                 }
                 if (pre_mask) {
                     float4 mk = pre[hh][j];

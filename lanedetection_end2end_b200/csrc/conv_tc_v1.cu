@@ -294,7 +294,6 @@ int lf_conv1d_tc_v1(const LfConvTcArgs* args, lf_stream_t stream_) {
     const LfConvTcArgs& p = *args;
     LF_REQUIRE(p.in && p.wpack && p.out);
     if (p.stats_partial || p.mask_scale) return LF_ERR_UNSUPPORTED;  // BN-statistics epilogue exists in the slab kernel only
-    if (p.mask_bits || p.relu_bits_out) return LF_ERR_UNSUPPORTED;   // byte masks: slab / 3xTF32 kernels only
     if (!(p.C == 64 || p.C == 128)) return LF_ERR_UNSUPPORTED;
     TcArgsV1 a{};
     if (!pick_patch_v1(p.H, p.W, &a.bx, &a.by)) return LF_ERR_UNSUPPORTED;

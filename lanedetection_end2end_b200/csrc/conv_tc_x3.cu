@@ -420,7 +420,7 @@ extern "C" int lf_conv1d_tc_x3(const LfConvTcArgs* args, lf_stream_t stream_) {
     int ahead = 0;
     if (pl.epi_groups == 2) {
         if (p.add_src && p.add_mask && !p.mask_src) ahead = 2;
-        else if (p.mask_src || p.add_src || p.mask_bits) ahead = 1;
+        else if (p.mask_src || p.add_src) ahead = 1;
     }
     static const bool no_ahead1 = getenv("LANEFIT_X3_NOAHEAD1") != nullptr;   // A/B switch for the measurement of AHEAD = 1
     if (no_ahead1 && ahead == 1 && !(p.add_src && !p.mask_src)) ahead = 0;
@@ -431,9 +431,6 @@ extern "C" int lf_conv1d_tc_x3(const LfConvTcArgs* args, lf_stream_t stream_) {
     a.stats_partial = p.stats_partial;
     a.mask_scale = p.mask_scale;
     a.mask_shift = p.mask_shift;
-    a.relu_bits_out = static_cast<uint8_t*>(p.relu_bits_out);
-    a.mask_bits = static_cast<const uint8_t*>(p.mask_bits);
-    LF_REQUIRE(!(p.mask_bits && p.mask_src) && (!p.relu_bits_out || (p.relu & 1)));
     LF_REQUIRE(!p.mask_scale || (p.mask_shift && p.mask_src && p.stats_partial));
     a.N = p.N; a.H = p.H; a.W = p.W; a.Ctot = p.C; a.relu = p.relu;
     a.vertical = pl.vertical; a.TA = pl.TA; a.TB = pl.TB; a.tb_shift = pl.tb_shift; a.dil = pl.dil;

@@ -576,7 +576,7 @@ def _taps_axis(taps):
 
 
 def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_src=None, add_mask=None, colsum=None,
-                mask_affine=None, stats_partial=None, relu_bits=None, mask_bits=None):
+                mask_affine=None, stats_partial=None):
     """3-tap convolution on tcgen05.  taps: [(dy, dx)] * 3 in weight-slot order.  colsum: optional [C]
     tensor receiving the column sums of `out` (bias gradient), accumulated in the kernel's epilogue."""
     N, H, W, C = x.shape
@@ -593,19 +593,15 @@ def run_conv_tc(taps, x, wpack, out, bias=None, relu=False, mask_src=None, add_s
         a.colsum_partial = part.data_ptr()
     if stats_partial is not None:
         a.stats_partial = stats_partial.data_ptr()
-    if relu_bits is not None:          # uint8 [N,H,W,C/4] OUT: the ReLU mask of this launch's output, 4 channels per byte
-        a.relu_bits_out = relu_bits.data_ptr()
-    if mask_bits is not None:          # such a tensor IN, as this launch's ReLU-backward mask (instead of mask_src)
-        a.mask_bits = mask_bits.data_ptr()
     if mask_affine is not None:        # (scale, shift): mask_src is a BatchNorm INPUT, the mask bit is fma(x, scale, shift) > 0
         a.mask_scale, a.mask_shift = mask_affine[0].data_ptr(), mask_affine[1].data_ptr()
     a.N, a.H, a.W, a.C = N, H, W, C
     for t, (dy, dx) in enumerate(taps):
         a.dy[t], a.dx[t] = dy, dx
     a.relu = int(relu)
-    n_operands = 2 + (mask_src is not None) + (add_src is not None) + (add_mask is not None) + ((relu_bits is not None) + (mask_bits is not None)) / 16.0
+    n_operands = 2 + (mask_src is not None) + (add_src is not None) + (add_mask is not None)
     _capi.call("lf_conv1d_tc_x3" if x3_mode() else "lf_conv1d_tc", ctypes.byref(a), _stream(), flops=2 * N * H * W * 3 * C * C,
-               nbytes=int(4 * n_operands * N * H * W * C))
+               nbytes=4 * n_operands * N * H * W * C)
     if part is not None:
         if _DEFERRED is not None:
             _reduce(part, rows, 1, 1, C, 1, C, colsum, 0, 0, 1)
@@ -653,7 +649,7 @@ def conv3(x, w, vertical, dil, transposed, colsum=None, wp=None, **epi):
         xs = x.view(N, H, W // SUPER, SUPER * C)
         sgn = -1 if transposed else 1
         taps = [((sgn * (k - 1), 0) if vertical else (0, sgn * (k - 1))) for k in range(3)]
-        epi_s = {k: (v.view(N, H, W // SUPER, -1) if (torch.is_tensor(v) and v.dim() == 4) else v) for k, v in epi.items()}
+        epi_s = {k: (v.view(N, H, W // SUPER, SUPER * C) if (torch.is_tensor(v) and v.dim() == 4) else v) for k, v in epi.items()}
         if epi_s.get("bias") is not None:
             epi_s["bias"] = epi_s["bias"].repeat(SUPER)
         cs = torch.empty(SUPER * C, dtype=torch.float32, device=x.device) if colsum is not None else None
@@ -993,46 +989,26 @@ class DownFunction(torch.autograd.Function):
 # --------------------------------------------------------------------------------------
 # non_bottleneck_1d  (ERFNet.py:25-60)
 # --------------------------------------------------------------------------------------
-# ReLU masks of t1 / t4 as byte tensors (4 channels per byte), written by the forward conv's epilogue and read by the masked
-# input-gradient launch instead of the fp32 activation: 1/16 of the mask bytes (3xTF32 kernels only; bit-identical results)
-RELU_BYTE_MASKS = os.environ.get("LANEFIT_RELU_BITS", "1") != "0"
-
-
-def _byte_masks_ok(x, dil):
-    """Both the convs that produce t1 / t4 (vertical, d = 1 / dil) and the input gradients that consume their masks
-    (horizontal, d = 1 / dil) run on the 3xTF32 kernel (directly or as the C = 16 super-pixel view)?"""
-    if not (RELU_BYTE_MASKS and x3_mode()):
-        return False
-    if super_ok(x, 1) and dil == 1:
-        return True
-    return all(tc_supported(x, v, d) for v in (True, False) for d in (1, dil))
-
-
 class Nb1dFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, g1, be1, w3, b3, w4, b4, g2, be2, rm1, rv1, rm2, rv2, dil, drop, training):
         _capi.require_cuda(x)
         N, H, W, C = x.shape
-        bits = _byte_masks_ok(x, dil) and training
-        m1 = torch.empty(N, H, W, C // 4, dtype=torch.uint8, device=x.device) if bits else None
-        m4 = torch.empty(N, H, W, C // 4, dtype=torch.uint8, device=x.device) if bits else None
-        t1 = conv3(x, w1, True, 1, False, bias=b1, relu=True, **({"relu_bits": m1} if bits else {}))
+        t1 = conv3(x, w1, True, 1, False, bias=b1, relu=True)
         t2, s1 = conv3_bn_stats(t1, w2, False, 1, b2, g1, be1, rm1, rv1, training)
         t3 = bn_apply(t2, s1, relu=True)
-        t4 = conv3(t3, w3, True, dil, False, bias=b3, relu=True, **({"relu_bits": m4} if bits else {}))
+        t4 = conv3(t3, w3, True, dil, False, bias=b3, relu=True)
         t5, s2 = conv3_bn_stats(t4, w4, False, dil, b4, g2, be2, rm2, rv2, training)
         y = bn_apply(t5, s2, relu=True, drop=drop, res=x)
-        empty = x.new_empty(0)
         ctx.save_for_backward(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1.mean, s1.invstd, s2.mean, s2.invstd,
-                              drop if drop is not None else empty, s1.scale, s1.shift,
-                              m1 if bits else empty, m4 if bits else empty)
-        ctx.cfg = (dil, training, drop is not None, bits)
+                              drop if drop is not None else x.new_empty(0), s1.scale, s1.shift)
+        ctx.cfg = (dil, training, drop is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, m1, is1, m2, is2, drop, sc1, sh1, bm1, bm4) = ctx.saved_tensors
-        dil, training, has_drop, bits = ctx.cfg
+        (x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, m1, is1, m2, is2, drop, sc1, sh1) = ctx.saved_tensors
+        dil, training, has_drop = ctx.cfg
         _require_training_for_backward(training)
         drop = drop if has_drop else None
         dy = dy.contiguous()
@@ -1044,13 +1020,12 @@ class Nb1dFunction(torch.autograd.Function):
         global _DEFERRED
         _DEFERRED = jobs = []
         try:
-            return Nb1dFunction._backward_body(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1, s2, drop, dil, dy, jobs,
-                                               (bm1, bm4) if bits else None)
+            return Nb1dFunction._backward_body(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1, s2, drop, dil, dy, jobs)
         finally:
             _DEFERRED = None
 
     @staticmethod
-    def _backward_body(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1, s2, drop, dil, dy, jobs, byte_masks=None):
+    def _backward_body(x, t1, t2, t3, t4, t5, y, w1, w2, w3, w4, g1, g2, s1, s2, drop, dil, dy, jobs):
         N, H, W, C = x.shape
         # y = relu(bn2(t5)*drop + x).  The apply pass also emits gm = dy*(y>0), the gradient of the skip connection, so the
         # block's last conv adds one pre-masked operand instead of reading dy and y again in its epilogue.
@@ -1068,8 +1043,7 @@ class Nb1dFunction(torch.autograd.Function):
         db1, db3 = _empty((C,), x), _empty((C,), x)
         # conv1x3_2 (dilated)
         dw4, _ = wgrad3(t4, d5, w4, False, dil, bias_grad="skip")
-        d4 = (conv3(d5, w4, False, dil, True, colsum=db3, mask_bits=byte_masks[1]) if byte_masks is not None
-              else conv3(d5, w4, False, dil, True, colsum=db3, mask_src=t4))
+        d4 = conv3(d5, w4, False, dil, True, colsum=db3, mask_src=t4)
         # conv3x1_2 (dilated)
         dw3, _ = wgrad3(t3, d4, w3, True, dil, bias_grad="skip")
         fused = dgrad_relu_bn_fused(d4, w3, True, dil, t2, s1, g1)
@@ -1081,8 +1055,7 @@ class Nb1dFunction(torch.autograd.Function):
             d2, dg1, dbe1 = bn_backward(d3, None, None, t2, s1, g1)
         # conv1x3_1
         dw2, _ = wgrad3(t1, d2, w2, False, 1, bias_grad="skip")
-        d1 = (conv3(d2, w2, False, 1, True, colsum=db1, mask_bits=byte_masks[0]) if byte_masks is not None
-              else conv3(d2, w2, False, 1, True, colsum=db1, mask_src=t1))
+        d1 = conv3(d2, w2, False, 1, True, colsum=db1, mask_src=t1)
         # conv3x1_1, plus the residual branch: dx = dgrad + dy*(y>0)
         dw1, _ = wgrad3(x, d1, w1, True, 1, bias_grad="skip")
         dx = conv3(d1, w1, True, 1, True, add_src=gm) if gm is not None else conv3(d1, w1, True, 1, True, add_src=dy, add_mask=y)

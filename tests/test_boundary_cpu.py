@@ -47,7 +47,7 @@ def test_ctypes_struct_layout_matches_header():
             decl = decl.strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(float|int|double|long long|void|LfTcgView)\s*\*?", "", decl)
+            decl = re.sub(r"^(const\s+)?(float|int|double|long long|LfTcgView)\s*\*?", "", decl)
             for part in decl.split(","):
                 names.append(re.sub(r"\[.*\]", "", part.replace("*", "")).strip())
         mine = [f[0] for f in cls._fields_]

@@ -529,30 +529,3 @@ def test_premasked_residual_gradient_is_bit_identical():
             o.PREMASK_RESIDUAL = True
         for a, b in zip(res[True], res[False]):
             assert torch.equal(a, b)
-
-
-def test_relu_byte_masks_are_bit_identical():
-    """ops_net.RELU_BYTE_MASKS: the forward convs emit the ReLU mask of t1 / t4 as 1 byte per 4 channels and the masked input
-    gradients read that instead of the fp32 activation -- same mask bits, so every gradient must be bit-identical
-    (C = 64, C = 128 dilated, and the C = 16 super-pixel view)."""
-    from lanedetection_end2end_b200.Networks import ERFNet
-    o = ops()
-    o.set_conv_mode("tf32x3")
-    for C, dil, H, W in ((64, 1, 64, 128), (128, 4, 32, 64), (16, 1, 128, 256)):
-        torch.manual_seed(2)
-        blk = ERFNet.non_bottleneck_1d(C, 0.0, dil).cuda().train()
-        x = torch.randn(2, C, H, W, device="cuda")
-        gy = torch.randn(2, C, H, W, device="cuda")
-        res = {}
-        try:
-            for bits in (False, True):
-                o.RELU_BYTE_MASKS = bits
-                xi = x.clone().requires_grad_(True)
-                blk.zero_grad()
-                blk(xi).backward(gy)
-                torch.cuda.synchronize()
-                res[bits] = [xi.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
-        finally:
-            o.RELU_BYTE_MASKS = True
-        for a, b in zip(res[True], res[False]):
-            assert torch.equal(a, b), C
