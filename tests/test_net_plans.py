@@ -408,3 +408,78 @@ def test_tcg_weight_gradients_match_torch(monkeypatch):
         F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), w, stride=2, padding=1, output_padding=1).backward(
             du.permute(0, 3, 1, 2).double())
         assert torch.allclose(dw.double(), w.grad, atol=1e-4, rtol=1e-5), (I, O)
+
+
+def test_heads_dense_conv_forms_match_torch(monkeypatch):
+    """ops_heads: the Classification heads' 1x1 / 3x3 stride-1 convolutions, their input gradients and weight gradients are
+    expressed as run-time-tap launches of lf_conv_tcg / lf_wgrad_tcg (tap lists, packed operands, split launches, the final
+    view / permute).  Run that host code on the CPU with the two kernels replaced by literal restatements of their contracts
+    and compare with torch's own convolutions and autograd."""
+    import torch.nn.functional as F
+    from lanedetection_end2end_b200 import ops_net as o, ops_heads as hd, _capi
+    live = []
+
+    class FakeLib:
+        @staticmethod
+        def lf_conv_tcg_supported(N, H, W, Kc, Ng):
+            return 1
+
+        @staticmethod
+        def lf_wgrad_tcg_ctas(N, Hs, Ws, Ka, Nn, nblocks):
+            return 3 if ((nblocks + 3) // 4) * Nn <= 512 else 0
+
+    def fake_call(name, *args, **kw):
+        if name == "lf_conv_tcg":
+            _emulate_conv_tcg(args[0]._obj, live)
+        elif name == "lf_wgrad_tcg":
+            _emulate_wgrad_tcg(args[0]._obj, live)
+        elif name == "lf_wgrad_reduce":
+            partial, nsplit, ntaps, cp, cq, cpp, cqp, dst, st_, sp, sq, _stream = args
+            src = next(t for t in live if t.data_ptr() == partial)
+            red = src.view(nsplit, cp, cq).double().sum(0).float()
+            res = next(t for t in live if t.data_ptr() <= dst < t.data_ptr() + t.numel() * 4)
+            off = (dst - res.data_ptr()) // 4
+            res.reshape(-1)[off:off + cp * cq] = red.reshape(-1)
+        else:
+            raise AssertionError(name)
+
+    real_empty = torch.empty
+
+    def tracking_empty(*a_, **kw):
+        t = real_empty(*a_, **kw)
+        live.append(t)
+        return t
+
+    monkeypatch.setattr(o, "_stream", lambda: None)
+    monkeypatch.setattr(o, "_lib", lambda: FakeLib)
+    monkeypatch.setattr(_capi, "lib", lambda: FakeLib)
+    monkeypatch.setattr(hd, "ptr", lambda t: t.data_ptr() if t is not None else None)
+    monkeypatch.setattr(_capi, "call", fake_call)
+    monkeypatch.setattr(o, "CONV_MODE", "tf32")            # single operands (the hi/lo split is a pure re-encoding of the same matrix)
+    monkeypatch.setattr(torch, "empty", tracking_empty)
+    g = torch.Generator().manual_seed(3)
+    for (Ci, Co, k, H, W) in [(128, 128, 1, 4, 32), (128, 64, 3, 8, 16), (64, 64, 3, 4, 32)]:
+        N = 2
+        x = torch.randn(N, H, W, Ci, generator=g)
+        w = torch.randn(Co, Ci, k, k, generator=g) * 0.1
+        b = torch.randn(Co, generator=g)
+        live[:] = [x, b]
+        monkeypatch.setattr(o, "packed", lambda w_, kind, fn, split=False: _keep(live, fn(w_)))
+        y = hd.conv_fwd(x, w, b)
+        ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=(k - 1) // 2).permute(0, 2, 3, 1)
+        assert torch.allclose(y.double(), ref, atol=1e-5), ("fwd", Ci, Co, k)
+        dy = torch.randn(N, H, W, Co, generator=g)
+        live.append(dy)
+        dx = hd.conv_dgrad(dy, w)
+        xin = x.permute(0, 3, 1, 2).double().requires_grad_(True)
+        wd = w.double().requires_grad_(True)
+        F.conv2d(xin, wd, padding=(k - 1) // 2).backward(dy.permute(0, 3, 1, 2).double())
+        assert torch.allclose(dx.double(), xin.grad.permute(0, 2, 3, 1), atol=1e-5), ("dgrad", Ci, Co, k)
+        dw = hd.conv_wgrad(x, dy, w)
+        assert dw.shape == w.shape and torch.allclose(dw.double(), wd.grad, atol=1e-4, rtol=1e-5), ("wgrad", Ci, Co, k)
+
+
+def _keep(live, t):
+    """Register a freshly packed operand so that the emulators can resolve its pointer."""
+    live.append(t)
+    return t
