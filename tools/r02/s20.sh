@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, session 17: final tree -- full GPU suite + smoke (final tree)
+# round 2, session 20: full GPU suite + smoke on the then-final tree
 set -x
 mkdir -p gpurun_out/r02
 O=gpurun_out/r02
