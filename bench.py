@@ -503,8 +503,7 @@ def run_ours(a, cfg):
         v = float(loss.item())                    # D2H read of the step's result
         st = int(model.lsq_status.item())
         if st:
-            raise RuntimeError("status word %d (1 singular / 2 non-finite / 4 not positive definite normal matrix, "
-                               "8 zero BatchNorm weight in the fused backward)" % st)
+            raise RuntimeError("status word %d (1 singular / 2 non-finite / 4 not positive definite normal matrix)" % st)
         return v
 
     sampler = ClockSampler(local) if rank == 0 else None
