@@ -715,7 +715,7 @@ def main():
                     choices=["fp32", "tf32", "tf32x3"],
                     help="tf32x3 = tcgen05 with 3xTF32 operand splits (fp32-grade, default); tf32 = single-pass TF32 on tcgen05 "
                          "(labelled extra, 1e-3 accuracy); fp32 = CUDA-core FFMA kernels")
-    ap.add_argument("--max-seconds", dest="max_seconds", type=int, default=int(os.environ.get("LANEFIT_BENCH_MAX_SECONDS", "600")),
+    ap.add_argument("--max-seconds", dest="max_seconds", type=int, default=int(os.environ.get("LANEFIT_BENCH_MAX_SECONDS", "900")),
                     help="wall-clock watchdog: abort (exit 3, stacks on stderr) instead of hanging the box")
     a = ap.parse_args()
     if a.max_seconds > 0:
